@@ -1,0 +1,168 @@
+/*
+ * b200mix — C ABI of the B200-native (sm_100a) hot path that replaces, for PaddleMIX's denoiser-forward /
+ * ViT+LLM attention path, the arithmetic the reference delegates to paddlepaddle-gpu and to its Triton custom ops.
+ *
+ * Conventions (mirrors the ownership model of the reference's custom ops, paddlemix/triton_ops/triton_ops.py:641-693:
+ * inputs are borrowed raw device pointers, work is enqueued on the caller's stream, no hidden synchronisation):
+ *   - every pointer is a DEVICE pointer unless the name says host; the caller owns all buffers;
+ *   - activations are bf16 row-major, images are NHWC ([B,H,W,C], the reference's data_format="NHWC" switch,
+ *     ppdiffusers/models/unet_2d_condition.py:227,881-882); biases / modulation vectors / statistics are fp32;
+ *   - Linear weights are [N_out, K_in] with K contiguous (torch layout; Paddle's [in,out] nn.Linear.weight,
+ *     ppdiffusers/models/modeling_pytorch_paddle_utils.py:27-63, is transposed once at load by the Python shim);
+ *     conv3x3 weights are [C_out, kh, kw, C_in];
+ *   - every function returns 0 on success or a negative b200mix_status and never aborts;
+ *     b200mix_last_error() returns a thread-local message for the last failure;
+ *   - `stream` is a cudaStream_t passed as void*.
+ * There is no CPU fallback: every entry point fails with B200MIX_ERR_NO_DEVICE when no sm_100 device is present.
+ */
+#ifndef B200MIX_H_
+#define B200MIX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b200mix_status {
+  B200MIX_OK = 0,
+  B200MIX_ERR_INVALID = -1,   /* bad shape / alignment / argument */
+  B200MIX_ERR_CUDA = -2,      /* a CUDA runtime/driver call failed */
+  B200MIX_ERR_NO_DEVICE = -3, /* no sm_100 device visible */
+  B200MIX_ERR_UNSUPPORTED = -4
+} b200mix_status;
+
+enum { B200MIX_ACT_NONE = 0, B200MIX_ACT_SILU = 1, B200MIX_ACT_GELU_ERF = 2, B200MIX_ACT_GELU_TANH = 3, B200MIX_ACT_QUICK_GELU = 4 };
+enum { B200MIX_GLU_NONE = 0, B200MIX_GLU_GEGLU = 1, B200MIX_GLU_SWIGLU = 2 };
+
+/* Fused GEMM epilogue, applied in this order on the fp32 accumulator of element (m, n):
+ *   v = acc + bias[n] + row_add[(m / rows_per_group) * ld_row + n]
+ *   v = act(v)
+ *   glu != 0: columns are interleaved (2j = value, 2j+1 = gate); out[m, j] = value * gelu_erf(gate)   (GEGLU,
+ *             ppdiffusers/models/activations.py:83-104) or silu(gate) * value (SwiGLU, modeling_qwen2_vl.py:492-493);
+ *             the output then has N/2 columns
+ *   v = v * row_gate[(m / rows_per_group) * ld_row + n]          (AdaLN-Zero gate, attention.py:196-214)
+ *   v = (v + residual[m * ldr + n]) * out_scale                  (ResnetBlock2D output_scale_factor, resnet.py:806)
+ */
+typedef struct b200mix_epilogue {
+  const float* bias;      /* [N] or NULL */
+  const float* row_add;   /* [groups, ld_row] or NULL */
+  const float* row_gate;  /* [groups, ld_row] or NULL */
+  int64_t ld_row;
+  int64_t rows_per_group; /* rows of the output sharing one row_add/row_gate row (H*W or sequence length) */
+  const void* residual;   /* bf16 [M, ldr] or NULL */
+  int64_t ldr;
+  int32_t act;            /* B200MIX_ACT_* */
+  int32_t glu;            /* B200MIX_GLU_* */
+  int32_t out_fp32;       /* 0: bf16 output, 1: fp32 output */
+  float out_scale;        /* 1.0f for none */
+} b200mix_epilogue;
+
+const char* b200mix_last_error(void);
+const char* b200mix_version(void);
+/* Select the device for the calling thread and verify it is sm_100. Replaces paddle.set_device / the implicit
+ * place of paddle::Tensor in the reference ops. */
+int b200mix_init(int device);
+int b200mix_num_sms(void);
+
+/* ---- dense contractions on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> fused epilogue) ------- */
+
+/* C[M, N(/2 if glu)] = epilogue(A[M,K] @ W[N,K]^T). Replaces F.linear (ppdiffusers/models/lora.py:453-459) and
+ * 1x1 conv on NHWC (lora.py:365-377). A, W bf16; lda/ldw/ldc in elements, multiples of 8. */
+int b200mix_linear(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M, int64_t N,
+                   int64_t K, const b200mix_epilogue* epi, void* stream);
+
+/* y[B,Ho,Wo,Cout] = epilogue(conv3x3(x[B,H,W,Cin], w[Cout,3,3,Cin], padding 1, stride 1|2)). Implicit GEMM without
+ * im2col: each of the 9 taps is a shifted TMA box load with hardware zero fill at the borders.
+ * Replaces F.conv2d in ResnetBlock2D / Downsample2D / Upsample2D / conv_out (resnet.py:271-294,169-218,728-808).
+ * Cin must be a multiple of 64 (conv_in with Cin=4 is b200mix_conv3x3_small_cin). */
+int b200mix_conv3x3(const void* x, const void* w, void* y, int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                    int32_t stride, const b200mix_epilogue* epi, void* stream);
+
+/* conv3x3 stride 1 pad 1 for tiny Cin (UNet conv_in, unet_2d_condition.py:1064): x fp32 or bf16 NHWC [B,H,W,Cin],
+ * w bf16 [Cout,3,3,Cin], bias fp32, y bf16 NHWC. CUDA-core kernel (K = 9*Cin = 36 is below one MMA k-block). */
+int b200mix_conv3x3_small_cin(const void* x, int32_t x_fp32, const void* w, const float* bias, void* y, int64_t B,
+                              int64_t H, int64_t W, int64_t Cin, int64_t Cout, void* stream);
+
+/* Scaled dot-product attention, flash-style on tcgen05 (S=QK^T and O+=PV in TMEM, online softmax in registers).
+ * Semantics = the `math` branch of scaled_dot_product_attention_ (ppdiffusers/patches/paddle_patch.py:445-461):
+ * softmax(q k^T * scale [+ causal mask]) v. q/k/v/o are bf16 with head_dim contiguous; strides in elements for
+ * (batch, seq, head). D in {64, 128}; heads with other sizes are zero-padded by the shim at weight-load time.
+ * Hq % Hkv == 0 (GQA, modeling_qwen2_vl.py:497-506). cu_seqlens (int32 device [nseq+1], may be NULL) switches on the
+ * varlen block-diagonal mode of the Qwen2-VL ViT (modeling_qwen2_vl.py:354-381): then B must be 1 and both q and k
+ * are packed along seq. kv_len (<= Sk) masks the key tail (cross-attention with 77 text tokens). */
+int b200mix_sdpa(const void* q, const void* k, const void* v, void* o, int64_t B, int64_t Hq, int64_t Hkv, int64_t Sq,
+                 int64_t Sk, int64_t D, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t k_sb, int64_t k_ss,
+                 int64_t k_sh, int64_t v_sb, int64_t v_ss, int64_t v_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh,
+                 float scale, int32_t causal, const int32_t* cu_seqlens, int32_t nseq, void* stream);
+
+/* ---- HBM-bound normalisation / modulation kernels (coalesced 16-byte accesses, fp32 statistics) -------------- */
+
+/* GroupNorm (+ optional SiLU) over NHWC bf16; the input may be the channel-concatenation [x1 | x2] of two tensors
+ * (skip connections, unet_2d_blocks.py:2353-2356) which is thereby never materialised. x2 may be NULL (C2 = 0).
+ * Replaces nn.GroupNorm + nonlinearity (resnet.py:667-692,760-786; transformer_2d.py:161; unet_2d_condition.py:1193).
+ * y bf16 [B,H,W,C1+C2]. Two launches: statistics, then apply. `stats` = scratch of B*groups*16 bytes (two doubles per
+ * (batch, group), zeroed by the call). */
+int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2, int64_t C2, const float* gamma,
+                           const float* beta, void* y, void* stats, int64_t B, int64_t HW, int32_t groups, float eps,
+                           int32_t silu, void* stream);
+
+/* Row-wise LayerNorm family. For each row m of x[M,N] (bf16):
+ *   r = x + gate[g]*delta (if delta given; also written to resid_out)            (fused_adaLN_scale_residual,
+ *   y = LN(r) [*weight + bias] [*(1 + scale[g]) + shift[g]]                       triton_ops.py:702-755,981-1027)
+ * with g = m / rows_per_group; gate/scale/shift fp32 [groups, ld_mod]. rms != 0 switches to RMSNorm
+ * (x * rsqrt(mean(x^2)+eps) * weight, modeling_qwen2_vl.py:467-478). */
+int b200mix_layernorm(const void* x, const void* delta, const float* gate, void* resid_out, void* y,
+                      const float* weight, const float* bias, const float* scale, const float* shift, int64_t ld_mod,
+                      int64_t rows_per_group, int64_t M, int64_t N, float eps, int32_t rms, void* stream);
+
+/* ---- small elementwise kernels ------------------------------------------------------------------------------ */
+
+/* Sinusoidal timestep embedding, fp32 math (embeddings.py:26-64): out[b, :] for t[b]; flip_sin_to_cos, shift, scale
+ * as in the reference; out bf16 or fp32 [B, ld_out] written at column offset col0. */
+int b200mix_timestep_embedding(const float* t, void* out, int32_t out_fp32, int64_t B, int64_t dim, int64_t ld_out,
+                               int64_t col0, int32_t flip_sin_to_cos, float downscale_freq_shift, float scale,
+                               float max_period, void* stream);
+
+/* y = act(x) elementwise for bf16/fp32 vectors (SiLU on temb, resnet.py:772-776). */
+int b200mix_activation(const void* x, void* y, int64_t n, int32_t act, int32_t x_fp32, int32_t y_fp32, void* stream);
+
+/* Nearest-neighbour x2 upsample NHWC bf16 (F.interpolate(scale_factor=2, mode="nearest"), resnet.py:197-199). */
+int b200mix_upsample_nearest2x_nhwc(const void* x, void* y, int64_t B, int64_t H, int64_t W, int64_t C, void* stream);
+
+/* Channel concat of two NHWC bf16 tensors (unet_2d_blocks.py:2353-2356), for the 1x1 shortcut input. */
+int b200mix_concat_channels(const void* x1, int64_t C1, const void* x2, int64_t C2, void* y, int64_t rows,
+                            void* stream);
+
+/* Layout/dtype conversion: NCHW fp32|bf16 -> NHWC bf16 and back (pipelines hand NCHW latents to unet.forward). */
+int b200mix_nchw_to_nhwc(const void* x, int32_t x_fp32, void* y, int64_t B, int64_t C, int64_t H, int64_t W,
+                         void* stream);
+int b200mix_nhwc_to_nchw(const void* x, void* y, int32_t y_fp32, int64_t B, int64_t C, int64_t H, int64_t W,
+                         void* stream);
+
+/* Fused classifier-free-guidance combine + DDIM step (eta = 0, epsilon prediction), fp32 state:
+ *   eps = eps_u + g*(eps_c - eps_u)  (pipeline_stable_diffusion.py:882-884; eps_c NULL => eps = eps_u)
+ *   x0 = (x - sqrt_beta_t*eps) / sqrt_alpha_t ; x_prev = sqrt_alpha_prev*x0 + sqrt_beta_prev*eps
+ * The four scalars are computed on the host by the scheduler, bit-exactly as scheduling_ddim.py:410-457 does, and
+ * applied here with the same operation order in fp32. eps inputs bf16 or fp32 (eps_fp32). */
+int b200mix_ddim_step(const void* eps_u, const void* eps_c, int32_t eps_fp32, float guidance, const float* x,
+                      float* x_prev, int64_t n, float sqrt_alpha_t, float sqrt_beta_t, float sqrt_alpha_prev,
+                      float sqrt_beta_prev, void* stream);
+
+/* FlowMatchEuler step (scheduling_flow_match_euler_discrete.py:244-275): x_prev = x + dt * v, fp32 state. */
+int b200mix_euler_step(const void* v_u, const void* v_c, int32_t v_fp32, float guidance, const float* x, float* x_prev,
+                       int64_t n, float dt, void* stream);
+
+/* fp32 <-> bf16 casts (round-to-nearest-even). */
+int b200mix_cast(const void* x, void* y, int64_t n, int32_t x_fp32, int32_t y_fp32, void* stream);
+
+/* Rotary embedding applied in place on x (token stride ld_tok, head stride ld_head, first D dims of each head
+ * rotated; bf16, rotate_half convention, fp32 math) with per-token cos/sin fp32 [T, D] (apply_rotary_pos_emb_vision, modeling_qwen2_vl.py:227-238; M-RoPE tables are gathered on the
+ * host side by the shim exactly as apply_multimodal_rotary_pos_emb :179-224 does). */
+int b200mix_rope_inplace(void* x, int64_t T, int64_t H, int64_t D, int64_t ld_tok, int64_t ld_head, const float* cos,
+                         const float* sin, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MIX_H_ */

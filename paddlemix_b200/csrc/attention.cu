@@ -1,0 +1,414 @@
+// Flash-style scaled-dot-product attention on tcgen05 tensor cores.
+//
+// One CTA = one 128-row query tile of one (batch, head). 192 threads:
+//   warp 0     TMA producer: Q once, then K/V tiles through a shared-memory ring (128B swizzle)
+//   warp 1     TMEM owner + MMA issuer: S[j&1] = Q K_j^T (K-major x K-major), O += P_j V_j (P K-major from smem,
+//              V consumed in its natural [kv, d] layout as an MN-major B operand)
+//   warps 2-5  softmax: one query row per thread (TMEM lane == row, so row max / row sum need no shuffles),
+//              online softmax in fp32 with exp2, lazy rescale of the TMEM-resident O accumulator (only when the
+//              running max grows by more than 2^8), P written as bf16 into swizzled smem for the second MMA.
+// QK^T of tile j+1 is issued before softmax(j) finishes, so tensor cores and MUFU overlap.
+//
+// Semantics follow the reference's `math` SDPA (ppdiffusers/patches/paddle_patch.py:445-461): softmax(q k^T * scale
+// [+ causal]) v, [B,S,H,D] in / out; GQA per modeling_qwen2_vl.py:497-506; varlen block-diagonal per :354-381.
+#include <algorithm>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+struct AttnParams {
+  int Hq, Hkv, Sq, Sk;
+  float scale_log2;
+  int causal;
+  const int* cu;
+  int nseq;
+  int q_pos[3], k_pos[3], v_pos[3];  // tensor-map coordinate slot (1..3) of (seq, head, batch)
+  __nv_bfloat16* o;
+  long long o_sb, o_ss, o_sh;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tma_load_rows(void* dst, const CUtensorMap* m, uint64_t* bar, const int (&pos)[3], int d0,
+                                              int s0, int h, int b) {
+  int c[4];
+  c[0] = d0;
+  c[pos[0]] = s0;
+  c[pos[1]] = h;
+  c[pos[2]] = b;
+  tma_load_4d(dst, m, bar, c[0], c[1], c[2], c[3]);
+}
+
+template <int D>
+__global__ void __launch_bounds__(192, 1)
+    attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
+  constexpr int DC = D / 64;               // 64-wide head-dim chunks (one 128B swizzle atom each)
+  constexpr int TILE_BYTES = 128 * D * 2;  // one 128-row tile of Q / K / V
+  constexpr int KS = (D == 64) ? 3 : 2;    // K/V ring depth
+  constexpr int P_BYTES = 128 * 128 * 2;
+  constexpr uint32_t TM_S = 0, TM_O = 256;
+
+  // ---- which tile am I? (uniform across the CTA) ----
+  int qt = blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  int q_begin, q_end, kv_begin, kv_end, q_rel0, causal_off;
+  if (p.cu) {
+    int i = 0;
+    bool found = false;
+    for (; i < p.nseq; ++i) {
+      const int len = p.cu[i + 1] - p.cu[i];
+      const int nt = (len + 127) >> 7;
+      if (qt < nt) {
+        found = true;
+        break;
+      }
+      qt -= nt;
+    }
+    if (!found) return;
+    q_begin = p.cu[i] + qt * 128;
+    q_end = p.cu[i + 1];
+    kv_begin = p.cu[i];
+    kv_end = p.cu[i + 1];
+    q_rel0 = qt * 128;
+    causal_off = 0;
+  } else {
+    q_begin = qt * 128;
+    q_end = p.Sq;
+    kv_begin = 0;
+    kv_end = p.Sk;
+    q_rel0 = q_begin;
+    causal_off = p.Sk - p.Sq;
+  }
+  const int kv_len = kv_end - kv_begin;
+  int n_kv = kv_len;
+  if (p.causal) n_kv = min(kv_len, q_rel0 + 128 + causal_off);
+  const int n_tiles = (n_kv + 127) >> 7;
+  const int hk = h / (p.Hq / p.Hkv);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;
+  uint8_t* sV = sK + KS * TILE_BYTES;
+  uint8_t* sP = sV + KS * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // KS
+  uint64_t* k_empty = k_full + KS;    // KS
+  uint64_t* v_full = k_empty + KS;    // KS
+  uint64_t* v_empty = v_full + KS;    // KS
+  uint64_t* s_full = v_empty + KS;    // 2
+  uint64_t* p_full = s_full + 2;      // 1
+  uint64_t* pv_done = p_full + 1;     // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KS; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      mbar_expect_tx(q_full, TILE_BYTES);
+#pragma unroll
+      for (int dc = 0; dc < DC; ++dc) tma_load_rows(sQ + dc * 16384, &tmQ, q_full, p.q_pos, dc * 64, q_begin, h, b);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        const int row0 = kv_begin + j * 128;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], TILE_BYTES);
+#pragma unroll
+        for (int dc = 0; dc < DC; ++dc)
+          tma_load_rows(sK + st * TILE_BYTES + dc * 16384, &tmK, &k_full[st], p.k_pos, dc * 64, row0, hk, b);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], TILE_BYTES);
+#pragma unroll
+        for (int dc = 0; dc < DC; ++dc)
+          tma_load_rows(sV + st * TILE_BYTES + dc * 16384, &tmV, &v_full[st], p.v_pos, dc * 64, row0, hk, b);
+        if (++st == KS) st = 0, ph ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);  // B (= V) is MN-major
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      auto issue_qk = [&](int j, int st) {
+        const uint32_t k_addr = smem_u32(sK + st * TILE_BYTES);
+        const uint32_t d_tmem = tmem_base + TM_S + (j & 1) * 128;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+          umma_bf16_ss(d_tmem, make_smem_desc_sw128(q_addr + off, 16, 1024),
+                       make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, k != 0 ? 1u : 0u);
+        }
+      };
+      mbar_wait(q_full, 0);
+      int kst = 0;
+      uint32_t kph = 0;  // K ring position of the NEXT QK^T to issue
+      int vst = 0;
+      uint32_t vph = 0;  // V ring position of the next PV
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      umma_commit(&k_empty[0]);
+      umma_commit(&s_full[0]);
+      if (++kst == KS) kst = 0, kph ^= 1;
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) {
+          mbar_wait(&k_full[kst], kph);
+          tc_fence_after();
+          issue_qk(j + 1, kst);
+          umma_commit(&k_empty[kst]);
+          umma_commit(&s_full[(j + 1) & 1]);
+          if (++kst == KS) kst = 0, kph ^= 1;
+        }
+        mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[vst], vph);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sV + vst * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t ad = make_smem_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc_sw128(v_addr + k * 2048, 16384, 1024);
+          umma_bf16_ss(tmem_base + TM_O, ad, bd, idesc_pv, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&v_empty[vst]);
+        umma_commit(pv_done);
+        if (++vst == KS) vst = 0, vph ^= 1;
+      }
+    }
+  } else {
+    // ===== softmax warps: one query row per thread =====
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+    const int row_limit_base = p.causal ? (q_rel0 + row + causal_off + 1) : kv_len;
+    float m = -INFINITY, l = 0.0f;
+    uint8_t* p_row = sP + row * 128;
+    const int sw = row & 7;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(lane_base + TM_S + (j & 1) * 128 + c * 32, sv[c]);
+      tmem_wait_ld();
+
+      const int limit = min(kv_len, row_limit_base) - j * 128;  // columns [0, limit) of this tile are visible
+      float mx = -INFINITY;
+      if (limit >= 128) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float s = (c * 32 + i < limit) ? __uint_as_float(sv[c][i]) : -INFINITY;
+            sv[c][i] = __float_as_uint(s);
+            mx = fmaxf(mx, s);
+          }
+      }
+      const float m_cand = fmaxf(m, mx);
+      const bool grow = (m_cand - m) * p.scale_log2 > 8.0f;  // also true for the first finite tile (m = -inf)
+      float alpha = 1.0f;
+      if (grow) {
+        alpha = fast_exp2((m - m_cand) * p.scale_log2);
+        m = m_cand;
+        l *= alpha;
+      }
+      const float m_scaled = (m == -INFINITY) ? 0.0f : m * p.scale_log2;
+
+      // exponentiate, accumulate the row sum in fp32, pack P to bf16
+      uint32_t pk[64];
+      float sum = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float e0 = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_scaled));
+          const float e1 = fast_exp2(fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, -m_scaled));
+          sum += e0 + e1;
+          pk[c * 16 + (i >> 1)] = pack_bf16x2(e0, e1);
+        }
+      l += sum;
+
+      if (j > 0) {
+        // O (and the P buffer) are free once PV_{j-1} has completed
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(lane_base + TM_O + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(lane_base + TM_O + c * 32, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      // P -> smem in the K-major SW128 layout the MMA expects (16-byte unit u of row r lives at u ^ (r & 7))
+#pragma unroll
+      for (int g8 = 0; g8 < 16; ++g8) {
+        const int chunk = g8 >> 3, u = g8 & 7;
+        uint4 w = make_uint4(pk[g8 * 4 + 0], pk[g8 * 4 + 1], pk[g8 * 4 + 2], pk[g8 * 4 + 3]);
+        *reinterpret_cast<uint4*>(p_row + chunk * 16384 + ((u ^ sw) << 4)) = w;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+
+    // ---- epilogue: O / l -> global ----
+    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv_l = (l > 0.0f) ? 1.0f / l : 0.0f;
+    const int q_abs = q_begin + row;
+    const bool valid = q_abs < q_end;
+    __nv_bfloat16* dst = p.o + static_cast<long long>(b) * p.o_sb + static_cast<long long>(q_abs) * p.o_ss +
+                         static_cast<long long>(h) * p.o_sh;
+#pragma unroll 1
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(lane_base + TM_O + c * 32, o);
+      tmem_wait_ld();
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+          reinterpret_cast<uint4*>(dst + c * 32)[i] = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// Build a 4-D tensor map over (d, seq, head, batch) for a [.., D]-contiguous bf16 tensor with arbitrary (16-byte
+// aligned) strides; outer dims are ordered by increasing stride. pos[] returns the coordinate slot of (seq, head, batch).
+static int make_attn_tmap(CUtensorMap* tm, const void* ptr, int64_t D, int64_t S, int64_t H, int64_t B, int64_t ss,
+                          int64_t sh, int64_t sb, int pos[3]) {
+  struct Dim {
+    int64_t size, stride;
+    int which;
+  };
+  Dim d[3] = {{S, ss, 0}, {H, sh, 1}, {B, sb, 2}};
+  int64_t span = D;
+  for (int i = 0; i < 3; ++i)
+    if (d[i].size > 1) span = std::max(span, d[i].size * d[i].stride);
+  for (int i = 0; i < 3; ++i)
+    if (d[i].size <= 1) d[i].stride = (span + 7) / 8 * 8 + 8 * (i + 1);  // size-1 dims: any valid stride, sorted last
+  std::sort(d, d + 3, [](const Dim& a, const Dim& b2) { return a.stride < b2.stride; });
+  uint64_t dims[4] = {(uint64_t)D, 0, 0, 0};
+  uint64_t strides[3];
+  uint32_t box[4] = {64, 1, 1, 1};
+  for (int i = 0; i < 3; ++i) {
+    dims[i + 1] = (uint64_t)d[i].size;
+    strides[i] = (uint64_t)d[i].stride * 2;
+    pos[d[i].which] = i + 1;
+    if (d[i].which == 0) box[i + 1] = 128;
+  }
+  return encode_tmap_bf16_sw128(tm, ptr, 4, dims, strides, box);
+}
+
+template <int D>
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                       dim3 grid, cudaStream_t stream) {
+  constexpr int KS = (D == 64) ? 3 : 2;
+  constexpr int smem_bytes = (1 + 2 * KS) * 128 * D * 2 + 128 * 128 * 2 + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  attn_kernel<D><<<grid, 192, smem_bytes, stream>>>(tq, tk, tv, p);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200mix_sdpa(const void* q, const void* k, const void* v, void* o, int64_t B, int64_t Hq, int64_t Hkv,
+                            int64_t Sq, int64_t Sk, int64_t D, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t k_sb,
+                            int64_t k_ss, int64_t k_sh, int64_t v_sb, int64_t v_ss, int64_t v_sh, int64_t o_sb,
+                            int64_t o_ss, int64_t o_sh, float scale, int32_t causal, const int32_t* cu_seqlens,
+                            int32_t nseq, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(q && k && v && o, "sdpa: null pointer");
+  B200_CHECK_ARG(D == 64 || D == 128, "sdpa: head_dim %lld unsupported (64 or 128; pad at weight-load time)",
+                 (long long)D);
+  B200_CHECK_ARG(B > 0 && Hq > 0 && Hkv > 0 && Sq > 0 && Sk > 0, "sdpa: bad shape");
+  B200_CHECK_ARG(Hq % Hkv == 0, "sdpa: Hq %% Hkv != 0");
+  B200_CHECK_ARG(!cu_seqlens || (B == 1 && nseq > 0 && Sq == Sk), "sdpa: varlen mode needs B == 1, Sq == Sk");
+  const int64_t all_strides[12] = {q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb, o_ss, o_sh};
+  for (int i = 0; i < 12; ++i)
+    B200_CHECK_ARG(all_strides[i] % 8 == 0, "sdpa: stride %d (= %lld) must be a multiple of 8 elements", i,
+                   (long long)all_strides[i]);
+  B200_CHECK_ARG(reinterpret_cast<uintptr_t>(o) % 16 == 0, "sdpa: output must be 16-byte aligned");
+
+  AttnParams p = {};
+  p.Hq = (int)Hq, p.Hkv = (int)Hkv, p.Sq = (int)Sq, p.Sk = (int)Sk;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.causal = causal;
+  p.cu = cu_seqlens;
+  p.nseq = nseq;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.o_sb = o_sb, p.o_ss = o_ss, p.o_sh = o_sh;
+  CUtensorMap tq, tk, tv;
+  if (int rc = make_attn_tmap(&tq, q, D, Sq, Hq, B, q_ss, q_sh, q_sb, p.q_pos)) return rc;
+  if (int rc = make_attn_tmap(&tk, k, D, Sk, Hkv, B, k_ss, k_sh, k_sb, p.k_pos)) return rc;
+  if (int rc = make_attn_tmap(&tv, v, D, Sk, Hkv, B, v_ss, v_sh, v_sb, p.v_pos)) return rc;
+  int64_t q_tiles = (Sq + 127) / 128 + (cu_seqlens ? nseq : 0);
+  dim3 grid((unsigned)q_tiles, (unsigned)Hq, (unsigned)B);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (D == 64) return launch_attn<64>(tq, tk, tv, p, grid, st);
+  return launch_attn<128>(tq, tk, tv, p, grid, st);
+}

@@ -1,0 +1,514 @@
+// Implicit-GEMM on 5th-gen tensor cores: one persistent, warp-specialised kernel that serves
+//   * Linear / 1x1 conv        C[M,N] = A[M,K] W[N,K]^T                       (1 tap)
+//   * conv3x3 NHWC, stride 1|2 y = sum_taps shift(x) W_tap^T                  (9 taps, im2col-free)
+// Data path: TMA (cp.async.bulk.tensor, 128B swizzle, hardware zero fill for halos / ragged edges) -> shared memory
+// ring -> tcgen05.mma (bf16 x bf16 -> fp32, 128 x BN x 16 per instruction) -> double-buffered TMEM accumulators ->
+// tcgen05.ld -> fused epilogue (bias / temb row-add / activation / GEGLU|SwiGLU / AdaLN gate / residual) -> HBM.
+//
+// Roles (192 threads): warp 0 = TMA producer (1 elected lane), warp 1 = TMEM owner + MMA issuer (1 elected lane),
+// warps 2..5 = epilogue (warp%4 selects the TMEM lane quarter). The epilogue of tile i overlaps the main loop of
+// tile i+1 through the two TMEM accumulator stages.
+//
+// Replaces (reference): F.linear / F.conv2d call sites ppdiffusers/models/lora.py:365-377,453-459,
+// resnet.py:728-808, attention.py:623-677 (FeedForward/GEGLU), and their cuBLASLt / cuDNN kernels inside Paddle.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+struct IGemmParams {
+  int N;        // accumulator columns (before GLU halving)
+  int Kc;       // reduction length per tap (C_in or K)
+  int ntaps;    // 1 or 9
+  int kchunks;  // ceil(Kc / 64)
+  int TW, TH, TB;  // tile box in (x, y, b); TW*TH*TB == 128
+  int Wo, Ho, Bn;  // output extents in (x, y, b); plain GEMM: Wo = M, Ho = Bn = 1
+  int tiles_x, tiles_y, tiles_b, tiles_n;
+  int tap_dc[9], tap_dx[9], tap_p[9], tap_dy[9];
+  // epilogue
+  const float* bias;
+  const float* row_add;
+  const float* row_gate;
+  long long ld_row;
+  int rows_per_group;
+  const __nv_bfloat16* residual;
+  long long ldr;
+  void* C;
+  long long ldc;
+  int act, glu, out_fp32, vec_ok;
+  float out_scale;
+};
+
+__device__ __forceinline__ float act_silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float act_gelu_tanh(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(u));
+}
+__device__ __forceinline__ float act_quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case B200MIX_ACT_SILU: return act_silu(v);
+    case B200MIX_ACT_GELU_ERF: return act_gelu_erf(v);
+    case B200MIX_ACT_GELU_TANH: return act_gelu_tanh(v);
+    case B200MIX_ACT_QUICK_GELU: return act_quick_gelu(v);
+    default: return v;
+  }
+}
+
+// One 32-column chunk of one accumulator row -> global memory.
+__device__ __forceinline__ void epilogue_chunk(const IGemmParams& p, const uint32_t (&r)[32], long long gm, long long g,
+                                               int n_abs) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  const bool full = (n_abs + 32 <= p.N);
+  const bool vec = full && p.vec_ok;
+
+  if (p.bias) {
+    if (full) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_abs);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b = __ldg(b4 + j);
+        v[4 * j + 0] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n_abs + j < p.N) v[j] += __ldg(p.bias + n_abs + j);
+    }
+  }
+  if (p.row_add) {
+    const float* ra = p.row_add + g * p.ld_row + n_abs;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (full || n_abs + j < p.N) v[j] += __ldg(ra + j);
+  }
+  if (p.act != B200MIX_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+  }
+
+  if (p.glu) {
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float val = v[2 * j], gate = v[2 * j + 1];
+      o[j] = (p.glu == B200MIX_GLU_GEGLU) ? val * act_gelu_erf(gate) : val * act_silu(gate);
+    }
+    const int ncol = n_abs >> 1;
+    const int nout = p.N >> 1;
+    if (p.out_fp32) {
+      float* dst = reinterpret_cast<float*>(p.C) + gm * p.ldc + ncol;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (ncol + j < nout) dst[j] = o[j];
+    } else {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + gm * p.ldc + ncol;
+      if (vec) {
+        uint4 w0 = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                              pack_bf16x2(o[6], o[7]));
+        uint4 w1 = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]),
+                              pack_bf16x2(o[14], o[15]));
+        reinterpret_cast<uint4*>(dst)[0] = w0;
+        reinterpret_cast<uint4*>(dst)[1] = w1;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (ncol + j < nout) dst[j] = __float2bfloat16(o[j]);
+      }
+    }
+    return;
+  }
+
+  if (p.row_gate) {
+    const float* rg = p.row_gate + g * p.ld_row + n_abs;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (full || n_abs + j < p.N) v[j] *= __ldg(rg + j);
+  }
+  if (p.residual) {
+    const __nv_bfloat16* rs = p.residual + gm * p.ldr + n_abs;
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 w = __ldg(reinterpret_cast<const uint4*>(rs) + j);
+        v[8 * j + 0] += bf16_lo(w.x), v[8 * j + 1] += bf16_hi(w.x);
+        v[8 * j + 2] += bf16_lo(w.y), v[8 * j + 3] += bf16_hi(w.y);
+        v[8 * j + 4] += bf16_lo(w.z), v[8 * j + 5] += bf16_hi(w.z);
+        v[8 * j + 6] += bf16_lo(w.w), v[8 * j + 7] += bf16_hi(w.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n_abs + j < p.N) v[j] += __bfloat162float(rs[j]);
+    }
+  }
+  if (p.out_scale != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+  }
+
+  if (p.out_fp32) {
+    float* dst = reinterpret_cast<float*>(p.C) + gm * p.ldc + n_abs;
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n_abs + j < p.N) dst[j] = v[j];
+    }
+  } else {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + gm * p.ldc + n_abs;
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 w = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        reinterpret_cast<uint4*>(dst)[j] = w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n_abs + j < p.N) dst[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+template <int BN>
+struct IGemmCfg {
+  static constexpr int A_BYTES = 128 * 128;  // 128 rows x 64 bf16 (128 B per row, SW128)
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int ACC_STRIDE = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+    igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ IGemmParams p) {
+  using Cfg = IGemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull = empty_bar + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 128);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int total_tiles = tiles_m * p.tiles_n;
+  const int kblocks = p.ntaps * p.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+        const int tx = mt % p.tiles_x;
+        const int ty = (mt / p.tiles_x) % p.tiles_y;
+        const int tb = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.TW, y0 = ty * p.TH, b0 = tb * p.TB, n0 = nt * BN;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int dc = p.tap_dc[tap], dx = p.tap_dx[tap], pp = p.tap_p[tap], dy = p.tap_dy[tap];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sB = sA + Cfg::A_BYTES;
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_5d(sA, &tmA, &full_bar[stage], kc * 64 + dc, x0 + dx, pp, y0 + dy, b0);
+            tma_load_2d(sB, &tmB, &full_bar[stage], tap * p.Kc + kc * 64, n0);
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+        umma_commit(&tfull[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tw = row % p.TW;
+    const int th = (row / p.TW) % p.TH;
+    const int tbb = row / (p.TW * p.TH);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+      const int tx = mt % p.tiles_x;
+      const int ty = (mt / p.tiles_x) % p.tiles_y;
+      const int tb = mt / (p.tiles_x * p.tiles_y);
+      const int x = tx * p.TW + tw, y = ty * p.TH + th, b = tb * p.TB + tbb;
+      const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.Bn);
+      const long long gm = (static_cast<long long>(b) * p.Ho + y) * p.Wo + x;
+      const long long g = gm / p.rows_per_group;
+      const int n0 = nt * BN;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_addr + c * 32, r);
+        tmem_wait_ld();
+        if (valid && n0 + c * 32 < p.N) epilogue_chunk(p, r, gm, g, n0 + c * 32);
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IGemmParams& p, cudaStream_t stream) {
+  using Cfg = IGemmCfg<BN>;
+  constexpr int smem_bytes = STAGES * Cfg::STAGE_BYTES + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  const int total = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+  int grid = num_sms();
+  if (grid > total) grid = total;
+  igemm_kernel<BN, STAGES><<<grid, 192, smem_bytes, stream>>>(tmA, tmB, p);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+static int pick_bn(long long tiles_m, long long N, int glu) {
+  const int cands[5] = {256, 160, 128, 64, 32};
+  double best = 1e30;
+  int best_bn = 128;
+  const int sms = num_sms();
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cands[i];
+    const long long tn = (N + bn - 1) / bn;
+    const long long waves = (tiles_m * tn + sms - 1) / sms;
+    const double per_tile = (2 * bn > 128 + bn) ? 2.0 * bn : 128.0 + bn;  // MMA-bound vs smem-read-bound
+    const double cost = double(waves) * per_tile + 0.02 * per_tile;       // slight preference for fewer, larger tiles
+    if (cost < best) best = cost, best_bn = bn;
+  }
+  (void)glu;
+  return best_bn;
+}
+
+static int dispatch_igemm(const CUtensorMap& tmA, const void* W, long long ldw, long long Ktot, IGemmParams& p,
+                          cudaStream_t stream, int force_bn) {
+  const long long tiles_m = (long long)p.tiles_x * p.tiles_y * p.tiles_b;
+  const int bn = force_bn > 0 ? force_bn : pick_bn(tiles_m, p.N, p.glu);
+  p.tiles_n = (p.N + bn - 1) / bn;
+  CUtensorMap tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)p.N};
+    uint64_t strides[1] = {(uint64_t)ldw * 2};
+    uint32_t box[2] = {64, (uint32_t)bn};
+    int rc = encode_tmap_bf16_sw128(&tmB, W, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  switch (bn) {
+    case 256: return launch_igemm<256, 4>(tmA, tmB, p, stream);
+    case 160: return launch_igemm<160, 6>(tmA, tmB, p, stream);
+    case 128: return launch_igemm<128, 6>(tmA, tmB, p, stream);
+    case 64: return launch_igemm<64, 8>(tmA, tmB, p, stream);
+    case 32: return launch_igemm<32, 8>(tmA, tmB, p, stream);
+    default: set_error("unsupported BN %d", bn); return B200MIX_ERR_INVALID;
+  }
+}
+
+static int fill_epilogue(IGemmParams& p, const b200mix_epilogue* e, void* C, long long ldc, long long rows_default) {
+  static const b200mix_epilogue kNone = {nullptr, nullptr, nullptr, 0, 0, nullptr, 0, 0, 0, 0, 1.0f};
+  if (!e) e = &kNone;
+  p.bias = e->bias;
+  p.row_add = e->row_add;
+  p.row_gate = e->row_gate;
+  p.ld_row = e->ld_row;
+  p.rows_per_group = (int)(e->rows_per_group > 0 ? e->rows_per_group : rows_default);
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(e->residual);
+  p.ldr = e->ldr;
+  p.C = C;
+  p.ldc = ldc;
+  p.act = e->act;
+  p.glu = e->glu;
+  p.out_fp32 = e->out_fp32;
+  p.out_scale = e->out_scale == 0.0f ? 1.0f : e->out_scale;
+  B200_CHECK_ARG(!(p.glu && (p.N & 1)), "GLU epilogue needs an even N (got %d)", p.N);
+  B200_CHECK_ARG(!(p.glu && (p.row_gate || p.residual)), "GLU epilogue cannot be combined with gate/residual");
+  const int out_elem = p.out_fp32 ? 4 : 2;
+  bool vec = (reinterpret_cast<uintptr_t>(C) % 16 == 0) && ((ldc * out_elem) % 16 == 0);
+  if (p.residual) vec = vec && (reinterpret_cast<uintptr_t>(p.residual) % 16 == 0) && ((p.ldr * 2) % 16 == 0);
+  if (p.bias) vec = vec && (reinterpret_cast<uintptr_t>(p.bias) % 16 == 0);
+  p.vec_ok = vec ? 1 : 0;
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// Test hook: force a tile width (0 = heuristic). Not part of the public header.
+static int g_force_bn = 0;
+extern "C" void b200mix_debug_force_bn(int bn) { g_force_bn = bn; }
+
+extern "C" int b200mix_linear(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M,
+                              int64_t N, int64_t K, const b200mix_epilogue* epi, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(A && W && C, "linear: null pointer");
+  B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "linear: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N,
+                 (long long)K);
+  B200_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0, "linear: lda/ldw must be multiples of 8 elements (16 B TMA strides)");
+  B200_CHECK_ARG(lda >= K && ldw >= K, "linear: leading dimensions smaller than K");
+  B200_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31), "linear: M/N too large");
+
+  IGemmParams p = {};
+  p.N = (int)N;
+  p.Kc = (int)K;
+  p.ntaps = 1;
+  p.kchunks = (int)((K + 63) / 64);
+  p.TW = 128, p.TH = 1, p.TB = 1;
+  p.Wo = (int)M, p.Ho = 1, p.Bn = 1;
+  p.tiles_x = (int)((M + 127) / 128), p.tiles_y = 1, p.tiles_b = 1;
+  if (int rc = fill_epilogue(p, epi, C, ldc, M)) return rc;
+
+  CUtensorMap tmA;
+  {
+    uint64_t dims[5] = {(uint64_t)K, (uint64_t)M, 1, 1, 1};
+    uint64_t rowb = (uint64_t)lda * 2;
+    uint64_t strides[4] = {rowb, rowb * (uint64_t)M, rowb * (uint64_t)M, rowb * (uint64_t)M};
+    uint32_t box[5] = {64, 128, 1, 1, 1};
+    if (int rc = encode_tmap_bf16_sw128(&tmA, A, 5, dims, strides, box)) return rc;
+  }
+  return dispatch_igemm(tmA, W, ldw, K, p, reinterpret_cast<cudaStream_t>(stream), g_force_bn);
+}
+
+extern "C" int b200mix_conv3x3(const void* x, const void* w, void* y, int64_t B, int64_t H, int64_t W, int64_t Cin,
+                               int64_t Cout, int32_t stride, const b200mix_epilogue* epi, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(x && w && y, "conv3x3: null pointer");
+  B200_CHECK_ARG(stride == 1 || stride == 2, "conv3x3: stride must be 1 or 2");
+  B200_CHECK_ARG(Cin % 64 == 0, "conv3x3: Cin=%lld must be a multiple of 64 (use conv3x3_small_cin)", (long long)Cin);
+  B200_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cout > 0, "conv3x3: bad shape");
+  B200_CHECK_ARG(stride == 1 || (H % 2 == 0 && W % 2 == 0), "conv3x3: stride 2 needs even H, W");
+  const int64_t Ho = H / stride, Wo = W / stride;
+
+  IGemmParams p = {};
+  p.N = (int)Cout;
+  p.Kc = (int)Cin;
+  p.ntaps = 9;
+  p.kchunks = (int)(Cin / 64);
+  // tile box: TW x TH x TB = 128 output pixels
+  int TW = 1;
+  while (TW * 2 <= Wo && TW < 128 && Wo % (TW * 2) == 0) TW *= 2;
+  int TH = 1;
+  while (TW * TH * 2 <= 128 && TH * 2 <= Ho && Ho % (TH * 2) == 0) TH *= 2;
+  int TB = 128 / (TW * TH);
+  B200_CHECK_ARG(TW * TH * TB == 128, "conv3x3: cannot tile %lldx%lld output into 128-pixel boxes", (long long)Ho,
+                 (long long)Wo);
+  p.TW = TW, p.TH = TH, p.TB = TB;
+  p.Wo = (int)Wo, p.Ho = (int)Ho, p.Bn = (int)B;
+  p.tiles_x = (int)((Wo + TW - 1) / TW);
+  p.tiles_y = (int)((Ho + TH - 1) / TH);
+  p.tiles_b = (int)((B + TB - 1) / TB);
+  for (int kh = 0; kh < 3; ++kh) {
+    for (int kw = 0; kw < 3; ++kw) {
+      const int t = kh * 3 + kw;
+      if (stride == 1) {
+        p.tap_dc[t] = 0, p.tap_dx[t] = kw - 1, p.tap_p[t] = 0, p.tap_dy[t] = kh - 1;
+      } else {
+        // input (h, w) = (2*oh + kh - 1, 2*ow + kw - 1) on the parity view [B, H/2, 2, W/2, 2*C]
+        const int wp = (kw == 1) ? 0 : 1, dx = (kw == 0) ? -1 : 0;
+        const int hp = (kh == 1) ? 0 : 1, dy = (kh == 0) ? -1 : 0;
+        p.tap_dc[t] = wp * (int)Cin, p.tap_dx[t] = dx, p.tap_p[t] = hp, p.tap_dy[t] = dy;
+      }
+    }
+  }
+  if (int rc = fill_epilogue(p, epi, y, Cout, Ho * Wo)) return rc;
+  if (p.glu) {
+    set_error("conv3x3: GLU epilogue not supported");
+    return B200MIX_ERR_INVALID;
+  }
+
+  CUtensorMap tmA;
+  {
+    uint64_t dims[5], strides[4];
+    if (stride == 1) {
+      dims[0] = Cin, dims[1] = W, dims[2] = 1, dims[3] = H, dims[4] = B;
+      strides[0] = Cin * 2, strides[1] = W * Cin * 2, strides[2] = W * Cin * 2, strides[3] = H * W * Cin * 2;
+    } else {
+      dims[0] = 2 * Cin, dims[1] = W / 2, dims[2] = 2, dims[3] = H / 2, dims[4] = B;
+      strides[0] = 2 * Cin * 2, strides[1] = W * Cin * 2, strides[2] = 2 * W * Cin * 2, strides[3] = H * W * Cin * 2;
+    }
+    uint32_t box[5] = {64, (uint32_t)TW, 1, (uint32_t)TH, (uint32_t)TB};
+    if (int rc = encode_tmap_bf16_sw128(&tmA, x, 5, dims, strides, box)) return rc;
+  }
+  return dispatch_igemm(tmA, w, 9 * Cin, 9 * Cin, p, reinterpret_cast<cudaStream_t>(stream), g_force_bn);
+}

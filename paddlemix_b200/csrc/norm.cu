@@ -1,0 +1,315 @@
+// HBM-bound normalisation kernels: GroupNorm(+SiLU) on NHWC with fused channel-concat input, and the row-wise
+// LayerNorm / RMSNorm family with fused residual-gate and AdaLN modulation. 16-byte coalesced accesses, fp32 math.
+//
+// Replaces (reference): nn.GroupNorm + SiLU in ResnetBlock2D (ppdiffusers/models/resnet.py:667-692,760-786),
+// Transformer2DModel.norm (transformer_2d.py:161), conv_norm_out (unet_2d_condition.py:604,1193-1195);
+// nn.LayerNorm in BasicTransformerBlock (attention.py:307-350); the Triton ops fused_adaLN_scale_residual /
+// adaptive_layer_norm / rms_norm (paddlemix/triton_ops/triton_ops.py:702-755, 981-1027, 1198-1232) and
+// Qwen2RMSNorm (paddlemix/models/qwen2_vl/modeling_qwen2_vl.py:467-478).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ void unpack8(const uint4& w, float (&f)[8]) {
+  f[0] = bf16_lo(w.x), f[1] = bf16_hi(w.x), f[2] = bf16_lo(w.y), f[3] = bf16_hi(w.y);
+  f[4] = bf16_lo(w.z), f[5] = bf16_hi(w.z), f[6] = bf16_lo(w.w), f[7] = bf16_hi(w.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------------------
+// GroupNorm statistics: per (batch, group) sum and sum of squares, accumulated in double through atomics.
+// Block = PPB pixels x CV 8-channel vectors; each thread owns a fixed channel vector => fully coalesced rows.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2,
+                                int C2, double* __restrict__ stats, long long HW, int groups, int PPB, int pix_per_cta) {
+  extern __shared__ float sm[];  // [2*C]
+  const int C = C1 + C2;
+  const int CV = C >> 3;
+  const int cv = threadIdx.x % CV;
+  const int pl = threadIdx.x / CV;
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.0f;
+  __syncthreads();
+
+  const int c0 = cv * 8;
+  const __nv_bfloat16* src;
+  long long ld;
+  int cc;
+  if (c0 < C1) {
+    src = x1 + static_cast<long long>(b) * HW * C1, ld = C1, cc = c0;
+  } else {
+    src = x2 + static_cast<long long>(b) * HW * C2, ld = C2, cc = c0 - C1;
+  }
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.0f, q[i] = 0.0f;
+  const long long p_begin = static_cast<long long>(blockIdx.x) * pix_per_cta;
+  const long long p_end = min(HW, p_begin + pix_per_cta);
+  if (pl < PPB) {
+    for (long long pix = p_begin + pl; pix < p_end; pix += PPB) {
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(src + pix * ld + cc));
+      float f[8];
+      unpack8(w, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += f[i], q[i] += f[i] * f[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sm[c0 + i], s[i]);
+      atomicAdd(&sm[C + c0 + i], q[i]);
+    }
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double ss = 0.0, qq = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) ss += sm[c], qq += sm[C + c];
+    atomicAdd(&stats[(static_cast<long long>(b) * groups + g) * 2 + 0], ss);
+    atomicAdd(&stats[(static_cast<long long>(b) * groups + g) * 2 + 1], qq);
+  }
+}
+
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2,
+                                int C2, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                __nv_bfloat16* __restrict__ y, const double* __restrict__ stats, long long HW,
+                                int groups, float eps, int silu, int PPB, int pix_per_cta) {
+  const int C = C1 + C2;
+  const int CV = C >> 3;
+  const int cv = threadIdx.x % CV;
+  const int pl = threadIdx.x / CV;
+  const int b = blockIdx.y;
+  if (pl >= PPB) return;
+  const int c0 = cv * 8;
+  const int cpg = C / groups;
+  const double n = static_cast<double>(HW) * cpg;
+  float a[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    const int g = c / cpg;
+    const double su = stats[(static_cast<long long>(b) * groups + g) * 2 + 0];
+    const double sq = stats[(static_cast<long long>(b) * groups + g) * 2 + 1];
+    const double mean = su / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = rsqrtf(static_cast<float>(var) + eps);
+    a[i] = rstd * gamma[c];
+    sh[i] = beta[c] - static_cast<float>(mean) * a[i];
+  }
+  const __nv_bfloat16* src;
+  long long ld;
+  int cc;
+  if (c0 < C1) {
+    src = x1 + static_cast<long long>(b) * HW * C1, ld = C1, cc = c0;
+  } else {
+    src = x2 + static_cast<long long>(b) * HW * C2, ld = C2, cc = c0 - C1;
+  }
+  __nv_bfloat16* dst = y + static_cast<long long>(b) * HW * C + c0;
+  const long long p_begin = static_cast<long long>(blockIdx.x) * pix_per_cta;
+  const long long p_end = min(HW, p_begin + pix_per_cta);
+  for (long long pix = p_begin + pl; pix < p_end; pix += PPB) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(src + pix * ld + cc));
+    float f[8];
+    unpack8(w, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = fmaf(f[i], a[i], sh[i]);
+      f[i] = silu ? silu_f(v) : v;
+    }
+    *reinterpret_cast<uint4*>(dst + pix * C) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Row-wise LayerNorm / RMSNorm: one warp per row, the row lives in registers (two-pass mean / variance).
+// ------------------------------------------------------------------------------------------------------------
+struct LNParams {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* delta;
+  const float* gate;
+  __nv_bfloat16* resid_out;
+  __nv_bfloat16* y;
+  const float* weight;
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  long long ld_mod;
+  long long rows_per_group;
+  long long M;
+  int N;
+  float eps;
+  int rms;
+};
+
+template <int VPL>
+__global__ void __launch_bounds__(256) layernorm_kernel(const LNParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (row >= p.M) return;
+  const int NV = p.N >> 3;
+  const long long g = row / p.rows_per_group;
+  const __nv_bfloat16* xr = p.x + row * p.N;
+  float v[VPL][8];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < NV) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + vi), v[i]);
+      if (p.delta) {
+        float d[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p.delta + row * p.N) + vi), d);
+        if (p.gate) {
+          const float* gp = p.gate + g * p.ld_mod + vi * 8;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[i][k] = fmaf(__ldg(gp + k), d[k], v[i][k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[i][k] += d[k];
+        }
+        if (p.resid_out) {
+          // the residual stream is stored in bf16: normalise the rounded value so both outputs agree
+          uint4 w = pack8(v[i]);
+          *(reinterpret_cast<uint4*>(p.resid_out + row * p.N) + vi) = w;
+          unpack8(w, v[i]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += v[i][k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[i][k] = 0.0f;
+    }
+  }
+  float mean = 0.0f;
+  if (!p.rms) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mean = sum / p.N;
+  }
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < NV) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = v[i][k] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / p.N + p.eps);
+
+  __nv_bfloat16* yr = p.y + row * p.N;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < NV) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (v[i][k] - mean) * rstd;
+      if (p.rms && p.weight) {
+        // Qwen2RMSNorm: normalised value is cast to the activation dtype first, then multiplied by the weight
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          o[k] = __bfloat162float(__float2bfloat16(o[k])) * __ldg(p.weight + vi * 8 + k);
+      } else if (p.weight) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] *= __ldg(p.weight + vi * 8 + k);
+      }
+      if (p.bias) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += __ldg(p.bias + vi * 8 + k);
+      }
+      if (p.scale) {
+        const float* sp = p.scale + g * p.ld_mod + vi * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] *= (1.0f + __ldg(sp + k));
+      }
+      if (p.shift) {
+        const float* sp = p.shift + g * p.ld_mod + vi * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += __ldg(sp + k);
+      }
+      *(reinterpret_cast<uint4*>(yr) + vi) = pack8(o);
+    }
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2, int64_t C2, const float* gamma,
+                                      const float* beta, void* y, void* stats, int64_t B, int64_t HW, int32_t groups,
+                                      float eps, int32_t silu, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  const int64_t C = C1 + C2;
+  B200_CHECK_ARG(x1 && y && gamma && beta && stats, "groupnorm: null pointer");
+  B200_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && (C2 == 0 || x2), "groupnorm: channel counts must be multiples of 8");
+  B200_CHECK_ARG(C % groups == 0, "groupnorm: C=%lld not divisible by groups=%d", (long long)C, groups);
+  B200_CHECK_ARG(C / 8 <= 1024, "groupnorm: C too large");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int CV = (int)(C / 8);
+  int PPB = 256 / CV;
+  if (PPB < 1) PPB = 1;
+  const int threads = ((CV * PPB + 31) / 32) * 32;
+  long long ctas_per_b = (4LL * num_sms() + B - 1) / B;
+  long long pix_per_cta = (HW + ctas_per_b - 1) / ctas_per_b;
+  pix_per_cta = ((pix_per_cta + PPB - 1) / PPB) * PPB;
+  if (pix_per_cta < PPB) pix_per_cta = PPB;
+  const unsigned gx = (unsigned)((HW + pix_per_cta - 1) / pix_per_cta);
+  double* dstats = reinterpret_cast<double*>(stats);
+  B200_CUDA(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * B * groups, st));
+  dim3 grid(gx, (unsigned)B);
+  gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x1), (int)C1, reinterpret_cast<const __nv_bfloat16*>(x2), (int)C2, dstats,
+      HW, groups, PPB, (int)pix_per_cta);
+  B200_LAUNCH_CHECK();
+  gn_apply_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x1), (int)C1,
+                                            reinterpret_cast<const __nv_bfloat16*>(x2), (int)C2, gamma, beta,
+                                            reinterpret_cast<__nv_bfloat16*>(y), dstats, HW, groups, eps, silu, PPB,
+                                            (int)pix_per_cta);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_layernorm(const void* x, const void* delta, const float* gate, void* resid_out, void* y,
+                                 const float* weight, const float* bias, const float* scale, const float* shift,
+                                 int64_t ld_mod, int64_t rows_per_group, int64_t M, int64_t N, float eps, int32_t rms,
+                                 void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(x && y, "layernorm: null pointer");
+  B200_CHECK_ARG(N % 8 == 0 && N > 0 && N <= 8192, "layernorm: N=%lld must be a multiple of 8 and <= 8192",
+                 (long long)N);
+  B200_CHECK_ARG(M > 0, "layernorm: M must be positive");
+  LNParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.delta = reinterpret_cast<const __nv_bfloat16*>(delta);
+  p.gate = gate;
+  p.resid_out = reinterpret_cast<__nv_bfloat16*>(resid_out);
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.weight = weight, p.bias = bias, p.scale = scale, p.shift = shift;
+  p.ld_mod = ld_mod;
+  p.rows_per_group = rows_per_group > 0 ? rows_per_group : M;
+  p.M = M, p.N = (int)N, p.eps = eps, p.rms = rms;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((M + 7) / 8);
+  const int nv = (int)(N / 8);
+  if (nv <= 64) layernorm_kernel<2><<<grid, 256, 0, st>>>(p);
+  else if (nv <= 128) layernorm_kernel<4><<<grid, 256, 0, st>>>(p);
+  else if (nv <= 192) layernorm_kernel<6><<<grid, 256, 0, st>>>(p);
+  else if (nv <= 256) layernorm_kernel<8><<<grid, 256, 0, st>>>(p);
+  else if (nv <= 512) layernorm_kernel<16><<<grid, 256, 0, st>>>(p);
+  else layernorm_kernel<32><<<grid, 256, 0, st>>>(p);
+  B200_LAUNCH_CHECK();
+  return 0;
+}

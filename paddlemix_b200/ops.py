@@ -1,0 +1,288 @@
+"""Tensor-level wrappers over the C ABI. torch is used for device memory and streams only: every function below
+enqueues hand-written sm_100a kernels from libb200mix.so on torch's current CUDA stream and raises if that fails.
+"""
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, GLU_GEGLU, GLU_NONE, GLU_SWIGLU,
+                   Epilogue, check, lib)
+
+bf16 = torch.bfloat16
+_launches = 0  # number of our kernels launched (bench.py reports it as gpu_launches)
+
+
+def launches() -> int:
+    return _launches
+
+
+def reset_launches():
+    global _launches
+    _launches = 0
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _req(t, dtype, name):
+    if not t.is_cuda:
+        raise _lib.B200MixError(f"{name} must be a CUDA tensor (b200mix has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def init(device: int = 0):
+    check(lib.b200mix_init(int(device)), "b200mix_init")
+
+
+def make_epilogue(bias=None, row_add=None, row_gate=None, ld_row=0, rows_per_group=0, residual=None, ldr=0,
+                  act=ACT_NONE, glu=GLU_NONE, out_fp32=False, out_scale=1.0) -> Epilogue:
+    e = Epilogue()
+    e.bias = None if bias is None else _req(bias, torch.float32, "bias").data_ptr()
+    e.row_add = None if row_add is None else _req(row_add, torch.float32, "row_add").data_ptr()
+    e.row_gate = None if row_gate is None else _req(row_gate, torch.float32, "row_gate").data_ptr()
+    e.ld_row = int(ld_row)
+    e.rows_per_group = int(rows_per_group)
+    e.residual = None if residual is None else _req(residual, bf16, "residual").data_ptr()
+    e.ldr = int(ldr)
+    e.act = int(act)
+    e.glu = int(glu)
+    e.out_fp32 = 1 if out_fp32 else 0
+    e.out_scale = float(out_scale)
+    return e
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, act=ACT_NONE, glu=GLU_NONE, residual=None, row_add=None,
+           row_gate=None, rows_per_group=0, out_fp32=False, out=None, out_scale=1.0) -> torch.Tensor:
+    """out[M, N(/2)] = epilogue(a[M, K] @ w[N, K]^T). a: bf16 [..., K] (last dim contiguous), w: bf16 [N, K]."""
+    _req(a, bf16, "a"), _req(w, bf16, "w")
+    K = a.shape[-1]
+    a2 = a.reshape(-1, K)
+    if a2.stride(-1) != 1:
+        a2 = a2.contiguous()
+    M, N = a2.shape[0], w.shape[0]
+    n_out = N // 2 if glu else N
+    if out is None:
+        out = torch.empty(*a.shape[:-1], n_out, device=a.device, dtype=torch.float32 if out_fp32 else bf16)
+    res2 = None
+    if residual is not None:
+        res2 = residual.reshape(-1, residual.shape[-1])
+    mod = row_add if row_add is not None else row_gate
+    e = make_epilogue(bias=bias, row_add=row_add, row_gate=row_gate, ld_row=0 if mod is None else mod.stride(0),
+                      rows_per_group=rows_per_group, residual=res2, ldr=0 if res2 is None else res2.stride(0), act=act,
+                      glu=glu, out_fp32=out_fp32, out_scale=out_scale)
+    out2 = out.reshape(-1, n_out)
+    check(lib.b200mix_linear(_p(a2), a2.stride(0), _p(w), w.stride(0), _p(out2), out2.stride(0), M, N, K,
+                             ctypes.byref(e), _stream()), "b200mix_linear")
+    _count()
+    return out
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor, bias=None, *, stride=1, row_add=None, residual=None, act=ACT_NONE,
+            out_scale=1.0, out=None) -> torch.Tensor:
+    """x: bf16 NHWC [B,H,W,Cin] contiguous; w: bf16 [Cout,3,3,Cin] contiguous; returns bf16 NHWC."""
+    _req(x, bf16, "x"), _req(w, bf16, "w")
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    assert x.is_contiguous() and w.is_contiguous()
+    Ho, Wo = H // stride, W // stride
+    if out is None:
+        out = torch.empty(B, Ho, Wo, Cout, device=x.device, dtype=bf16)
+    e = make_epilogue(bias=bias, row_add=row_add, ld_row=0 if row_add is None else row_add.stride(0),
+                      rows_per_group=Ho * Wo, residual=residual, ldr=Cout, act=act, out_scale=out_scale)
+    check(lib.b200mix_conv3x3(_p(x), _p(w), _p(out), B, H, W, Cin, Cout, stride, ctypes.byref(e), _stream()),
+          "b200mix_conv3x3")
+    _count()
+    return out
+
+
+def conv3x3_small_cin(x: torch.Tensor, w: torch.Tensor, bias=None) -> torch.Tensor:
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    assert x.is_contiguous() and w.is_contiguous() and x.dtype in (torch.float32, bf16)
+    out = torch.empty(B, H, W, Cout, device=x.device, dtype=bf16)
+    check(lib.b200mix_conv3x3_small_cin(_p(x), 1 if x.dtype == torch.float32 else 0, _p(w), _p(bias), _p(out), B, H, W,
+                                        Cin, Cout, _stream()), "b200mix_conv3x3_small_cin")
+    _count()
+    return out
+
+
+def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[float] = None, causal=False,
+         cu_seqlens: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q: [B,Sq,Hq,D], k/v: [B,Sk,Hkv,D] bf16 views (head_dim contiguous; other strides arbitrary multiples of 8).
+    Returns [B,Sq,Hq,D] (the reference layout of scaled_dot_product_attention_)."""
+    _req(q, bf16, "q"), _req(k, bf16, "k"), _req(v, bf16, "v")
+    B, Sq, Hq, D = q.shape
+    _, Sk, Hkv, _ = k.shape
+    assert q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1
+    if out is None:
+        out = torch.empty(B, Sq, Hq, D, device=q.device, dtype=bf16)
+    if scale is None:
+        scale = D ** -0.5
+    nseq = 0 if cu_seqlens is None else cu_seqlens.numel() - 1
+    check(lib.b200mix_sdpa(_p(q), _p(k), _p(v), _p(out), B, Hq, Hkv, Sq, Sk, D, q.stride(0), q.stride(1), q.stride(2),
+                           k.stride(0), k.stride(1), k.stride(2), v.stride(0), v.stride(1), v.stride(2), out.stride(0),
+                           out.stride(1), out.stride(2), float(scale), 1 if causal else 0, _p(cu_seqlens), nseq,
+                           _stream()), "b200mix_sdpa")
+    _count()
+    return out
+
+
+_gn_scratch = {}
+
+
+def groupnorm_nhwc(x1: torch.Tensor, gamma, beta, *, x2=None, groups=32, eps=1e-5, silu=False, out=None):
+    """x1: bf16 [B,H,W,C1] (optionally concatenated on channels with x2 [B,H,W,C2]); returns bf16 [B,H,W,C1+C2]."""
+    _req(x1, bf16, "x1")
+    B, C1 = x1.shape[0], x1.shape[-1]
+    HW = x1.numel() // (B * C1)
+    C2 = 0 if x2 is None else x2.shape[-1]
+    assert x1.is_contiguous() and (x2 is None or x2.is_contiguous())
+    if out is None:
+        out = torch.empty(*x1.shape[:-1], C1 + C2, device=x1.device, dtype=bf16)
+    key = (x1.device, B * groups)
+    st = _gn_scratch.get(key)
+    if st is None:
+        st = torch.empty(B * groups * 2, device=x1.device, dtype=torch.float64)
+        _gn_scratch[key] = st
+    check(lib.b200mix_groupnorm_nhwc(_p(x1), C1, _p(x2), C2, _p(gamma), _p(beta), _p(out), _p(st), B, HW, groups,
+                                     float(eps), 1 if silu else 0, _stream()), "b200mix_groupnorm_nhwc")
+    _count(2)
+    return out
+
+
+def layernorm(x: torch.Tensor, weight=None, bias=None, *, eps=1e-5, rms=False, delta=None, gate=None, scale=None,
+              shift=None, rows_per_group=0, want_resid=False, out=None):
+    """Row-wise (RMS/Layer)Norm with optional fused residual update x + gate*delta and AdaLN modulation.
+    Returns y, or (resid, y) when want_resid."""
+    _req(x, bf16, "x")
+    N = x.shape[-1]
+    x2 = x.reshape(-1, N)
+    assert x2.is_contiguous()
+    M = x2.shape[0]
+    if out is None:
+        out = torch.empty_like(x)
+    resid = torch.empty_like(x) if (want_resid and delta is not None) else None
+    mod = gate if gate is not None else (scale if scale is not None else shift)
+    ld_mod = 0 if mod is None else mod.stride(0)
+    check(lib.b200mix_layernorm(_p(x2), _p(delta), _p(gate), _p(resid), _p(out), _p(weight), _p(bias), _p(scale),
+                                _p(shift), ld_mod, rows_per_group, M, N, float(eps), 1 if rms else 0, _stream()),
+          "b200mix_layernorm")
+    _count()
+    if want_resid:
+        return (resid if resid is not None else x), out
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, *, flip_sin_to_cos=True, downscale_freq_shift=0.0, scale=1.0,
+                       max_period=10000.0, out=None, col0=0, out_dtype=bf16):
+    _req(t, torch.float32, "t")
+    B = t.numel()
+    if out is None:
+        out = torch.empty(B, dim, device=t.device, dtype=out_dtype)
+    check(lib.b200mix_timestep_embedding(_p(t), _p(out), 1 if out.dtype == torch.float32 else 0, B, dim, out.stride(0),
+                                         col0, 1 if flip_sin_to_cos else 0, float(downscale_freq_shift), float(scale),
+                                         float(max_period), _stream()), "b200mix_timestep_embedding")
+    _count()
+    return out
+
+
+def activation(x: torch.Tensor, act: int, out_dtype=None):
+    assert x.is_contiguous() and x.dtype in (torch.float32, bf16)
+    out = torch.empty_like(x, dtype=out_dtype or x.dtype)
+    check(lib.b200mix_activation(_p(x), _p(out), x.numel(), act, 1 if x.dtype == torch.float32 else 0,
+                                 1 if out.dtype == torch.float32 else 0, _stream()), "b200mix_activation")
+    _count()
+    return out
+
+
+def upsample_nearest2x(x: torch.Tensor):
+    _req(x, bf16, "x")
+    B, H, W, C = x.shape
+    out = torch.empty(B, 2 * H, 2 * W, C, device=x.device, dtype=bf16)
+    check(lib.b200mix_upsample_nearest2x_nhwc(_p(x), _p(out), B, H, W, C, _stream()), "b200mix_upsample")
+    _count()
+    return out
+
+
+def concat_channels(x1: torch.Tensor, x2: torch.Tensor):
+    C1, C2 = x1.shape[-1], x2.shape[-1]
+    rows = x1.numel() // C1
+    out = torch.empty(*x1.shape[:-1], C1 + C2, device=x1.device, dtype=bf16)
+    check(lib.b200mix_concat_channels(_p(x1), C1, _p(x2), C2, _p(out), rows, _stream()), "b200mix_concat_channels")
+    _count()
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor):
+    B, C, H, W = x.shape
+    assert x.is_contiguous() and x.dtype in (torch.float32, bf16)
+    out = torch.empty(B, H, W, C, device=x.device, dtype=bf16)
+    check(lib.b200mix_nchw_to_nhwc(_p(x), 1 if x.dtype == torch.float32 else 0, _p(out), B, C, H, W, _stream()),
+          "b200mix_nchw_to_nhwc")
+    _count()
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, out_dtype=torch.float32, out=None):
+    B, H, W, C = x.shape
+    _req(x, bf16, "x")
+    if out is None:
+        out = torch.empty(B, C, H, W, device=x.device, dtype=out_dtype)
+    check(lib.b200mix_nhwc_to_nchw(_p(x), _p(out), 1 if out.dtype == torch.float32 else 0, B, C, H, W, _stream()),
+          "b200mix_nhwc_to_nchw")
+    _count()
+    return out
+
+
+def ddim_step(eps_u, eps_c, guidance, x, sa_t, sb_t, sa_p, sb_p, out=None):
+    _req(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.b200mix_ddim_step(_p(eps_u), _p(eps_c), 1 if eps_u.dtype == torch.float32 else 0, float(guidance), _p(x),
+                                _p(out), x.numel(), float(sa_t), float(sb_t), float(sa_p), float(sb_p), _stream()),
+          "b200mix_ddim_step")
+    _count()
+    return out
+
+
+def euler_step(v_u, v_c, guidance, x, dt, out=None):
+    _req(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.b200mix_euler_step(_p(v_u), _p(v_c), 1 if v_u.dtype == torch.float32 else 0, float(guidance), _p(x),
+                                 _p(out), x.numel(), float(dt), _stream()), "b200mix_euler_step")
+    _count()
+    return out
+
+
+def cast(x: torch.Tensor, dtype):
+    assert x.is_contiguous()
+    out = torch.empty_like(x, dtype=dtype)
+    check(lib.b200mix_cast(_p(x), _p(out), x.numel(), 1 if x.dtype == torch.float32 else 0,
+                           1 if dtype == torch.float32 else 0, _stream()), "b200mix_cast")
+    _count()
+    return out
+
+
+def rope_inplace(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, rot_dim: Optional[int] = None):
+    """x: bf16 [T, H, Dpad] view (last dim contiguous); cos/sin fp32 [T, rot_dim]."""
+    T, H, Dp = x.shape
+    D = rot_dim or Dp
+    check(lib.b200mix_rope_inplace(_p(x), T, H, D, x.stride(0), x.stride(1), _p(cos), _p(sin), _stream()),
+          "b200mix_rope_inplace")
+    _count()
+    return x

@@ -1,0 +1,312 @@
+"""Kernel-level parity: every CUDA kernel, called through the C ABI, against a plain PyTorch fp32 evaluation of the
+same operator on the same (bf16-rounded) inputs. Tolerances are stated per test."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from paddlemix_b200 import ops as _ops
+    _ops.init(0)
+    return _ops
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=bf16):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+def close(a, b, atol, rtol, what=""):
+    a, b = a.float().cpu(), b.float().cpu()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{what}: {bad}/{a.numel()} mismatches, max err {err.max().item():.4g}, ref max {b.abs().max().item():.4g}"
+
+
+# bf16 output of a K-long fp32-accumulated dot product: 2^-8 relative rounding on the output dominates.
+GEMM_RTOL, GEMM_ATOL = 1.0e-2, 2e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 640, 320), (8, 1280, 320), (1000, 328, 200), (4096, 1920, 640),
+                                   (77, 64, 2048), (300, 40, 1176)])
+@pytest.mark.parametrize("bn", [0, 32, 64, 128, 160, 256])
+def test_linear_plain(ops, M, N, K, bn):
+    from paddlemix_b200._lib import lib
+    a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    lib.b200mix_debug_force_bn(bn)
+    try:
+        out = ops.linear(a, w, bias)
+    finally:
+        lib.b200mix_debug_force_bn(0)
+    ref = a.float() @ w.float().t() + bias
+    close(out, ref, GEMM_ATOL, GEMM_RTOL, f"linear {M}x{N}x{K} bn={bn}")
+
+
+def test_linear_persistent_many_tiles(ops):
+    M, N, K = 8192, 2560, 1280  # 64 x 10+ tiles: several tiles per CTA, both TMEM stages and all ring phases
+    a, w = rnd(M, K, seed=4), rnd(N, K, seed=5, scale=K ** -0.5)
+    out = ops.linear(a, w)
+    ref = a.float() @ w.float().t()
+    close(out, ref, GEMM_ATOL, GEMM_RTOL, "big linear")
+
+
+@pytest.mark.parametrize("act", [1, 2, 3, 4])
+def test_linear_act(ops, act):
+    M, N, K = 512, 256, 192
+    a, w = rnd(M, K, seed=6), rnd(N, K, seed=7, scale=K ** -0.5)
+    bias = rnd(N, seed=8, dtype=torch.float32)
+    out = ops.linear(a, w, bias, act=act)
+    z = a.float() @ w.float().t() + bias
+    ref = {1: F.silu(z), 2: F.gelu(z), 3: F.gelu(z, approximate="tanh"), 4: z * torch.sigmoid(1.702 * z)}[act]
+    close(out, ref, GEMM_ATOL, GEMM_RTOL, f"act {act}")
+
+
+@pytest.mark.parametrize("glu", [1, 2])
+def test_linear_glu(ops, glu):
+    M, N2, K = 640, 384, 320
+    a = rnd(M, K, seed=9)
+    wv, wg = rnd(N2, K, seed=10, scale=K ** -0.5), rnd(N2, K, seed=11, scale=K ** -0.5)
+    bv, bg = rnd(N2, seed=12, dtype=torch.float32), rnd(N2, seed=13, dtype=torch.float32)
+    w = torch.stack([wv, wg], dim=1).reshape(2 * N2, K).contiguous()  # interleave rows: 2j = value, 2j+1 = gate
+    b = torch.stack([bv, bg], dim=1).reshape(2 * N2).contiguous()
+    out = ops.linear(a, w, b, glu=glu)
+    val = a.float() @ wv.float().t() + bv
+    gate = a.float() @ wg.float().t() + bg
+    ref = val * (F.gelu(gate) if glu == 1 else F.silu(gate))
+    assert out.shape == (M, N2)
+    close(out, ref, GEMM_ATOL, 1.5e-2, f"glu {glu}")
+
+
+def test_linear_gate_residual_rowadd_fp32(ops):
+    B, S, N, K = 3, 200, 256, 128
+    a, w = rnd(B * S, K, seed=14), rnd(N, K, seed=15, scale=K ** -0.5)
+    bias = rnd(N, seed=16, dtype=torch.float32)
+    gate, radd = rnd(B, N, seed=17, dtype=torch.float32), rnd(B, N, seed=18, dtype=torch.float32)
+    res = rnd(B * S, N, seed=19)
+    out = ops.linear(a, w, bias, residual=res, row_gate=gate, row_add=radd, rows_per_group=S, out_fp32=True)
+    z = a.float() @ w.float().t() + bias + radd.repeat_interleave(S, 0)
+    ref = z * gate.repeat_interleave(S, 0) + res.float()
+    assert out.dtype == torch.float32
+    close(out, ref, 1e-3, 1e-3, "gate/residual/rowadd fp32")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(2, 16, 16, 64, 64, 1), (1, 8, 8, 128, 320, 1), (3, 32, 32, 320, 640, 1),
+                                                   (2, 64, 64, 64, 128, 1), (2, 16, 16, 64, 64, 2), (3, 32, 32, 320, 320, 2),
+                                                   (1, 128, 128, 64, 32, 1), (2, 32, 32, 320, 4, 1)])
+def test_conv3x3(ops, B, H, W, Cin, Cout, stride):
+    x = rnd(B, H, W, Cin, seed=20)
+    w = rnd(Cout, 3, 3, Cin, seed=21, scale=(9 * Cin) ** -0.5)
+    bias = rnd(Cout, seed=22, dtype=torch.float32)
+    temb = rnd(B, Cout, seed=23, dtype=torch.float32)
+    out = ops.conv3x3(x, w, bias, stride=stride, row_add=temb)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, stride=stride, padding=1)
+    ref = (ref + temb[:, :, None, None]).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    close(out, ref, GEMM_ATOL, GEMM_RTOL, f"conv3x3 {B}x{H}x{W} {Cin}->{Cout} s{stride}")
+
+
+def test_conv3x3_residual(ops):
+    B, H, W, C = 2, 32, 32, 128
+    x, w = rnd(B, H, W, C, seed=24), rnd(C, 3, 3, C, seed=25, scale=(9 * C) ** -0.5)
+    res = rnd(B, H, W, C, seed=26)
+    out = ops.conv3x3(x, w, None, residual=res, out_scale=0.5)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), None, padding=1).permute(0, 2, 3, 1)
+    close(out, (ref + res.float()) * 0.5, GEMM_ATOL, GEMM_RTOL, "conv residual")
+
+
+def test_conv_small_cin(ops):
+    B, H, W, Cin, Cout = 2, 32, 32, 4, 320
+    x = rnd(B, H, W, Cin, seed=27, dtype=torch.float32)
+    w, bias = rnd(Cout, 3, 3, Cin, seed=28, scale=0.2), rnd(Cout, seed=29, dtype=torch.float32)
+    out = ops.conv3x3_small_cin(x, w, bias)
+    xr = x.to(bf16).float()
+    ref = F.conv2d(xr.permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
+    close(out, ref, 1e-2, 1e-2, "conv_in")
+
+
+def ref_sdpa(q, k, v, scale, causal=False, cu=None):
+    # q [B,Sq,Hq,D], k/v [B,Sk,Hkv,D] -> [B,Sq,Hq,D]; fp32 math softmax(q k^T * scale + mask) v
+    B, Sq, Hq, D = q.shape
+    Sk, Hkv = k.shape[1], k.shape[2]
+    qf, kf, vf = q.float().permute(0, 2, 1, 3), k.float().permute(0, 2, 1, 3), v.float().permute(0, 2, 1, 3)
+    kf, vf = kf.repeat_interleave(Hq // Hkv, 1), vf.repeat_interleave(Hq // Hkv, 1)
+    s = qf @ kf.transpose(-1, -2) * scale
+    mask = torch.zeros(Sq, Sk, device=q.device)
+    if causal:
+        i = torch.arange(Sq, device=q.device)[:, None] + (Sk - Sq)
+        mask = mask.masked_fill(torch.arange(Sk, device=q.device)[None, :] > i, float("-inf"))
+    if cu is not None:
+        seg = torch.zeros(Sq, dtype=torch.long, device=q.device)
+        for i in range(len(cu) - 1):
+            seg[cu[i]:cu[i + 1]] = i
+        mask = mask.masked_fill(seg[:, None] != seg[None, :], float("-inf"))
+    p = torch.softmax(s + mask, -1)
+    return (p @ vf).permute(0, 2, 1, 3)
+
+
+# P is rounded to bf16 before the PV product and the output is bf16: 2^-8 relative on O(1) values.
+ATT_ATOL, ATT_RTOL = 1.5e-2, 2e-2
+
+
+@pytest.mark.parametrize("B,Sq,Sk,Hq,Hkv,D,causal", [
+    (2, 128, 128, 2, 2, 64, False), (1, 256, 384, 3, 3, 64, False), (2, 1024, 1024, 4, 4, 64, False),
+    (2, 200, 77, 5, 5, 64, False), (1, 4250, 4250, 2, 2, 64, False), (2, 128, 128, 2, 2, 128, False),
+    (1, 768, 768, 4, 2, 128, True), (2, 300, 300, 2, 1, 128, True), (1, 64, 64, 8, 8, 64, False),
+])
+def test_sdpa(ops, B, Sq, Sk, Hq, Hkv, D, causal):
+    q, k, v = rnd(B, Sq, Hq, D, seed=30), rnd(B, Sk, Hkv, D, seed=31), rnd(B, Sk, Hkv, D, seed=32)
+    scale = D ** -0.5
+    out = ops.sdpa(q, k, v, scale=scale, causal=causal)
+    ref = ref_sdpa(q, k, v, scale, causal)
+    close(out, ref, ATT_ATOL, ATT_RTOL, f"sdpa B{B} Sq{Sq} Sk{Sk} H{Hq}/{Hkv} D{D} causal={causal}")
+
+
+def test_sdpa_large_logits(ops):
+    # large |q.k| exercises the lazy-rescale path (running max grows by more than 2^8 between tiles)
+    B, S, H, D = 1, 512, 2, 64
+    q, k, v = rnd(B, S, H, D, seed=33, scale=4.0), rnd(B, S, H, D, seed=34, scale=4.0), rnd(B, S, H, D, seed=35)
+    out = ops.sdpa(q, k, v, scale=D ** -0.5)
+    close(out, ref_sdpa(q, k, v, D ** -0.5), ATT_ATOL, ATT_RTOL, "sdpa large logits")
+
+
+def test_sdpa_fused_qkv_strides(ops):
+    # q/k/v as strided views into one fused projection buffer [B, S, 3*H*D] (how the UNet calls it)
+    B, S, H, D = 2, 256, 5, 64
+    qkv = rnd(B, S, 3 * H * D, seed=36)
+    q, k, v = (qkv[:, :, i * H * D:(i + 1) * H * D].unflatten(-1, (H, D)) for i in range(3))
+    out = ops.sdpa(q, k, v)
+    close(out, ref_sdpa(q, k, v, D ** -0.5), ATT_ATOL, ATT_RTOL, "sdpa strided")
+
+
+def test_sdpa_varlen(ops):
+    H, D = 4, 128
+    lens = [1024, 200, 77, 384]
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    T = cu[-1]
+    q, k, v = rnd(1, T, H, D, seed=37), rnd(1, T, H, D, seed=38), rnd(1, T, H, D, seed=39)
+    cu_t = torch.tensor(cu, dtype=torch.int32, device="cuda")
+    out = ops.sdpa(q, k, v, cu_seqlens=cu_t)
+    ref = ref_sdpa(q, k, v, D ** -0.5, cu=cu)
+    close(out, ref, ATT_ATOL, ATT_RTOL, "sdpa varlen")
+
+
+@pytest.mark.parametrize("B,HW,C1,C2,silu", [(2, 64, 320, 0, True), (3, 1024, 640, 0, False), (2, 256, 1280, 640, True),
+                                             (1, 4096, 320, 320, True), (2, 100, 32, 0, True), (2, 64, 1280, 1280, True)])
+def test_groupnorm(ops, B, HW, C1, C2, silu):
+    x1 = rnd(B, HW, C1, seed=40) * 2 + 0.5
+    x2 = None if C2 == 0 else rnd(B, HW, C2, seed=41)
+    C = C1 + C2
+    gamma, beta = rnd(C, seed=42, dtype=torch.float32), rnd(C, seed=43, dtype=torch.float32)
+    x1 = x1.to(bf16)
+    out = ops.groupnorm_nhwc(x1, gamma, beta, x2=x2, groups=32, eps=1e-5, silu=silu)
+    xc = x1 if x2 is None else torch.cat([x1, x2], -1)
+    ref = F.group_norm(xc.float().permute(0, 2, 1), 32, gamma, beta, 1e-5).permute(0, 2, 1)
+    if silu:
+        ref = F.silu(ref)
+    close(out, ref, 2e-2, 1e-2, f"groupnorm {B}x{HW}x{C1}+{C2}")
+
+
+@pytest.mark.parametrize("M,N", [(77, 320), (4096, 640), (1000, 1280), (616, 1536), (33, 3584), (5, 8192), (64, 64)])
+def test_layernorm_affine(ops, M, N):
+    x = rnd(M, N, seed=44) + 0.3
+    x = x.to(bf16)
+    w, b = rnd(N, seed=45, dtype=torch.float32), rnd(N, seed=46, dtype=torch.float32)
+    out = ops.layernorm(x, w, b, eps=1e-5)
+    close(out, F.layer_norm(x.float(), (N,), w, b, 1e-5), 2e-2, 1e-2, f"layernorm {M}x{N}")
+
+
+def test_layernorm_adaln_fused(ops):
+    # the reference Triton op fused_adaLN_scale_residual (triton_ops.py:790-798): resi = x + gate*mha; y = LN(resi)*(1+scale)+shift
+    B, S, N = 3, 154, 1536
+    x, mha = rnd(B, S, N, seed=47), rnd(B, S, N, seed=48)
+    gate, scale, shift = (rnd(B, N, seed=s, dtype=torch.float32) for s in (49, 50, 51))
+    resid, y = ops.layernorm(x, None, None, eps=1e-6, delta=mha, gate=gate, scale=scale, shift=shift, rows_per_group=S,
+                             want_resid=True)
+    r_ref = x.float() + gate[:, None] * mha.float()
+    close(resid, r_ref, 2e-2, 1e-2, "adaln resid")
+    r_b = r_ref.to(bf16).float()
+    y_ref = F.layer_norm(r_b, (N,), None, None, 1e-6) * (1 + scale[:, None]) + shift[:, None]
+    close(y, y_ref, 3e-2, 1.5e-2, "adaln y")
+
+
+def test_rmsnorm(ops):
+    M, N = 300, 3584
+    x, w = rnd(M, N, seed=52), rnd(N, seed=53, dtype=torch.float32)
+    out = ops.layernorm(x, w, None, eps=1e-6, rms=True)
+    xf = x.float()
+    ref = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).to(bf16).float() * w
+    close(out, ref, 2e-2, 1e-2, "rmsnorm")
+
+
+def test_timestep_embedding(ops):
+    t = torch.tensor([981.0, 1.0, 481.0, 0.0], device="cuda")
+    for dim, flip, shift in [(320, True, 0.0), (256, True, 0.0), (256, False, 1.0)]:
+        out = ops.timestep_embedding(t, dim, flip_sin_to_cos=flip, downscale_freq_shift=shift, out_dtype=torch.float32)
+        half = dim // 2
+        exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32, device="cuda") / (half - shift)
+        emb = t[:, None] * torch.exp(exponent)[None]
+        ref = torch.cat([torch.sin(emb), torch.cos(emb)], -1)
+        if flip:
+            ref = torch.cat([ref[:, half:], ref[:, :half]], -1)
+        close(out, ref, 2e-4, 0, f"timestep embedding {dim}")
+
+
+def test_elementwise_misc(ops):
+    x = rnd(2, 8, 8, 64, seed=54)
+    up = ops.upsample_nearest2x(x)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), ref)
+    y = rnd(2, 8, 8, 32, seed=55)
+    assert torch.equal(ops.concat_channels(x, y), torch.cat([x, y], -1))
+    lat = rnd(2, 4, 16, 16, seed=56, dtype=torch.float32)
+    nhwc = ops.nchw_to_nhwc(lat)
+    assert torch.equal(nhwc, lat.permute(0, 2, 3, 1).to(bf16))
+    back = ops.nhwc_to_nchw(nhwc)
+    assert torch.equal(back, lat.to(bf16).float())
+    for act, fn in [(1, F.silu), (2, F.gelu)]:
+        a = rnd(1000, seed=57, dtype=torch.float32)
+        close(ops.activation(a, act), fn(a), 1e-5, 1e-5, "activation")
+    assert torch.equal(ops.cast(lat, bf16), lat.to(bf16))
+
+
+def test_ddim_step_bit_exact(ops):
+    # fp32 inputs, same expression order as scheduling_ddim.py:420-457 -> bit-identical to the CPU evaluation
+    g = torch.Generator().manual_seed(58)
+    x, eu, ec = (torch.randn(2, 4, 32, 32, generator=g) for _ in range(3))
+    sa_t, sb_t, sa_p, sb_p = (torch.tensor(v, dtype=torch.float32) for v in (0.0413, 0.99915, 0.2213, 0.9752))
+    gs = 5.0
+    eps = eu + gs * (ec - eu)
+    x0 = (x - sb_t * eps) / sa_t
+    ref = sa_p * x0 + sb_p * eps
+    out = ops.ddim_step(eu.cuda(), ec.cuda(), gs, x.cuda(), sa_t.item(), sb_t.item(), sa_p.item(), sb_p.item())
+    assert torch.equal(out.cpu(), ref)
+    ref2 = sa_p * ((x - sb_t * eu) / sa_t) + sb_p * eu
+    out2 = ops.ddim_step(eu.cuda(), None, 0.0, x.cuda(), sa_t.item(), sb_t.item(), sa_p.item(), sb_p.item())
+    assert torch.equal(out2.cpu(), ref2)
+    dt = torch.tensor(-0.0371, dtype=torch.float32)
+    out3 = ops.euler_step(eu.cuda(), None, 0.0, x.cuda(), dt.item())
+    assert torch.equal(out3.cpu(), x + dt * eu)
+
+
+def test_rope(ops):
+    T, H, D = 50, 4, 80
+    x = rnd(T, H, 128, seed=59)
+    ang = torch.rand(T, D // 2, generator=torch.Generator().manual_seed(60)).cuda() * 6
+    cos, sin = torch.cat([ang.cos(), ang.cos()], -1).contiguous(), torch.cat([ang.sin(), ang.sin()], -1).contiguous()
+    xr = x.clone()
+    ops.rope_inplace(xr, cos, sin, rot_dim=D)
+    xf = x.float()[..., :D]
+    rot = torch.cat([-xf[..., D // 2:], xf[..., :D // 2]], -1)
+    ref = xf * cos[:, None] + rot * sin[:, None]
+    close(xr[..., :D], ref, 2e-2, 1e-2, "rope")
+    assert torch.equal(xr[..., D:], x[..., D:])
