@@ -149,9 +149,11 @@ int b200mix_ddim_step(const void* eps_u, const void* eps_c, int32_t eps_fp32, fl
                       float* x_prev, int64_t n, float sqrt_alpha_t, float sqrt_beta_t, float sqrt_alpha_prev,
                       float sqrt_beta_prev, void* stream);
 
-/* FlowMatchEuler step (scheduling_flow_match_euler_discrete.py:244-275): x_prev = x + dt * v, fp32 state. */
+/* FlowMatchEuler step (scheduling_flow_match_euler_discrete.py:244-275, s_churn = 0), fp32 state, same operation
+ * order as the reference: denoised = x - v*sigma; derivative = (x - denoised)/sigma; x_prev = x + derivative*dt
+ * with dt = sigma_next - sigma computed in fp32 on the host. */
 int b200mix_euler_step(const void* v_u, const void* v_c, int32_t v_fp32, float guidance, const float* x, float* x_prev,
-                       int64_t n, float dt, void* stream);
+                       int64_t n, float sigma, float dt, void* stream);
 
 /* fp32 <-> bf16 casts (round-to-nearest-even). */
 int b200mix_cast(const void* x, void* y, int64_t n, int32_t x_fp32, int32_t y_fp32, void* stream);

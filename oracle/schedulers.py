@@ -1,0 +1,196 @@
+"""ORACLE (test infrastructure, not product code): CPU restatement of the two schedulers on the hot path,
+DDIMScheduler (ppdiffusers/schedulers/scheduling_ddim.py:131-475) and FlowMatchEulerDiscreteScheduler
+(ppdiffusers/schedulers/scheduling_flow_match_euler_discrete.py:44-282), with torch fp32 tensors standing in for
+paddle fp32 tensors (0-d fp32 tensor ** 0.5 etc.).
+
+Pinned: every RNG-free golden of ppdiffusers/tests/schedulers/test_scheduler_ddim.py (timesteps :68, variances
+:116-126, full-loop sums :128-190) is asserted in tests/test_oracle_goldens.py.
+"""
+import math
+
+import numpy as np
+import torch
+
+
+def linspace_f32(start, end, steps):
+    """fp32 linspace evaluated the way the CPU kernels of Paddle and torch define it: step = (end-start)/(steps-1) in
+    fp32; element i is start + step*i in the first half and end - step*(steps-1-i) in the second half. Written out
+    explicitly (rather than calling torch.linspace, whose vectorised CPU kernel re-bases every 8/16 lanes) so that
+    the value of every beta is defined by this file alone."""
+    start, end = torch.tensor(start, dtype=torch.float32), torch.tensor(end, dtype=torch.float32)
+    step = (end - start) / torch.tensor(steps - 1, dtype=torch.float32)
+    i = torch.arange(steps, dtype=torch.float32)
+    lo = start + step * i
+    hi = end - step * (torch.tensor(steps - 1, dtype=torch.float32) - i)
+    return torch.where(torch.arange(steps) < steps // 2, lo, hi)
+
+
+def pow_half(t):
+    """`t ** 0.5` on an fp32 tensor the way Paddle's CPU pow kernel evaluates it (std::pow(float, 0.5f), i.e. the
+    correctly rounded square root). torch's CPU `** 0.5` / sqrt on fp32 is NOT correctly rounded (e.g.
+    0.33933258**0.5 -> 0.58252257 instead of 0.58252263), so numpy's IEEE sqrt is used instead."""
+    a = np.sqrt(np.asarray(t.detach().numpy(), dtype=np.float32), dtype=np.float32)
+    return torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).reshape(t.shape)
+
+
+def cumprod_f32(x):
+    """Running product with an fp32 accumulator (out[i] = fl32(out[i-1] * x[i])), the definition of an fp32 cumprod.
+    Spelled out because torch's CPU cumprod accumulates in double and rounds each output, which differs in the last
+    bit from a true fp32 scan for about a third of the 1000 alphas."""
+    out = torch.empty_like(x)
+    acc = torch.tensor(1.0, dtype=torch.float32)
+    for i in range(x.numel()):
+        acc = acc * x[i]
+        out[i] = acc
+    return out
+
+
+def betas_for_alpha_bar(num_diffusion_timesteps, max_beta=0.999):
+    """scheduling_ddim.py:52-93 (cosine)."""
+    def alpha_bar_fn(t):
+        return math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2
+    betas = []
+    for i in range(num_diffusion_timesteps):
+        t1 = i / num_diffusion_timesteps
+        t2 = (i + 1) / num_diffusion_timesteps
+        betas.append(min(1 - alpha_bar_fn(t2) / alpha_bar_fn(t1), max_beta))
+    return torch.tensor(betas, dtype=torch.float32)
+
+
+class DDIMScheduler:
+    order = 1
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                 clip_sample=True, set_alpha_to_one=True, steps_offset=0, prediction_type="epsilon",
+                 clip_sample_range=1.0, timestep_spacing="leading"):
+        self.num_train_timesteps = num_train_timesteps
+        self.clip_sample, self.clip_sample_range = clip_sample, clip_sample_range
+        self.steps_offset, self.prediction_type, self.timestep_spacing = steps_offset, prediction_type, timestep_spacing
+        if beta_schedule == "linear":  # :208-209
+            self.betas = linspace_f32(beta_start, beta_end, num_train_timesteps)
+        elif beta_schedule == "scaled_linear":  # :210-214
+            self.betas = linspace_f32(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps) ** 2
+        elif beta_schedule == "squaredcos_cap_v2":
+            self.betas = betas_for_alpha_bar(num_train_timesteps)
+        else:
+            raise NotImplementedError(beta_schedule)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = cumprod_f32(self.alphas)  # :225
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]  # :231
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps = None
+        self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
+
+    def scale_model_input(self, sample, timestep=None):  # :240-255
+        return sample
+
+    def _get_variance(self, timestep, prev_timestep):  # :257-265
+        alpha_prod_t = self.alphas_cumprod[timestep]
+        alpha_prod_t_prev = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        beta_prod_t = 1 - alpha_prod_t
+        beta_prod_t_prev = 1 - alpha_prod_t_prev
+        return (beta_prod_t_prev / beta_prod_t) * (1 - alpha_prod_t / alpha_prod_t_prev)
+
+    def set_timesteps(self, num_inference_steps):  # :305-348
+        self.num_inference_steps = num_inference_steps
+        if self.timestep_spacing == "linspace":
+            timesteps = np.linspace(0, self.num_train_timesteps - 1, num_inference_steps).round()[::-1].copy().astype(np.int64)
+        elif self.timestep_spacing == "leading":
+            step_ratio = self.num_train_timesteps // num_inference_steps
+            timesteps = (np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(np.int64)
+            timesteps += self.steps_offset
+        elif self.timestep_spacing == "trailing":
+            step_ratio = self.num_train_timesteps / num_inference_steps
+            timesteps = np.round(np.arange(self.num_train_timesteps, 0, -step_ratio)).astype(np.int64)
+            timesteps -= 1
+        else:
+            raise ValueError(self.timestep_spacing)
+        self.timesteps = torch.from_numpy(timesteps)
+
+    def step(self, model_output, timestep, sample, eta=0.0):  # :350-475
+        timestep = int(timestep)
+        prev_timestep = timestep - self.num_train_timesteps // self.num_inference_steps
+        alpha_prod_t = self.alphas_cumprod[timestep]
+        alpha_prod_t_prev = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        beta_prod_t = 1 - alpha_prod_t
+        if self.prediction_type == "epsilon":
+            pred_original_sample = (sample - pow_half(beta_prod_t) * model_output) / pow_half(alpha_prod_t)
+            pred_epsilon = model_output
+        elif self.prediction_type == "sample":
+            pred_original_sample = model_output
+            pred_epsilon = (sample - pow_half(alpha_prod_t) * pred_original_sample) / pow_half(beta_prod_t)
+        elif self.prediction_type == "v_prediction":
+            pred_original_sample = (pow_half(alpha_prod_t)) * sample - (pow_half(beta_prod_t)) * model_output
+            pred_epsilon = (pow_half(alpha_prod_t)) * model_output + (pow_half(beta_prod_t)) * sample
+        else:
+            raise ValueError(self.prediction_type)
+        if self.clip_sample:
+            pred_original_sample = pred_original_sample.clip(-self.clip_sample_range, self.clip_sample_range)
+        variance = self._get_variance(timestep, prev_timestep)
+        std_dev_t = eta * pow_half(variance)
+        pred_sample_direction = pow_half(1 - alpha_prod_t_prev - std_dev_t ** 2) * pred_epsilon
+        prev_sample = pow_half(alpha_prod_t_prev) * pred_original_sample + pred_sample_direction
+        assert eta == 0.0, "oracle covers the deterministic path (eta = 0) used by the pipelines"
+        return prev_sample
+
+    def step_scalars(self, timestep):
+        """The four fp32 scalars of the eta=0 epsilon step, each computed exactly as step() computes it."""
+        timestep = int(timestep)
+        prev_timestep = timestep - self.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[timestep]
+        a_p = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        b_t = 1 - a_t
+        std = 0.0 * pow_half(self._get_variance(timestep, prev_timestep))
+        return pow_half(a_t).item(), pow_half(b_t).item(), pow_half(a_p).item(), pow_half(1 - a_p - std ** 2).item()
+
+    def add_noise(self, original_samples, noise, timesteps):  # :478-500
+        sqrt_alpha_prod = pow_half(self.alphas_cumprod[timesteps])
+        sqrt_one_minus = pow_half(1 - self.alphas_cumprod[timesteps])
+        while sqrt_alpha_prod.ndim < original_samples.ndim:
+            sqrt_alpha_prod = sqrt_alpha_prod.unsqueeze(-1)
+            sqrt_one_minus = sqrt_one_minus.unsqueeze(-1)
+        return sqrt_alpha_prod * original_samples + sqrt_one_minus * noise
+
+
+class FlowMatchEulerDiscreteScheduler:
+    """scheduling_flow_match_euler_discrete.py: __init__ :64-83, set_timesteps :140-163, step :187-282."""
+    order = 1
+
+    def __init__(self, num_train_timesteps=1000, shift=1.0):
+        self.num_train_timesteps, self.shift = num_train_timesteps, shift
+        timesteps = np.linspace(1, num_train_timesteps, num_train_timesteps, dtype=np.float32)[::-1].copy()
+        timesteps = torch.from_numpy(timesteps).to(torch.float32)
+        sigmas = timesteps / num_train_timesteps
+        sigmas = shift * sigmas / (1 + (shift - 1) * sigmas)
+        self.timesteps = sigmas * num_train_timesteps
+        self.sigmas = sigmas
+        self.sigma_min, self.sigma_max = self.sigmas[-1].item(), self.sigmas[0].item()
+        self._step_index = None
+
+    def _sigma_to_t(self, sigma):
+        return sigma * self.num_train_timesteps
+
+    def set_timesteps(self, num_inference_steps):
+        self.num_inference_steps = num_inference_steps
+        timesteps = np.linspace(self._sigma_to_t(self.sigma_max), self._sigma_to_t(self.sigma_min), num_inference_steps)
+        sigmas = timesteps / self.num_train_timesteps
+        sigmas = self.shift * sigmas / (1 + (self.shift - 1) * sigmas)
+        sigmas = torch.from_numpy(sigmas).to(torch.float32)
+        self.timesteps = sigmas * self.num_train_timesteps
+        self.sigmas = torch.cat([sigmas, torch.zeros(1)])
+        self._step_index = None
+
+    def step(self, model_output, timestep, sample):
+        if self._step_index is None:
+            self._step_index = int((self.timesteps == timestep).nonzero()[0].item())
+        sample = sample.to(torch.float32)
+        sigma = self.sigmas[self._step_index]
+        sigma_next = self.sigmas[self._step_index + 1]
+        # :244-275 with s_churn = 0: gamma = 0, sigma_hat = sigma, denoised = sample - model_output*sigma,
+        # derivative = (sample - denoised)/sigma_hat, prev = sample + derivative*(sigma_next - sigma_hat)
+        denoised = sample - model_output * sigma
+        derivative = (sample - denoised) / sigma
+        dt = sigma_next - sigma
+        prev_sample = sample + derivative * dt
+        self._step_index += 1
+        return prev_sample.to(model_output.dtype)

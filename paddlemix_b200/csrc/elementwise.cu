@@ -186,14 +186,19 @@ __global__ void ddim_step_kernel(const void* __restrict__ eps_u, const void* __r
 }
 
 __global__ void euler_step_kernel(const void* __restrict__ v_u, const void* __restrict__ v_c, int v_fp32, float guidance,
-                                  const float* __restrict__ x, float* __restrict__ x_prev, long long n, float dt) {
+                                  const float* __restrict__ x, float* __restrict__ x_prev, long long n, float sigma,
+                                  float dt) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = load_any(v_u, i, v_fp32);
     if (v_c) {
       const float vc = load_any(v_c, i, v_fp32);
       v = __fadd_rn(v, __fmul_rn(guidance, __fsub_rn(vc, v)));
     }
-    x_prev[i] = __fadd_rn(x[i], __fmul_rn(dt, v));
+    // scheduling_flow_match_euler_discrete.py:262-270: denoised = x - v*sigma; derivative = (x - denoised)/sigma_hat
+    const float xi = x[i];
+    const float den = __fsub_rn(xi, __fmul_rn(v, sigma));
+    const float der = __fdiv_rn(__fsub_rn(xi, den), sigma);
+    x_prev[i] = __fadd_rn(xi, __fmul_rn(der, dt));
   }
 }
 
@@ -334,10 +339,10 @@ extern "C" int b200mix_ddim_step(const void* eps_u, const void* eps_c, int32_t e
 }
 
 extern "C" int b200mix_euler_step(const void* v_u, const void* v_c, int32_t v_fp32, float guidance, const float* x,
-                                  float* x_prev, int64_t n, float dt, void* stream) {
+                                  float* x_prev, int64_t n, float sigma, float dt, void* stream) {
   if (int rc = ensure_device()) return rc;
   B200_CHECK_ARG(v_u && x && x_prev && n > 0, "euler_step: bad arguments");
-  euler_step_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(v_u, v_c, v_fp32, guidance, x, x_prev, n, dt);
+  euler_step_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(v_u, v_c, v_fp32, guidance, x, x_prev, n, sigma, dt);
   B200_LAUNCH_CHECK();
   return 0;
 }

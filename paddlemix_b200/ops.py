@@ -259,12 +259,12 @@ def ddim_step(eps_u, eps_c, guidance, x, sa_t, sb_t, sa_p, sb_p, out=None):
     return out
 
 
-def euler_step(v_u, v_c, guidance, x, dt, out=None):
+def euler_step(v_u, v_c, guidance, x, sigma, dt, out=None):
     _req(x, torch.float32, "x")
     if out is None:
         out = torch.empty_like(x)
     check(lib.b200mix_euler_step(_p(v_u), _p(v_c), 1 if v_u.dtype == torch.float32 else 0, float(guidance), _p(x),
-                                 _p(out), x.numel(), float(dt), _stream()), "b200mix_euler_step")
+                                 _p(out), x.numel(), float(sigma), float(dt), _stream()), "b200mix_euler_step")
     _count()
     return out
 

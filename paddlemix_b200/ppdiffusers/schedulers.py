@@ -1,0 +1,168 @@
+"""Schedulers on the hot path, mirroring ppdiffusers' interface (set_timesteps / scale_model_input / step).
+
+The index and scalar math runs on the host in numpy float32, operation by operation as the reference does on 0-d
+fp32 tensors (ppdiffusers/schedulers/scheduling_ddim.py:205-238, 305-348, 410-457;
+scheduling_flow_match_euler_discrete.py:64-83, 140-163, 244-275); the elementwise update of the latent runs in one
+fused CUDA kernel (b200mix_ddim_step / b200mix_euler_step) that also folds in the classifier-free-guidance combine.
+tests/test_schedulers.py checks the host scalars bit-for-bit against the oracle.
+"""
+import math
+from typing import Optional
+
+import numpy as np
+
+f32 = np.float32
+
+
+def _betas_for_alpha_bar(n, max_beta=0.999):
+    def alpha_bar(t):
+        return math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2
+    return np.array([min(1 - alpha_bar((i + 1) / n) / alpha_bar(i / n), max_beta) for i in range(n)], dtype=f32)
+
+
+class DDIMScheduler:
+    """ppdiffusers.DDIMScheduler (scheduling_ddim.py:131) restricted to the deterministic sampling path."""
+
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.0001, beta_end: float = 0.02,
+                 beta_schedule: str = "linear", clip_sample: bool = True, set_alpha_to_one: bool = True,
+                 steps_offset: int = 0, prediction_type: str = "epsilon", timestep_spacing: str = "leading"):
+        if beta_schedule == "linear":
+            self.betas = _linspace_f32(beta_start, beta_end, num_train_timesteps)
+        elif beta_schedule == "scaled_linear":
+            self.betas = _linspace_f32(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps) ** 2
+        elif beta_schedule == "squaredcos_cap_v2":
+            self.betas = _betas_for_alpha_bar(num_train_timesteps)
+        else:
+            raise NotImplementedError(f"{beta_schedule} does is not implemented for {self.__class__}")
+        self.alphas = (f32(1.0) - self.betas).astype(f32)
+        self.alphas_cumprod = _cumprod_f32(self.alphas)
+        self.final_alpha_cumprod = f32(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.num_train_timesteps = num_train_timesteps
+        self.clip_sample = clip_sample
+        self.steps_offset = steps_offset
+        self.prediction_type = prediction_type
+        self.timestep_spacing = timestep_spacing
+        self.num_inference_steps: Optional[int] = None
+        self.timesteps = np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64)
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def set_timesteps(self, num_inference_steps: int):
+        if num_inference_steps > self.num_train_timesteps:
+            raise ValueError(
+                f"`num_inference_steps`: {num_inference_steps} cannot be larger than `self.config.train_timesteps`:"
+                f" {self.num_train_timesteps} as the unet model trained with this scheduler can only handle"
+                f" maximal {self.num_train_timesteps} timesteps.")
+        self.num_inference_steps = num_inference_steps
+        if self.timestep_spacing == "linspace":
+            t = np.linspace(0, self.num_train_timesteps - 1, num_inference_steps).round()[::-1].copy().astype(np.int64)
+        elif self.timestep_spacing == "leading":
+            step_ratio = self.num_train_timesteps // num_inference_steps
+            t = (np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(np.int64)
+            t += self.steps_offset
+        elif self.timestep_spacing == "trailing":
+            step_ratio = self.num_train_timesteps / num_inference_steps
+            t = np.round(np.arange(self.num_train_timesteps, 0, -step_ratio)).astype(np.int64)
+            t -= 1
+        else:
+            raise ValueError(f"{self.timestep_spacing} is not supported. Please make sure to choose one of 'leading' "
+                             "or 'trailing'.")
+        self.timesteps = t
+
+    def _get_variance(self, timestep, prev_timestep):
+        a_t = self.alphas_cumprod[timestep]
+        a_p = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        b_t, b_p = f32(1) - a_t, f32(1) - a_p
+        return f32(f32(b_p / b_t) * f32(f32(1) - f32(a_t / a_p)))
+
+    def step_scalars(self, timestep: int):
+        """(sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev-std^2)) as fp32, eta = 0 (:410-457)."""
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the "
+                             "scheduler")
+        timestep = int(timestep)
+        prev_timestep = timestep - self.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[timestep]
+        a_p = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        b_t = f32(f32(1) - a_t)
+        var = self._get_variance(timestep, prev_timestep)
+        std = f32(f32(0.0) * np.sqrt(var, dtype=f32))
+        dir_coef = np.sqrt(f32(f32(f32(1) - a_p) - f32(std * std)), dtype=f32)
+        return float(np.sqrt(a_t, dtype=f32)), float(np.sqrt(b_t, dtype=f32)), float(np.sqrt(a_p, dtype=f32)), float(dir_coef)
+
+    def step(self, model_output, timestep, sample, eta: float = 0.0, model_output_cond=None, guidance_scale=0.0,
+             out=None):
+        """sample, result: fp32 CUDA tensors; model_output: bf16/fp32 CUDA tensor of the same numel (any layout that
+        matches `sample` elementwise). With model_output_cond the CFG combine is fused into the same kernel."""
+        if eta != 0.0 or self.prediction_type != "epsilon" or self.clip_sample:
+            raise NotImplementedError("b200mix DDIM step covers eta=0, epsilon prediction, clip_sample=False "
+                                      "(the Stable Diffusion sampling configuration)")
+        from .. import ops
+        sa_t, sb_t, sa_p, sb_p = self.step_scalars(timestep)
+        return ops.ddim_step(model_output, model_output_cond, guidance_scale, sample, sa_t, sb_t, sa_p, sb_p, out=out)
+
+
+def _linspace_f32(start, end, n):
+    """float32 linspace as the CPU kernels of Paddle / torch define it: start + i*step for the first half,
+    end - (n-1-i)*step for the second half, step = (end-start)/(n-1), everything in fp32."""
+    start, end = f32(start), f32(end)
+    step = f32((end - start) / f32(n - 1))
+    i = np.arange(n)
+    half = n // 2
+    lo = (start + step * i.astype(f32)).astype(f32)
+    hi = (end - step * (n - 1 - i).astype(f32)).astype(f32)
+    return np.where(i < half, lo, hi).astype(f32)
+
+
+def _cumprod_f32(a):
+    out = np.empty_like(a, dtype=f32)
+    acc = f32(1.0)
+    for i, v in enumerate(a):
+        acc = f32(acc * v)
+        out[i] = acc
+    return out
+
+
+class FlowMatchEulerDiscreteScheduler:
+    """ppdiffusers.FlowMatchEulerDiscreteScheduler (scheduling_flow_match_euler_discrete.py:44)."""
+
+    order = 1
+
+    def __init__(self, num_train_timesteps: int = 1000, shift: float = 1.0):
+        self.num_train_timesteps, self.shift = num_train_timesteps, shift
+        t = np.linspace(1, num_train_timesteps, num_train_timesteps, dtype=f32)[::-1].copy()
+        sigmas = (t / f32(num_train_timesteps)).astype(f32)
+        sigmas = (f32(shift) * sigmas / (f32(1) + f32(shift - 1) * sigmas)).astype(f32)
+        self.timesteps = (sigmas * f32(num_train_timesteps)).astype(f32)
+        self.sigmas = sigmas
+        self.sigma_min, self.sigma_max = float(sigmas[-1]), float(sigmas[0])
+        self._step_index = None
+
+    def set_timesteps(self, num_inference_steps: int):
+        self.num_inference_steps = num_inference_steps
+        t = np.linspace(self.sigma_max * self.num_train_timesteps, self.sigma_min * self.num_train_timesteps,
+                        num_inference_steps)
+        sigmas = t / self.num_train_timesteps
+        sigmas = self.shift * sigmas / (1 + (self.shift - 1) * sigmas)
+        sigmas = sigmas.astype(f32)
+        self.timesteps = (sigmas * f32(self.num_train_timesteps)).astype(f32)
+        self.sigmas = np.concatenate([sigmas, np.zeros(1, dtype=f32)])
+        self._step_index = None
+
+    def step_scalars(self, timestep):
+        if self._step_index is None:
+            idx = np.nonzero(self.timesteps == f32(timestep))[0]
+            self._step_index = int(idx[0])
+        sigma = self.sigmas[self._step_index]
+        dt = f32(self.sigmas[self._step_index + 1] - sigma)
+        self._step_index += 1
+        return float(sigma), float(dt)
+
+    def step(self, model_output, timestep, sample, model_output_cond=None, guidance_scale=0.0, out=None):
+        from .. import ops
+        sigma, dt = self.step_scalars(timestep)
+        return ops.euler_step(model_output, model_output_cond, guidance_scale, sample, sigma, dt, out=out)

@@ -293,9 +293,11 @@ def test_ddim_step_bit_exact(ops):
     ref2 = sa_p * ((x - sb_t * eu) / sa_t) + sb_p * eu
     out2 = ops.ddim_step(eu.cuda(), None, 0.0, x.cuda(), sa_t.item(), sb_t.item(), sa_p.item(), sb_p.item())
     assert torch.equal(out2.cpu(), ref2)
-    dt = torch.tensor(-0.0371, dtype=torch.float32)
-    out3 = ops.euler_step(eu.cuda(), None, 0.0, x.cuda(), dt.item())
-    assert torch.equal(out3.cpu(), x + dt * eu)
+    sigma, sigma_next = torch.tensor(0.8731, dtype=torch.float32), torch.tensor(0.8360, dtype=torch.float32)
+    dt = sigma_next - sigma
+    out3 = ops.euler_step(eu.cuda(), None, 0.0, x.cuda(), sigma.item(), dt.item())
+    den = x - eu * sigma
+    assert torch.equal(out3.cpu(), x + (x - den) / sigma * dt)
 
 
 def test_rope(ops):

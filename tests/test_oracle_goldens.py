@@ -1,0 +1,101 @@
+"""Pins the oracle against every RNG-free golden the reference's own tests hold for this path:
+ppdiffusers/tests/schedulers/test_scheduler_ddim.py:68,116-190 (fixtures tests/schedulers/test_schedulers.py:261-303)
+and ppdiffusers/tests/models/test_layers_utils.py:32-115."""
+import numpy as np
+import torch
+
+from oracle.schedulers import DDIMScheduler
+from oracle.unet import get_timestep_embedding
+
+
+def dummy_sample_deter():  # test_schedulers.py:277-290
+    n = 4 * 3 * 8 * 8
+    s = torch.arange(n).reshape(3, 8, 8, 4) / n
+    return s.permute(3, 0, 1, 2)
+
+
+def dummy_noise_deter():  # :261-275
+    n = 4 * 3 * 8 * 8
+    s = torch.arange(n).flip(-1).reshape(3, 8, 8, 4) / n
+    return s.permute(3, 0, 1, 2)
+
+
+def dummy_model(sample, t):  # :295-303
+    return sample * t / (t + 1)
+
+
+def cfg(**kw):  # test_scheduler_ddim.py:25-35
+    c = dict(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", clip_sample=True)
+    c.update(kw)
+    return c
+
+
+def full_loop(**kw):  # :37-53
+    sch = DDIMScheduler(**cfg(**kw))
+    sample = dummy_sample_deter()
+    sch.set_timesteps(10)
+    for t in sch.timesteps:
+        sample = sch.step(dummy_model(sample, t), t, sample, 0.0)
+    return sample
+
+
+def test_steps_offset_golden():  # :61-68
+    sch = DDIMScheduler(**cfg(steps_offset=1))
+    sch.set_timesteps(5)
+    assert sch.timesteps.tolist() == [801, 601, 401, 201, 1]
+
+
+def test_variance_goldens():  # :116-126
+    sch = DDIMScheduler(**cfg())
+    for (t, p), v in {(0, 0): 0.0, (420, 400): 0.14771, (980, 960): 0.32460, (487, 486): 0.00979, (999, 998): 0.02}.items():
+        assert abs(sch._get_variance(t, p).item() - v) < 1e-5
+
+
+def test_full_loop_goldens():  # :128-162
+    for kw, (s, m) in [({}, (172.0067, 0.223967)), (dict(prediction_type="v_prediction"), (52.5302, 0.0684)),
+                       (dict(set_alpha_to_one=True, beta_start=0.01), (149.8295, 0.1951)),
+                       (dict(set_alpha_to_one=False, beta_start=0.01), (149.0784, 0.1941))]:
+        x = full_loop(**kw)
+        assert abs(x.abs().sum().item() - s) < 1e-2, (kw, x.abs().sum().item())
+        assert abs(x.abs().mean().item() - m) < 1e-3
+
+
+def test_full_loop_with_noise_golden():  # :164-190
+    sch = DDIMScheduler(**cfg())
+    sch.set_timesteps(10)
+    timesteps = sch.timesteps[8:]
+    sample = sch.add_noise(dummy_sample_deter(), dummy_noise_deter(), timesteps[:1])
+    for t in timesteps:
+        sample = sch.step(dummy_model(sample, t), t, sample, 0.0)
+    assert abs(sample.abs().sum().item() - 354.5418) < 1e-2
+    assert abs(sample.abs().mean().item() - 0.4616) < 1e-3
+
+
+def test_timestep_embedding_structure():  # test_layers_utils.py:32-52
+    t1 = get_timestep_embedding(torch.arange(16), 256)
+    assert (t1[0, :128] - 0).abs().sum() < 1e-5 and (t1[0, 128:] - 1).abs().sum() < 1e-5
+    assert (t1[:, -1] - 1).abs().sum() < 1e-5
+    grad_mean = np.abs(np.gradient(t1.numpy(), axis=-1)).mean(axis=1)
+    assert (np.diff(grad_mean) > 0).all()
+
+
+def test_timestep_embedding_flags():  # :54-88
+    ts = torch.arange(10)
+    assert torch.allclose(get_timestep_embedding(ts, 16),
+                          get_timestep_embedding(ts, 16, flip_sin_to_cos=False, downscale_freq_shift=1, max_period=10_000), atol=1e-2)
+    t1 = get_timestep_embedding(ts, 16, flip_sin_to_cos=True)
+    t1 = torch.cat([t1[:, 8:], t1[:, :8]], -1)
+    assert torch.allclose(t1, get_timestep_embedding(ts, 16, flip_sin_to_cos=False), 1e-3)
+    c = (get_timestep_embedding(ts, 16, downscale_freq_shift=0) - get_timestep_embedding(ts, 16, downscale_freq_shift=1))[:, 8:]
+    assert (c <= 0).all()
+
+
+def test_sinusoid_hardcoded_goldens():  # :90-115
+    ts = torch.arange(128)
+    t1 = get_timestep_embedding(ts, 64, downscale_freq_shift=1, flip_sin_to_cos=False)
+    t2 = get_timestep_embedding(ts, 64, downscale_freq_shift=0, flip_sin_to_cos=True)
+    t3 = get_timestep_embedding(ts, 64, scale=1000)
+    for t, gold in [(t1, [0.9646, 0.9804, 0.9892, 0.9615, 0.9787, 0.9882, 0.9582, 0.9769, 0.9872]),
+                    (t2, [0.3019, 0.228, 0.1716, 0.3146, 0.2377, 0.179, 0.3272, 0.2474, 0.1864]),
+                    (t3, [-0.9801, -0.9464, -0.9349, -0.3952, 0.8887, -0.9709, 0.5299, -0.2853, -0.9927])]:
+        assert torch.allclose(t[23:26, 47:50].flatten(), torch.tensor(gold), atol=0.01)
