@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+Workload (configs[1]): SD-XL base 1.0 UNet2DConditionModel, batch 8 per GPU, 1024x1024 (latent 128x128), DDIM
+(50-step schedule), bf16, synthetic inputs and random-init weights of the SDXL architecture. One bench "step" = one
+denoising timestep = one UNet forward over the batch + the fused DDIM update. Metric = denoiser-forward latents/s
+(images pushed through one denoiser forward per second, whole job); finished latents/s = that / 50.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1 is launched by `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...`: one rank per GPU,
+images sharded (8 per rank, weights replicated, weak scaling), no per-step communication, one all_gather of the
+finished latents at the end (outside the timed steps, like the reference's pipeline exit).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "denoiser_forward_latents_per_sec_sdxl_1024"
+UNIT = "latents/s"
+SDXL = dict(down_block_types=("DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"),
+            up_block_types=("CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"), block_out_channels=(320, 640, 1280),
+            cross_attention_dim=2048, transformer_layers_per_block=(1, 2, 10), attention_head_dim=(5, 10, 20),
+            use_linear_projection=True, addition_embed_type="text_time", addition_time_embed_dim=256,
+            projection_class_embeddings_input_dim=2816)
+DDIM = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+            set_alpha_to_one=False, steps_offset=1)
+SDXL_TFLOP_PER_SAMPLE = 6.761  # 2*MAC over conv/linear/QK^T/PV, SURVEY.md §8d (oracle.unet.unet_flops reproduces it)
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_forward_time(threads, budget_s=150.0, steps=1, warmup=0):
+    """Times the CPU restatement of the reference's UNet forward (oracle, kind='port'; PaddlePaddle itself is not
+    installable here) on a bounded sample of the workload: ONE image (B=1) of the SDXL 1024^2 forward per step.
+    Falls back to a 512^2 image, rescaled by the FLOP ratio and labelled as such, if one full-size image would not
+    fit the time budget."""
+    import torch
+
+    from oracle import unet as O
+    torch.set_num_threads(threads)
+    cfg = O.UNET_CONFIGS["sdxl"]
+    shapes = O.unet_param_shapes(cfg)
+    g = torch.Generator().manual_seed(1)
+    P = {}
+    for name, shp in shapes.items():  # fast init (values do not matter for timing; dense fp32)
+        P[name] = torch.empty(shp).uniform_(-0.02, 0.02, generator=g)
+    H = 128
+    x = torch.randn(1, 4, H, H, generator=g)
+    ctx = torch.randn(1, 77, 2048, generator=g)
+    added = {"text_embeds": torch.randn(1, 1280, generator=g), "time_ids": torch.tensor([[1024., 1024., 0, 0, 1024., 1024.]])}
+    # probe at 512^2 (1.59 TFLOP) to size the sample
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.unet_forward(cfg, P, x[:, :, :64, :64], 981, ctx, added)
+    probe = time.perf_counter() - t0
+    est_full = probe * (O.unet_flops(cfg, 1, 128, 128, 77) / O.unet_flops(cfg, 1, 64, 64, 77))
+    full = est_full * (steps + warmup) <= budget_s
+    xin = x if full else x[:, :, :64, :64]
+    scale = 1.0 if full else O.unet_flops(cfg, 1, 64, 64, 77) / O.unet_flops(cfg, 1, 128, 128, 77)
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.unet_forward(cfg, P, xin, 981, ctx, added)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.unet_forward(cfg, P, xin, 981, ctx, added)
+        dt = (time.perf_counter() - t0) / steps
+    sample = ("1 image (B=1) SDXL UNet forward at 1024x1024 (latent 128x128), fp32, torch-CPU restatement of the reference"
+              if full else
+              "1 image SDXL UNet forward at 512x512 (latent 64x64), fp32, rescaled to 1024^2 by the FLOP ratio 1.589/6.761 (extrapolated)")
+    return (1.0 / dt) * scale, dt, sample
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores. The reference is pure
+    Python on PaddlePaddle, which cannot be installed offline, so this runs the oracle port (cpu_baseline.kind='port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    value, dt, sample = cpu_reference_forward_time(threads, budget_s=240.0, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SDXL-base UNet2DConditionModel forward, 1024x1024, DDIM timestep (configs[1])",
+                       "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from paddlemix_b200 import ops
+    from paddlemix_b200.ppdiffusers.pipelines import GraphedUNet, all_gather_latents
+    from paddlemix_b200.ppdiffusers.schedulers import DDIMScheduler
+    from paddlemix_b200.ppdiffusers.unet_2d_condition import UNet2DConditionModel
+
+    B, H, L = args.batch, args.height // 8, 77
+    unet = UNet2DConditionModel(**SDXL).init_synthetic_weights(seed=1, device=local)
+    sched = DDIMScheduler(**DDIM)
+    sched.set_timesteps(50)
+    g = torch.Generator().manual_seed(2 + rank)
+    lat_h = torch.randn(B, 4, H, H, generator=g).pin_memory()
+    ctx_h = torch.randn(B, L, 2048, generator=g).to(torch.bfloat16).pin_memory()
+    te_h = torch.randn(B, 1280, generator=g).to(torch.bfloat16).pin_memory()
+    ids_h = torch.tensor([[float(args.height), float(args.height), 0, 0, float(args.height), float(args.height)]] * B).pin_memory()
+    out_h = torch.empty(B, 4, H, H).pin_memory()
+
+    den = GraphedUNet(unet, (B, 4, H, H), (B, L, 2048), {"text_embeds": (B, 1280), "time_ids": (B, 6)})
+    lat = lat_h.to(dev)
+    nxt = torch.empty_like(lat)
+    den(lat, 981.0, ctx_h.to(dev), {"text_embeds": te_h.to(dev), "time_ids": ids_h.to(dev)})
+    timesteps = [int(t) for t in sched.timesteps]
+
+    def step_resident(i, lat, nxt):
+        t = timesteps[i % len(timesteps)]
+        eps = den(lat, float(t))
+        sched.step(eps, t, lat, out=nxt)
+        return nxt, lat
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing: W warm-up, then exactly K steps bracketed by barrier + synchronize ----
+    for i in range(args.warmup):
+        lat, nxt = step_resident(i, lat, nxt)
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = ops.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        lat, nxt = step_resident(args.warmup + i, lat, nxt)
+    e1.record()
+    sync_all()
+    launches = ops.launches() - n0
+    ms = e0.elapsed_time(e1)
+    if sampler:
+        sampler.stop_flag = True
+    finished = all_gather_latents(lat)  # the path's only collective: finished latents of every rank
+    assert finished.shape[0] == B * world
+
+    # ---- end-to-end through the public API with host buffers: H2D of the step's inputs + D2H of its result ----
+    def step_e2e(i):
+        t = timesteps[i % len(timesteps)]
+        x = lat_h.to(dev, non_blocking=True)
+        eps = den(x, float(t), ctx_h.to(dev, non_blocking=True),
+                  {"text_embeds": te_h.to(dev, non_blocking=True), "time_ids": ids_h.to(dev, non_blocking=True)})
+        out = sched.step(eps, t, x)
+        out_h.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the result every step
+
+    for i in range(min(args.warmup, 3)):
+        step_e2e(i)
+    sync_all()
+    k2 = args.steps
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(k2):
+        step_e2e(i)
+    f1.record()
+    sync_all()
+    ms_e2e = max(f0.elapsed_time(f1), 0.0)
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max(ms_e2e, wall_e2e * 0.0 + ms_e2e)
+    h2d = lat_h.numel() * 4 + ctx_h.numel() * 2 + te_h.numel() * 2 + ids_h.numel() * 4
+    d2h = out_h.numel() * 4
+
+    # ---- max over ranks ----
+    tms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = tms.tolist()
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit GEMM): per-launch CUDA events in one eager forward ----
+    roof = None
+    prof = {}
+    if rank == 0:
+        x_nhwc = ops.nchw_to_nhwc(lat)
+        added = {"text_embeds": te_h.to(dev), "time_ids": ids_h.to(dev)}
+        tt = torch.full((B,), 981.0, device=dev)
+        ctx_d = ctx_h.to(dev)
+        unet.forward_nhwc(x_nhwc, tt, ctx_d, added)  # eager warm-up
+        torch.cuda.synchronize(dev)
+        ops.profile_begin()
+        unet.forward_nhwc(x_nhwc, tt, ctx_d, added)
+        prof = ops.profile_end()
+        peak_tf, peak_gbs, how = measured_peaks()
+        ig = prof.get("igemm")
+        if ig:
+            ach = ig["work"] / (ig["ms"] * 1e-3) / 1e12
+            total_ms = sum(v["ms"] for v in prof.values())
+            roof = {"kernel": "igemm_kernel (tcgen05 implicit GEMM: linear + conv3x3)", "bound": "tensor",
+                    "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
+                    "traffic": None, "peak_source": how, "launches_per_step": ig["calls"],
+                    "avg_launch_ms": round(ig["ms"] / ig["calls"], 4), "share_of_step": round(ig["ms"] / total_ms, 3),
+                    "algorithmic_tflop_per_step": round(ig["work"] / 1e12, 2),
+                    "by_kernel_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
+                    "by_kernel_achieved": {k: (round(v["work"] / (v["ms"] * 1e-3) / (1e12 if v["unit"] == "flop" else 1e9), 1),
+                                               "TFLOP/s" if v["unit"] == "flop" else "GB/s") for k, v in prof.items()}}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, dt, sample = cpu_reference_forward_time(os.cpu_count() or 1, budget_s=40.0)
+            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample,
+                   "seconds_per_sample": round(dt, 2)}
+        except Exception as ex:  # the baseline is a report, never a reason to lose the GPU number
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {ex}"}
+
+    value = B * world * args.steps / (ms * 1e-3)
+    e2e = B * world * k2 / (ms_e2e * 1e-3)
+    step_tflop = SDXL_TFLOP_PER_SAMPLE * B * (args.height / 1024.0) ** 2 if args.height == 1024 else None
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "SDXL-base UNet2DConditionModel forward + fused DDIM update per timestep (configs[1])",
+                   "batch_per_gpu": B, "global_batch": B * world, "resolution": f"{args.height}x{args.height}",
+                   "latent": f"{H}x{H}", "scheduler": "DDIM 50 steps (scaled_linear, steps_offset 1)", "cfg": "off (UNet rows = batch)",
+                   "parallelism": f"dp{world} (images sharded, weights replicated, one all_gather of finished latents)",
+                   "weights": "random init, SDXL-base architecture (2.57 B params)", "cuda_graph": True,
+                   "l2": "no explicit flush: 5.1 GB of weights + >10 GB of activations stream per step (>> 126 MB L2)"},
+        "finished_latents_per_sec_50_steps": round(value / 50.0, 4),
+        "model_tflops_per_sec": None if step_tflop is None else round(step_tflop * world / (ms / args.steps * 1e-3), 1),
+        "clocks": sampler.summary() if sampler else None,
+        "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": round(ms_e2e / k2, 3)},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--height", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -87,7 +87,7 @@ int b200mix_conv3x3_small_cin(const void* x, int32_t x_fp32, const void* w, cons
 /* Scaled dot-product attention, flash-style on tcgen05 (S=QK^T and O+=PV in TMEM, online softmax in registers).
  * Semantics = the `math` branch of scaled_dot_product_attention_ (ppdiffusers/patches/paddle_patch.py:445-461):
  * softmax(q k^T * scale [+ causal mask]) v. q/k/v/o are bf16 with head_dim contiguous; strides in elements for
- * (batch, seq, head). D in {64, 128}; heads with other sizes are zero-padded by the shim at weight-load time.
+ * (batch, seq, head). D in {64, 128, 192}; heads with other sizes are zero-padded by the shim at weight-load time.
  * Hq % Hkv == 0 (GQA, modeling_qwen2_vl.py:497-506). cu_seqlens (int32 device [nseq+1], may be NULL) switches on the
  * varlen block-diagonal mode of the Qwen2-VL ViT (modeling_qwen2_vl.py:354-381): then B must be 1 and both q and k
  * are packed along seq. kv_len (<= Sk) masks the key tail (cross-attention with 77 text tokens). */
@@ -101,11 +101,11 @@ int b200mix_sdpa(const void* q, const void* k, const void* v, void* o, int64_t B
 /* GroupNorm (+ optional SiLU) over NHWC bf16; the input may be the channel-concatenation [x1 | x2] of two tensors
  * (skip connections, unet_2d_blocks.py:2353-2356) which is thereby never materialised. x2 may be NULL (C2 = 0).
  * Replaces nn.GroupNorm + nonlinearity (resnet.py:667-692,760-786; transformer_2d.py:161; unet_2d_condition.py:1193).
- * y bf16 [B,H,W,C1+C2]. Two launches: statistics, then apply. `stats` = scratch of B*groups*16 bytes (two doubles per
- * (batch, group), zeroed by the call). */
+ * y bf16 [B,H,W,C1+C2]. Two launches: per-CTA partial statistics (double, fixed reduction
+ * order: bit-reproducible), then apply. `stats` = scratch of at least (4*num_sms + B) * groups * 16 bytes. */
 int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2, int64_t C2, const float* gamma,
-                           const float* beta, void* y, void* stats, int64_t B, int64_t HW, int32_t groups, float eps,
-                           int32_t silu, void* stream);
+                           const float* beta, void* y, void* stats, int64_t stats_bytes, int64_t B, int64_t HW,
+                           int32_t groups, float eps, int32_t silu, void* stream);
 
 /* Row-wise LayerNorm family. For each row m of x[M,N] (bf16):
  *   r = x + gate[g]*delta (if delta given; also written to resid_out)            (fused_adaLN_scale_residual,

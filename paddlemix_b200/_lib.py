@@ -49,7 +49,7 @@ SIGNATURES = {
     "b200mix_sdpa": [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 6 + [c_int64] * 12 +
                     [c_float, c_int32, c_void_p, c_int32, c_void_p],
     "b200mix_groupnorm_nhwc": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
-                               c_int64, c_int32, c_float, c_int32, c_void_p],
+                               c_int64, c_int64, c_int32, c_float, c_int32, c_void_p],
     "b200mix_layernorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                           c_int64, c_int64, c_int64, c_int64, c_float, c_int32, c_void_p],
     "b200mix_timestep_embedding": [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_int32, c_float,

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(192, 1)
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
   constexpr int DC = D / 64;               // 64-wide head-dim chunks (one 128B swizzle atom each)
   constexpr int TILE_BYTES = 128 * D * 2;  // one 128-row tile of Q / K / V
-  constexpr int KS = (D == 64) ? 3 : 2;    // K/V ring depth
+  constexpr int KS = (D == 64) ? 3 : (D == 128 ? 2 : 1);  // K/V ring depth
   constexpr int P_BYTES = 128 * 128 * 2;
   constexpr uint32_t TM_S = 0, TM_O = 256;
 
@@ -360,7 +360,7 @@ static int make_attn_tmap(CUtensorMap* tm, const void* ptr, int64_t D, int64_t S
 template <int D>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        dim3 grid, cudaStream_t stream) {
-  constexpr int KS = (D == 64) ? 3 : 2;
+  constexpr int KS = (D == 64) ? 3 : (D == 128 ? 2 : 1);
   constexpr int smem_bytes = (1 + 2 * KS) * 128 * D * 2 + 128 * 128 * 2 + 1024 + 256;
   static bool configured = false;
   if (!configured) {
@@ -383,7 +383,8 @@ extern "C" int b200mix_sdpa(const void* q, const void* k, const void* v, void* o
                             int32_t nseq, void* stream) {
   if (int rc = ensure_device()) return rc;
   B200_CHECK_ARG(q && k && v && o, "sdpa: null pointer");
-  B200_CHECK_ARG(D == 64 || D == 128, "sdpa: head_dim %lld unsupported (64 or 128; pad at weight-load time)",
+  B200_CHECK_ARG(D == 64 || D == 128 || D == 192,
+                 "sdpa: head_dim %lld unsupported (64, 128 or 192; pad at weight-load time)",
                  (long long)D);
   B200_CHECK_ARG(B > 0 && Hq > 0 && Hkv > 0 && Sq > 0 && Sk > 0, "sdpa: bad shape");
   B200_CHECK_ARG(Hq % Hkv == 0, "sdpa: Hq %% Hkv != 0");
@@ -410,5 +411,6 @@ extern "C" int b200mix_sdpa(const void* q, const void* k, const void* v, void* o
   dim3 grid((unsigned)q_tiles, (unsigned)Hq, (unsigned)B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (D == 64) return launch_attn<64>(tq, tk, tv, p, grid, st);
-  return launch_attn<128>(tq, tk, tv, p, grid, st);
+  if (D == 128) return launch_attn<128>(tq, tk, tv, p, grid, st);
+  return launch_attn<192>(tq, tk, tv, p, grid, st);
 }

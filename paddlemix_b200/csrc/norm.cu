@@ -22,20 +22,19 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 // ------------------------------------------------------------------------------------------------------------
-// GroupNorm statistics: per (batch, group) sum and sum of squares, accumulated in double through atomics.
-// Block = PPB pixels x CV 8-channel vectors; each thread owns a fixed channel vector => fully coalesced rows.
+// GroupNorm statistics: per (batch, CTA, group) partial sum / sum of squares in double, reduced in a fixed order
+// (no atomics => bit-reproducible). Block = PPB pixels x CV 8-channel vectors; each thread owns a fixed channel
+// vector, so every row is read with fully coalesced 16-byte loads.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2,
-                                int C2, double* __restrict__ stats, long long HW, int groups, int PPB, int pix_per_cta) {
-  extern __shared__ float sm[];  // [2*C]
+                                int C2, double* __restrict__ partial, long long HW, int groups, int PPB,
+                                int pix_per_cta) {
+  extern __shared__ float sm[];  // [PPB][2][C]
   const int C = C1 + C2;
   const int CV = C >> 3;
   const int cv = threadIdx.x % CV;
   const int pl = threadIdx.x / CV;
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.0f;
-  __syncthreads();
-
   const int c0 = cv * 8;
   const __nv_bfloat16* src;
   long long ld;
@@ -45,12 +44,12 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
   } else {
     src = x2 + static_cast<long long>(b) * HW * C2, ld = C2, cc = c0 - C1;
   }
-  float s[8], q[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = 0.0f, q[i] = 0.0f;
   const long long p_begin = static_cast<long long>(blockIdx.x) * pix_per_cta;
   const long long p_end = min(HW, p_begin + pix_per_cta);
   if (pl < PPB) {
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.0f, q[i] = 0.0f;
     for (long long pix = p_begin + pl; pix < p_end; pix += PPB) {
       const uint4 w = __ldg(reinterpret_cast<const uint4*>(src + pix * ld + cc));
       float f[8];
@@ -58,48 +57,55 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i] += f[i], q[i] += f[i] * f[i];
     }
+    float* dst = sm + static_cast<size_t>(pl) * 2 * C;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sm[c0 + i], s[i]);
-      atomicAdd(&sm[C + c0 + i], q[i]);
-    }
+    for (int i = 0; i < 8; ++i) dst[c0 + i] = s[i], dst[C + c0 + i] = q[i];
   }
   __syncthreads();
   const int cpg = C / groups;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double ss = 0.0, qq = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) ss += sm[c], qq += sm[C + c];
-    atomicAdd(&stats[(static_cast<long long>(b) * groups + g) * 2 + 0], ss);
-    atomicAdd(&stats[(static_cast<long long>(b) * groups + g) * 2 + 1], qq);
+    for (int l = 0; l < PPB; ++l) {
+      const float* row = sm + static_cast<size_t>(l) * 2 * C;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) ss += row[c], qq += row[C + c];
+    }
+    double* o = partial + ((static_cast<long long>(b) * gridDim.x + blockIdx.x) * groups + g) * 2;
+    o[0] = ss, o[1] = qq;
   }
 }
 
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2,
                                 int C2, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                __nv_bfloat16* __restrict__ y, const double* __restrict__ stats, long long HW,
+                                __nv_bfloat16* __restrict__ y, const double* __restrict__ partial, long long HW,
                                 int groups, float eps, int silu, int PPB, int pix_per_cta) {
+  extern __shared__ float sm[];  // [groups][2] = (mean, rstd)
   const int C = C1 + C2;
   const int CV = C >> 3;
   const int cv = threadIdx.x % CV;
   const int pl = threadIdx.x / CV;
   const int b = blockIdx.y;
-  if (pl >= PPB) return;
-  const int c0 = cv * 8;
   const int cpg = C / groups;
   const double n = static_cast<double>(HW) * cpg;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double su = 0.0, sq = 0.0;
+    const double* src = partial + (static_cast<long long>(b) * gridDim.x * groups + g) * 2;
+    for (unsigned i = 0; i < gridDim.x; ++i) su += src[static_cast<size_t>(i) * groups * 2], sq += src[static_cast<size_t>(i) * groups * 2 + 1];
+    const double mean = su / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    sm[2 * g] = static_cast<float>(mean);
+    sm[2 * g + 1] = rsqrtf(static_cast<float>(var) + eps);
+  }
+  __syncthreads();
+  if (pl >= PPB) return;
+  const int c0 = cv * 8;
   float a[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = c0 + i;
     const int g = c / cpg;
-    const double su = stats[(static_cast<long long>(b) * groups + g) * 2 + 0];
-    const double sq = stats[(static_cast<long long>(b) * groups + g) * 2 + 1];
-    const double mean = su / n;
-    double var = sq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = rsqrtf(static_cast<float>(var) + eps);
-    a[i] = rstd * gamma[c];
-    sh[i] = beta[c] - static_cast<float>(mean) * a[i];
+    a[i] = sm[2 * g + 1] * gamma[c];
+    sh[i] = beta[c] - sm[2 * g] * a[i];
   }
   const __nv_bfloat16* src;
   long long ld;
@@ -249,8 +255,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LNParams p) {
 using namespace b200;
 
 extern "C" int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2, int64_t C2, const float* gamma,
-                                      const float* beta, void* y, void* stats, int64_t B, int64_t HW, int32_t groups,
-                                      float eps, int32_t silu, void* stream) {
+                                      const float* beta, void* y, void* stats, int64_t stats_bytes, int64_t B, int64_t HW,
+                                      int32_t groups, float eps, int32_t silu, void* stream) {
   if (int rc = ensure_device()) return rc;
   const int64_t C = C1 + C2;
   B200_CHECK_ARG(x1 && y && gamma && beta && stats, "groupnorm: null pointer");
@@ -268,13 +274,14 @@ extern "C" int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2
   if (pix_per_cta < PPB) pix_per_cta = PPB;
   const unsigned gx = (unsigned)((HW + pix_per_cta - 1) / pix_per_cta);
   double* dstats = reinterpret_cast<double*>(stats);
-  B200_CUDA(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * B * groups, st));
+  B200_CHECK_ARG((long long)gx * B * groups * 2 * 8 <= stats_bytes,
+                 "groupnorm: stats scratch too small (%lld bytes needed)", (long long)gx * B * groups * 16);
   dim3 grid(gx, (unsigned)B);
-  gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), st>>>(
+  gn_stats_kernel<<<grid, threads, (size_t)PPB * 2 * C * sizeof(float), st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x1), (int)C1, reinterpret_cast<const __nv_bfloat16*>(x2), (int)C2, dstats,
       HW, groups, PPB, (int)pix_per_cta);
   B200_LAUNCH_CHECK();
-  gn_apply_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x1), (int)C1,
+  gn_apply_kernel<<<grid, threads, 2 * groups * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(x1), (int)C1,
                                             reinterpret_cast<const __nv_bfloat16*>(x2), (int)C2, gamma, beta,
                                             reinterpret_cast<__nv_bfloat16*>(y), dstats, HW, groups, eps, silu, PPB,
                                             (int)pix_per_cta);

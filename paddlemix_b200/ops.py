@@ -28,6 +28,47 @@ def _count(n=1):
     _launches += n
 
 
+# ---- optional per-launch timing (bench.py's roofline section): CUDA events on the launching stream ----------------
+_prof = None  # list of (kind, work, unit, start_event, end_event) while profiling
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """Returns {kind: dict(ms, work, unit, calls)} for the launches since profile_begin()."""
+    global _prof
+    recs, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {}
+    for kind, work, unit, e0, e1 in recs:
+        d = out.setdefault(kind, dict(ms=0.0, work=0.0, unit=unit, calls=0))
+        d["ms"] += e0.elapsed_time(e1)
+        d["work"] += work
+        d["calls"] += 1
+    return out
+
+
+class _Timed:
+    __slots__ = ("kind", "work", "unit", "e0")
+
+    def __init__(self, kind, work, unit):
+        self.kind, self.work, self.unit = kind, work, unit
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if _prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.append((self.kind, self.work, self.unit, self.e0, e1))
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -85,8 +126,9 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, act=ACT_NONE, glu=GLU
                       rows_per_group=rows_per_group, residual=res2, ldr=0 if res2 is None else res2.stride(0), act=act,
                       glu=glu, out_fp32=out_fp32, out_scale=out_scale)
     out2 = out.reshape(-1, n_out)
-    check(lib.b200mix_linear(_p(a2), a2.stride(0), _p(w), w.stride(0), _p(out2), out2.stride(0), M, N, K,
-                             ctypes.byref(e), _stream()), "b200mix_linear")
+    with _Timed("igemm", 2.0 * M * N * K, "flop"):
+        check(lib.b200mix_linear(_p(a2), a2.stride(0), _p(w), w.stride(0), _p(out2), out2.stride(0), M, N, K,
+                                 ctypes.byref(e), _stream()), "b200mix_linear")
     _count()
     return out
 
@@ -103,8 +145,9 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, bias=None, *, stride=1, row_add=No
         out = torch.empty(B, Ho, Wo, Cout, device=x.device, dtype=bf16)
     e = make_epilogue(bias=bias, row_add=row_add, ld_row=0 if row_add is None else row_add.stride(0),
                       rows_per_group=Ho * Wo, residual=residual, ldr=Cout, act=act, out_scale=out_scale)
-    check(lib.b200mix_conv3x3(_p(x), _p(w), _p(out), B, H, W, Cin, Cout, stride, ctypes.byref(e), _stream()),
-          "b200mix_conv3x3")
+    with _Timed("igemm", 2.0 * B * Ho * Wo * Cout * 9 * Cin, "flop"):
+        check(lib.b200mix_conv3x3(_p(x), _p(w), _p(out), B, H, W, Cin, Cout, stride, ctypes.byref(e), _stream()),
+              "b200mix_conv3x3")
     _count()
     return out
 
@@ -133,10 +176,11 @@ def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[f
     if scale is None:
         scale = D ** -0.5
     nseq = 0 if cu_seqlens is None else cu_seqlens.numel() - 1
-    check(lib.b200mix_sdpa(_p(q), _p(k), _p(v), _p(out), B, Hq, Hkv, Sq, Sk, D, q.stride(0), q.stride(1), q.stride(2),
-                           k.stride(0), k.stride(1), k.stride(2), v.stride(0), v.stride(1), v.stride(2), out.stride(0),
-                           out.stride(1), out.stride(2), float(scale), 1 if causal else 0, _p(cu_seqlens), nseq,
-                           _stream()), "b200mix_sdpa")
+    with _Timed("attention", 4.0 * B * Hq * Sq * Sk * D * (0.5 if causal else 1.0), "flop"):
+        check(lib.b200mix_sdpa(_p(q), _p(k), _p(v), _p(out), B, Hq, Hkv, Sq, Sk, D, q.stride(0), q.stride(1),
+                               q.stride(2), k.stride(0), k.stride(1), k.stride(2), v.stride(0), v.stride(1),
+                               v.stride(2), out.stride(0), out.stride(1), out.stride(2), float(scale),
+                               1 if causal else 0, _p(cu_seqlens), nseq, _stream()), "b200mix_sdpa")
     _count()
     return out
 
@@ -156,10 +200,11 @@ def groupnorm_nhwc(x1: torch.Tensor, gamma, beta, *, x2=None, groups=32, eps=1e-
     key = (x1.device, B * groups)
     st = _gn_scratch.get(key)
     if st is None:
-        st = torch.empty(B * groups * 2, device=x1.device, dtype=torch.float64)
+        st = torch.empty((1024 + B) * groups * 2, device=x1.device, dtype=torch.float64)
         _gn_scratch[key] = st
-    check(lib.b200mix_groupnorm_nhwc(_p(x1), C1, _p(x2), C2, _p(gamma), _p(beta), _p(out), _p(st), B, HW, groups,
-                                     float(eps), 1 if silu else 0, _stream()), "b200mix_groupnorm_nhwc")
+    with _Timed("groupnorm", 2.0 * 2 * B * HW * (C1 + C2), "byte"):  # algorithmic: read once + write once (bf16)
+        check(lib.b200mix_groupnorm_nhwc(_p(x1), C1, _p(x2), C2, _p(gamma), _p(beta), _p(out), _p(st), st.numel() * 8, B,
+                                         HW, groups, float(eps), 1 if silu else 0, _stream()), "b200mix_groupnorm_nhwc")
     _count(2)
     return out
 
@@ -178,9 +223,11 @@ def layernorm(x: torch.Tensor, weight=None, bias=None, *, eps=1e-5, rms=False, d
     resid = torch.empty_like(x) if (want_resid and delta is not None) else None
     mod = gate if gate is not None else (scale if scale is not None else shift)
     ld_mod = 0 if mod is None else mod.stride(0)
-    check(lib.b200mix_layernorm(_p(x2), _p(delta), _p(gate), _p(resid), _p(out), _p(weight), _p(bias), _p(scale),
-                                _p(shift), ld_mod, rows_per_group, M, N, float(eps), 1 if rms else 0, _stream()),
-          "b200mix_layernorm")
+    nbytes = 2.0 * M * N * (2 + (1 if delta is not None else 0) + (1 if resid is not None else 0))
+    with _Timed("layernorm", nbytes, "byte"):
+        check(lib.b200mix_layernorm(_p(x2), _p(delta), _p(gate), _p(resid), _p(out), _p(weight), _p(bias), _p(scale),
+                                    _p(shift), ld_mod, rows_per_group, M, N, float(eps), 1 if rms else 0, _stream()),
+              "b200mix_layernorm")
     _count()
     if want_resid:
         return (resid if resid is not None else x), out

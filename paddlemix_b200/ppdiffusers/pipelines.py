@@ -1,0 +1,180 @@
+"""The denoising loop of StableDiffusionPipeline / StableDiffusionXLPipeline
+(ppdiffusers/pipelines/stable_diffusion/pipeline_stable_diffusion.py:858-908,
+ ppdiffusers/pipelines/stable_diffusion_xl/pipeline_stable_diffusion_xl.py:1040-1082) on the B200-native UNet.
+
+Text encoders and the VAE run before / after the loop and are out of scope: the pipelines here take
+`prompt_embeds` (and `negative_prompt_embeds`) exactly as the reference pipelines accept them and return latents
+(`output_type="latent"`). One timestep = UNet forward on [uncond | cond] rows + fused CFG/DDIM kernel; the whole
+timestep is captured once into a CUDA graph (host cost of ~1.5k launches -> one graph launch) and replayed with the
+four DDIM scalars passed through a small device buffer... scalars change per step, so the scheduler kernel is
+launched outside the graph.
+
+Multi-GPU (data parallel over images): each rank takes a contiguous slice of the batch, replicates the
+weights, runs the loop with zero per-step communication, and `all_gather`s the finished latents once over NCCL.
+"""
+from typing import Any, Dict, Optional
+
+import torch
+
+from .schedulers import DDIMScheduler
+from .unet_2d_condition import UNet2DConditionModel
+
+bf16 = torch.bfloat16
+
+
+class GraphedUNet:
+    """Static-shape CUDA-graph wrapper around UNet2DConditionModel.forward_nhwc (+ NCHW<->NHWC conversion).
+    Inputs are copied into static device buffers; the timestep lives in a device tensor so it can change per replay."""
+
+    def __init__(self, unet: UNet2DConditionModel, sample_shape, ctx_shape, added_cond_shapes: Optional[Dict[str, Any]] = None,
+                 warmup: int = 2):
+        from .. import ops
+        dev = unet.device
+        self.unet = unet
+        self.sample = torch.zeros(sample_shape, device=dev, dtype=torch.float32)  # NCHW fp32 latents (model input)
+        self.ctx = torch.zeros(ctx_shape, device=dev, dtype=bf16)
+        self.t = torch.zeros(sample_shape[0], device=dev, dtype=torch.float32)
+        self.added = None
+        if added_cond_shapes:
+            self.added = {k: torch.zeros(s, device=dev, dtype=(bf16 if k == "text_embeds" else torch.float32))
+                          for k, s in added_cond_shapes.items()}
+        self.out = None
+        self.launches_per_replay = 0
+
+        def run():
+            x = ops.nchw_to_nhwc(self.sample)
+            y = unet.forward_nhwc(x, self.t, self.ctx, self.added)
+            return ops.nhwc_to_nchw(y, out_dtype=bf16)
+
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                run()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.launches()
+        with torch.cuda.graph(self.graph):
+            self.out = run()
+        self.launches_per_replay = ops.launches() - n0
+
+    def __call__(self, sample, timestep, ctx=None, added_cond_kwargs=None):
+        from .. import ops
+        self.sample.copy_(sample, non_blocking=True)
+        if ctx is not None:
+            self.ctx.copy_(ctx, non_blocking=True)
+        if torch.is_tensor(timestep):
+            self.t.copy_(timestep.to(torch.float32).reshape(-1).expand(self.t.shape[0]), non_blocking=True)
+        else:
+            self.t.fill_(float(timestep))
+        if added_cond_kwargs is not None and self.added is not None:
+            for k, v in added_cond_kwargs.items():
+                self.added[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        ops._count(self.launches_per_replay)
+        return self.out
+
+
+class StableDiffusionPipeline:
+    """Loop-only mirror of ppdiffusers.StableDiffusionPipeline / StableDiffusionXLPipeline.__call__."""
+
+    def __init__(self, unet: UNet2DConditionModel, scheduler: DDIMScheduler, use_cuda_graph: bool = True):
+        self.unet, self.scheduler, self.use_cuda_graph = unet, scheduler, use_cuda_graph
+        self._graphed = {}
+
+    def _denoiser(self, sample_shape, ctx_shape, added):
+        if not self.use_cuda_graph:
+            return None
+        key = (tuple(sample_shape), tuple(ctx_shape), None if added is None else tuple((k, tuple(v.shape)) for k, v in added.items()))
+        g = self._graphed.get(key)
+        if g is None:
+            g = GraphedUNet(self.unet, sample_shape, ctx_shape, None if added is None else {k: v.shape for k, v in added.items()})
+            self._graphed[key] = g
+        return g
+
+    @torch.no_grad()
+    def __call__(self, prompt=None, height: Optional[int] = None, width: Optional[int] = None,
+                 num_inference_steps: int = 50, guidance_scale: float = 7.5, negative_prompt=None, eta: float = 0.0,
+                 latents: Optional[torch.Tensor] = None, prompt_embeds: Optional[torch.Tensor] = None,
+                 negative_prompt_embeds: Optional[torch.Tensor] = None, output_type: str = "latent",
+                 added_cond_kwargs: Optional[Dict[str, torch.Tensor]] = None,
+                 negative_added_cond_kwargs: Optional[Dict[str, torch.Tensor]] = None, callback_on_step_end=None,
+                 generator: Optional[torch.Generator] = None):
+        if prompt is not None or negative_prompt is not None:
+            raise NotImplementedError("text encoders are outside the hot path: pass prompt_embeds / negative_prompt_embeds")
+        if prompt_embeds is None:
+            raise ValueError("Provide either `prompt` or `prompt_embeds`. Cannot leave both `prompt` and `prompt_embeds` undefined.")
+        if output_type != "latent":
+            raise NotImplementedError("the VAE decoder is outside the hot path: use output_type='latent'")
+        if eta != 0.0:
+            raise NotImplementedError("eta > 0 (stochastic DDIM) is outside the hot path")
+        from .. import ops
+        dev = self.unet.device
+        B = prompt_embeds.shape[0]
+        do_cfg = guidance_scale > 1.0  # pipeline_stable_diffusion.py:781
+        if do_cfg and negative_prompt_embeds is None:
+            negative_prompt_embeds = torch.zeros_like(prompt_embeds)
+        if latents is None:
+            if height is None or width is None:
+                raise ValueError("height/width (or latents) are required")
+            g = generator or torch.Generator().manual_seed(0)
+            latents = torch.randn(B, self.unet.config.in_channels, height // 8, width // 8, generator=g)
+        latents = latents.to(device=dev, dtype=torch.float32).contiguous() * self.scheduler.init_noise_sigma
+        ctx = prompt_embeds.to(device=dev, dtype=bf16)
+        added = None
+        if added_cond_kwargs is not None:
+            added = {k: v.to(dev) for k, v in added_cond_kwargs.items()}
+        if do_cfg:
+            ctx = torch.cat([negative_prompt_embeds.to(device=dev, dtype=bf16), ctx], 0)
+            if added is not None:
+                neg = negative_added_cond_kwargs or added_cond_kwargs
+                added = {k: torch.cat([neg[k].to(dev), added[k]], 0) for k in added}
+        ctx = ctx.contiguous()
+        if added is not None:
+            added = {k: (v.to(bf16) if k == "text_embeds" else v.to(torch.float32)).contiguous() for k, v in added.items()}
+        self.scheduler.set_timesteps(num_inference_steps)
+        rows = 2 * B if do_cfg else B
+        sample_shape = (rows,) + tuple(latents.shape[1:])
+        den = self._denoiser(sample_shape, ctx.shape, added)
+        model_in = torch.empty(sample_shape, device=dev, dtype=torch.float32)
+        nxt = torch.empty_like(latents)
+        first = True
+        for i, t in enumerate(self.scheduler.timesteps):
+            # latent_model_input = concat([latents] * 2) if CFG (:860); DDIM scale_model_input is the identity
+            if do_cfg:
+                model_in[:B].copy_(latents)
+                model_in[B:].copy_(latents)
+            else:
+                model_in = latents
+            if den is not None:
+                eps = den(model_in, float(t), ctx if first else None, added if first else None)
+            else:
+                eps = self.unet.forward(model_in, float(t), ctx, added_cond_kwargs=added, return_dict=False)[0]
+            first = False
+            if do_cfg:  # noise_pred_uncond + g*(noise_pred_text - noise_pred_uncond) (:882-884), fused with the step
+                self.scheduler.step(eps[:B], t, latents, model_output_cond=eps[B:], guidance_scale=guidance_scale, out=nxt)
+            else:
+                self.scheduler.step(eps, t, latents, out=nxt)
+            latents, nxt = nxt, latents
+            if callback_on_step_end is not None:
+                callback_on_step_end(self, i, t, {"latents": latents})
+        return latents
+
+
+def all_gather_latents(latents: torch.Tensor) -> torch.Tensor:
+    """The single collective of the data-parallel path: finished latents of every rank -> [world*B_local, ...]."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return latents
+    out = [torch.empty_like(latents) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, latents.contiguous())
+    return torch.cat(out, 0)
+
+
+def shard_batch(n: int, rank: int, world: int):
+    """Contiguous slice [lo, hi) of an n-image batch owned by `rank`; CFG pairs stay on one rank because the
+    uncond/cond rows are built per rank after sharding."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)

@@ -160,6 +160,7 @@ ATT_ATOL, ATT_RTOL = 1.5e-2, 2e-2
     (2, 128, 128, 2, 2, 64, False), (1, 256, 384, 3, 3, 64, False), (2, 1024, 1024, 4, 4, 64, False),
     (2, 200, 77, 5, 5, 64, False), (1, 4250, 4250, 2, 2, 64, False), (2, 128, 128, 2, 2, 128, False),
     (1, 768, 768, 4, 2, 128, True), (2, 300, 300, 2, 1, 128, True), (1, 64, 64, 8, 8, 64, False),
+    (2, 256, 256, 8, 8, 192, False), (1, 64, 77, 2, 2, 192, False), (1, 400, 400, 2, 2, 192, True),
 ])
 def test_sdpa(ops, B, Sq, Sk, Hq, Hkv, D, causal):
     q, k, v = rnd(B, Sq, Hq, D, seed=30), rnd(B, Sk, Hkv, D, seed=31), rnd(B, Sk, Hkv, D, seed=32)

@@ -3,11 +3,19 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 rc=0
-for grp in "linear" "conv" "sdpa" "norm or groupnorm or rmsnorm" "timestep or elementwise or ddim or rope"; do
-  name=$(echo "$grp" | awk '{print $1}')
-  timeout 600 python -m pytest tests/test_ops_gpu.py -q -m gpu -k "$grp" -x --no-header -p no:cacheprovider > gpurun_out/test_$name.log 2>&1
+run() {
+  name=$1; shift
+  timeout 900 python -m pytest "$@" -q -m gpu -x --no-header -p no:cacheprovider -s > gpurun_out/test_$name.log 2>&1
   code=$?
-  echo "== $name exit $code"; tail -n 15 gpurun_out/test_$name.log
+  echo "== $name exit $code"; tail -n 25 gpurun_out/test_$name.log
   [ $code -ne 0 ] && rc=1
-done
+}
+if [ "$1" != "unet" ]; then
+  run linear tests/test_ops_gpu.py -k "linear"
+  run conv tests/test_ops_gpu.py -k "conv"
+  run sdpa tests/test_ops_gpu.py -k "sdpa"
+  run norm tests/test_ops_gpu.py -k "norm"
+  run misc tests/test_ops_gpu.py -k "timestep or elementwise or ddim or rope"
+fi
+run unet tests/test_unet_gpu.py
 exit $rc
