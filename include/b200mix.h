@@ -42,7 +42,9 @@ enum { B200MIX_GLU_NONE = 0, B200MIX_GLU_GEGLU = 1, B200MIX_GLU_SWIGLU = 2 };
  *             ppdiffusers/models/activations.py:83-104) or silu(gate) * value (SwiGLU, modeling_qwen2_vl.py:492-493);
  *             the output then has N/2 columns
  *   v = v * row_gate[(m / rows_per_group) * ld_row + n]          (AdaLN-Zero gate, attention.py:196-214)
- *   v = (v + residual[m * ldr + n]) * out_scale                  (ResnetBlock2D output_scale_factor, resnet.py:806)
+ *   v = (v + residual[r * ldr + n]) * out_scale                  (ResnetBlock2D output_scale_factor, resnet.py:806)
+ *       with r = m, or m % residual_row_mod when residual_row_mod > 0 (a table shared by all groups, e.g. the
+ *       cropped positional embedding of PatchEmbed, embeddings.py:186-247)
  */
 typedef struct b200mix_epilogue {
   const float* bias;      /* [N] or NULL */
@@ -56,6 +58,7 @@ typedef struct b200mix_epilogue {
   int32_t glu;            /* B200MIX_GLU_* */
   int32_t out_fp32;       /* 0: bf16 output, 1: fp32 output */
   float out_scale;        /* 1.0f for none */
+  int64_t residual_row_mod; /* 0: residual row = m */
 } b200mix_epilogue;
 
 const char* b200mix_last_error(void);
@@ -71,6 +74,14 @@ int b200mix_num_sms(void);
  * 1x1 conv on NHWC (lora.py:365-377). A, W bf16; lda/ldw/ldc in elements, multiples of 8. */
 int b200mix_linear(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M, int64_t N,
                    int64_t K, const b200mix_epilogue* epi, void* stream);
+
+/* Batched-strided Linear: for b < nbatch, C_b[rows,N] = epilogue(A_b[rows,K] @ W^T), X_b = X + b * x_bstride
+ * (elements). Per-group epilogue vectors are indexed by b; r_bstride is the residual's batch stride. Lets the image
+ * and text token ranges of SD3's joint [B, n_img+n_txt, *] buffers be produced / consumed in place
+ * (JointAttnProcessor2_5 concat / split, attention_processor.py:934-975). */
+int b200mix_linear_batched(const void* A, int64_t lda, int64_t a_bstride, const void* W, int64_t ldw, void* C,
+                           int64_t ldc, int64_t c_bstride, int64_t rows, int64_t nbatch, int64_t N, int64_t K,
+                           const b200mix_epilogue* epi, int64_t r_bstride, void* stream);
 
 /* y[B,Ho,Wo,Cout] = epilogue(conv3x3(x[B,H,W,Cin], w[Cout,3,3,Cin], padding 1, stride 1|2)). Implicit GEMM without
  * im2col: each of the 9 taps is a shifted TMA box load with hardware zero fill at the borders.
@@ -154,6 +165,14 @@ int b200mix_ddim_step(const void* eps_u, const void* eps_c, int32_t eps_fp32, fl
  * with dt = sigma_next - sigma computed in fp32 on the host. */
 int b200mix_euler_step(const void* v_u, const void* v_c, int32_t v_fp32, float guidance, const float* x, float* x_prev,
                        int64_t n, float sigma, float dt, void* stream);
+
+/* SD3 / DiT patchify: x NCHW [B,C,H,W] (fp32|bf16) -> rows [B*(H/p)*(W/p), C*p*p] bf16 with the column order
+ * (c, ph, pw) of a flattened Conv2D weight [D,C,p,p] (PatchEmbed.proj, embeddings.py:143-150), and its inverse for
+ * the output head: rows [B*h*w, p*p*C] in (ph, pw, c) order -> NCHW [B,C,h*p,w*p] (transformer_sd3.py:350-356). */
+int b200mix_patchify(const void* x, int32_t x_fp32, void* y, int64_t B, int64_t C, int64_t H, int64_t W, int32_t p,
+                     void* stream);
+int b200mix_unpatchify(const void* x, void* y, int32_t y_fp32, int64_t B, int64_t C, int64_t h, int64_t w, int32_t p,
+                       void* stream);
 
 /* fp32 <-> bf16 casts (round-to-nearest-even). */
 int b200mix_cast(const void* x, void* y, int64_t n, int32_t x_fp32, int32_t y_fp32, void* stream);

@@ -30,6 +30,7 @@ class Epilogue(Structure):
         ("glu", c_int32),
         ("out_fp32", c_int32),
         ("out_scale", c_float),
+        ("residual_row_mod", c_int64),
     ]
 
 
@@ -42,6 +43,10 @@ SIGNATURES = {
     "b200mix_num_sms": [],
     "b200mix_linear": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
                        POINTER(Epilogue), c_void_p],
+    "b200mix_linear_batched": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                               c_int64, c_int64, POINTER(Epilogue), c_int64, c_void_p],
+    "b200mix_patchify": [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p],
+    "b200mix_unpatchify": [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p],
     "b200mix_conv3x3": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32,
                         POINTER(Epilogue), c_void_p],
     "b200mix_conv3x3_small_cin": [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,

@@ -19,6 +19,10 @@ __device__ __forceinline__ float ew_act(float v, int act) {
   }
 }
 
+__device__ __forceinline__ float load_any(const void* p, long long i, int fp32) {
+  return fp32 ? reinterpret_cast<const float*>(p)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+
 // embeddings.py:26-64 — exponent = -ln(max_period) * i / (half - shift); emb = scale * t * exp(exponent);
 // [sin | cos], swapped to [cos | sin] when flip_sin_to_cos.
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, void* __restrict__ out, int out_fp32, int B,
@@ -165,9 +169,6 @@ __global__ void conv3x3_small_cin_kernel(const void* __restrict__ x, int x_fp32,
   }
 }
 
-__device__ __forceinline__ float load_any(const void* p, long long i, int fp32) {
-  return fp32 ? reinterpret_cast<const float*>(p)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
-}
 
 // scheduling_ddim.py:410-457 with eta = 0, epsilon prediction, no clipping; every operation individually rounded
 // (no FMA contraction) so the result is bit-identical to the fp32 CPU evaluation of the same expression.
@@ -226,6 +227,43 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ x, long long T, int H, i
     const float s1 = sn[t * D + i], s2 = sn[t * D + i + half];
     p[i] = __float2bfloat16(x1 * c1 - x2 * s1);
     p[i + half] = __float2bfloat16(x2 * c2 + x1 * s2);
+  }
+}
+
+__global__ void patchify_kernel(const void* __restrict__ x, int x_fp32, __nv_bfloat16* __restrict__ y, int B, int C,
+                                int H, int W, int p) {
+  const int h = H / p, w = W / p, K = C * p * p;
+  const long long total = (long long)B * h * w * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    long long r = i / K;
+    const int pw = k % p, ph = (k / p) % p, c = k / (p * p);
+    const int ww = (int)(r % w);
+    r /= w;
+    const int hh = (int)(r % h);
+    const long long b = r / h;
+    const long long src = ((b * C + c) * H + hh * p + ph) * W + ww * p + pw;
+    y[i] = __float2bfloat16(load_any(x, src, x_fp32));
+  }
+}
+
+__global__ void unpatchify_kernel(const __nv_bfloat16* __restrict__ x, void* __restrict__ y, int y_fp32, int B, int C,
+                                  int h, int w, int p) {
+  const int H = h * p, W = w * p;
+  const long long total = (long long)B * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W);
+    long long r = i / W;
+    const int Y = (int)(r % H);
+    r /= H;
+    const int c = (int)(r % C);
+    const long long b = r / C;
+    const int hh = Y / p, ph = Y % p, ww = X / p, pw = X % p;
+    const float v = __bfloat162float(x[((b * h + hh) * w + ww) * (long long)(p * p * C) + (ph * p + pw) * C + c]);
+    if (y_fp32) reinterpret_cast<float*>(y)[i] = v;
+    else reinterpret_cast<__nv_bfloat16*>(y)[i] = __float2bfloat16(v);
   }
 }
 
@@ -343,6 +381,26 @@ extern "C" int b200mix_euler_step(const void* v_u, const void* v_c, int32_t v_fp
   if (int rc = ensure_device()) return rc;
   B200_CHECK_ARG(v_u && x && x_prev && n > 0, "euler_step: bad arguments");
   euler_step_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(v_u, v_c, v_fp32, guidance, x, x_prev, n, sigma, dt);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_patchify(const void* x, int32_t x_fp32, void* y, int64_t B, int64_t C, int64_t H, int64_t W,
+                                int32_t p, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(x && y && p > 0 && H % p == 0 && W % p == 0, "patchify: bad arguments");
+  patchify_kernel<<<ew_grid(B * C * H * W, 256), 256, 0, ST(stream)>>>(x, x_fp32, reinterpret_cast<__nv_bfloat16*>(y),
+                                                                       (int)B, (int)C, (int)H, (int)W, p);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_unpatchify(const void* x, void* y, int32_t y_fp32, int64_t B, int64_t C, int64_t h, int64_t w,
+                                  int32_t p, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(x && y && p > 0, "unpatchify: bad arguments");
+  unpatchify_kernel<<<ew_grid(B * C * h * w * p * p, 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), y, y_fp32, (int)B, (int)C, (int)h, (int)w, p);
   B200_LAUNCH_CHECK();
   return 0;
 }

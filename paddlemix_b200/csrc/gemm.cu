@@ -37,6 +37,10 @@ struct IGemmParams {
   long long ldc;
   int act, glu, out_fp32, vec_ok;
   float out_scale;
+  // batched-strided mode (b200mix_linear_batched): row (b, x) of the output lives at C + b*c_bstride + x*ldc and the
+  // residual at residual + b*r_bstride + x*ldr; plain mode (c_bstride == 0) uses the flat row index for both.
+  long long c_bstride, r_bstride;
+  long long res_row_mod;  // > 0: residual row = flat row % res_row_mod (a [rows, N] table shared by all groups)
 };
 
 __device__ __forceinline__ float act_silu(float x) { return x / (1.0f + __expf(-x)); }
@@ -59,8 +63,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 // One 32-column chunk of one accumulator row -> global memory.
-__device__ __forceinline__ void epilogue_chunk(const IGemmParams& p, const uint32_t (&r)[32], long long gm, long long g,
-                                               int n_abs) {
+__device__ __forceinline__ void epilogue_chunk(const IGemmParams& p, const uint32_t (&r)[32], long long c_off,
+                                               long long r_off, long long g, int n_abs) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -102,12 +106,12 @@ __device__ __forceinline__ void epilogue_chunk(const IGemmParams& p, const uint3
     const int ncol = n_abs >> 1;
     const int nout = p.N >> 1;
     if (p.out_fp32) {
-      float* dst = reinterpret_cast<float*>(p.C) + gm * p.ldc + ncol;
+      float* dst = reinterpret_cast<float*>(p.C) + c_off + ncol;
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if (ncol + j < nout) dst[j] = o[j];
     } else {
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + gm * p.ldc + ncol;
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + c_off + ncol;
       if (vec) {
         uint4 w0 = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
                               pack_bf16x2(o[6], o[7]));
@@ -131,7 +135,7 @@ __device__ __forceinline__ void epilogue_chunk(const IGemmParams& p, const uint3
       if (full || n_abs + j < p.N) v[j] *= __ldg(rg + j);
   }
   if (p.residual) {
-    const __nv_bfloat16* rs = p.residual + gm * p.ldr + n_abs;
+    const __nv_bfloat16* rs = p.residual + r_off + n_abs;
     if (vec) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -153,7 +157,7 @@ __device__ __forceinline__ void epilogue_chunk(const IGemmParams& p, const uint3
   }
 
   if (p.out_fp32) {
-    float* dst = reinterpret_cast<float*>(p.C) + gm * p.ldc + n_abs;
+    float* dst = reinterpret_cast<float*>(p.C) + c_off + n_abs;
     if (vec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -164,7 +168,7 @@ __device__ __forceinline__ void epilogue_chunk(const IGemmParams& p, const uint3
         if (n_abs + j < p.N) dst[j] = v[j];
     }
   } else {
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + gm * p.ldc + n_abs;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + c_off + n_abs;
     if (vec) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -301,7 +305,16 @@ __global__ void __launch_bounds__(192, 1)
       const int x = tx * p.TW + tw, y = ty * p.TH + th, b = tb * p.TB + tbb;
       const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.Bn);
       const long long gm = (static_cast<long long>(b) * p.Ho + y) * p.Wo + x;
-      const long long g = gm / p.rows_per_group;
+      long long g, c_off, r_off;
+      if (p.c_bstride) {  // batched-strided: group == batch
+        g = b;
+        c_off = static_cast<long long>(b) * p.c_bstride + static_cast<long long>(x) * p.ldc;
+        r_off = static_cast<long long>(b) * p.r_bstride + static_cast<long long>(x) * p.ldr;
+      } else {
+        g = gm / p.rows_per_group;
+        c_off = gm * p.ldc;
+        r_off = (p.res_row_mod > 0 ? gm % p.res_row_mod : gm) * p.ldr;
+      }
       const int n0 = nt * BN;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
@@ -311,7 +324,7 @@ __global__ void __launch_bounds__(192, 1)
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c * 32, r);
         tmem_wait_ld();
-        if (valid && n0 + c * 32 < p.N) epilogue_chunk(p, r, gm, g, n0 + c * 32);
+        if (valid && n0 + c * 32 < p.N) epilogue_chunk(p, r, c_off, r_off, g, n0 + c * 32);
       }
       tc_fence_before();
       mbar_arrive(&tempty[as]);
@@ -386,7 +399,7 @@ static int dispatch_igemm(const CUtensorMap& tmA, const void* W, long long ldw, 
 }
 
 static int fill_epilogue(IGemmParams& p, const b200mix_epilogue* e, void* C, long long ldc, long long rows_default) {
-  static const b200mix_epilogue kNone = {nullptr, nullptr, nullptr, 0, 0, nullptr, 0, 0, 0, 0, 1.0f};
+  static const b200mix_epilogue kNone = {nullptr, nullptr, nullptr, 0, 0, nullptr, 0, 0, 0, 0, 1.0f, 0};
   if (!e) e = &kNone;
   p.bias = e->bias;
   p.row_add = e->row_add;
@@ -395,6 +408,7 @@ static int fill_epilogue(IGemmParams& p, const b200mix_epilogue* e, void* C, lon
   p.rows_per_group = (int)(e->rows_per_group > 0 ? e->rows_per_group : rows_default);
   p.residual = reinterpret_cast<const __nv_bfloat16*>(e->residual);
   p.ldr = e->ldr;
+  p.res_row_mod = e->residual_row_mod;
   p.C = C;
   p.ldc = ldc;
   p.act = e->act;
@@ -511,4 +525,43 @@ extern "C" int b200mix_conv3x3(const void* x, const void* w, void* y, int64_t B,
     if (int rc = encode_tmap_bf16_sw128(&tmA, x, 5, dims, strides, box)) return rc;
   }
   return dispatch_igemm(tmA, w, 9 * Cin, 9 * Cin, p, reinterpret_cast<cudaStream_t>(stream), g_force_bn);
+}
+
+
+// Batched-strided Linear: for b in [0, nbatch): C_b[rows, N] = epilogue(A_b[rows, K] @ W[N, K]^T) with
+// A_b = A + b*a_bstride, C_b = C + b*c_bstride, residual_b = residual + b*r_bstride (strides in elements). The
+// epilogue's per-group vectors (row_add / row_gate) are indexed by b. Used to read / write the image and text token
+// ranges of SD3's joint [B, n_img + n_txt, *] buffers in place (attention_processor.py:934-975 concatenates and
+// splits them; here the concat is never materialised).
+extern "C" int b200mix_linear_batched(const void* A, int64_t lda, int64_t a_bstride, const void* W, int64_t ldw, void* C,
+                                      int64_t ldc, int64_t c_bstride, int64_t rows, int64_t nbatch, int64_t N, int64_t K,
+                                      const b200mix_epilogue* epi, int64_t r_bstride, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(A && W && C, "linear_batched: null pointer");
+  B200_CHECK_ARG(rows > 0 && nbatch > 0 && N > 0 && K > 0, "linear_batched: bad shape");
+  B200_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && a_bstride % 8 == 0 && c_bstride > 0,
+                 "linear_batched: strides must be multiples of 8 elements and c_bstride > 0");
+  IGemmParams p = {};
+  p.N = (int)N;
+  p.Kc = (int)K;
+  p.ntaps = 1;
+  p.kchunks = (int)((K + 63) / 64);
+  p.TW = 128, p.TH = 1, p.TB = 1;
+  p.Wo = (int)rows, p.Ho = 1, p.Bn = (int)nbatch;
+  p.tiles_x = (int)((rows + 127) / 128), p.tiles_y = 1, p.tiles_b = (int)nbatch;
+  if (int rc = fill_epilogue(p, epi, C, ldc, rows)) return rc;
+  p.c_bstride = c_bstride;
+  p.r_bstride = r_bstride;
+  const int out_elem = p.out_fp32 ? 4 : 2;
+  if ((c_bstride * out_elem) % 16 != 0 || (p.residual && (r_bstride * 2) % 16 != 0)) p.vec_ok = 0;
+  CUtensorMap tmA;
+  {
+    uint64_t dims[5] = {(uint64_t)K, (uint64_t)rows, 1, 1, (uint64_t)nbatch};
+    uint64_t rowb = (uint64_t)lda * 2;
+    uint64_t bb = (uint64_t)(nbatch > 1 ? a_bstride : (int64_t)(lda * rows)) * 2;
+    uint64_t strides[4] = {rowb, bb, bb, bb};
+    uint32_t box[5] = {64, 128, 1, 1, 1};
+    if (int rc = encode_tmap_bf16_sw128(&tmA, A, 5, dims, strides, box)) return rc;
+  }
+  return dispatch_igemm(tmA, W, ldw, K, p, reinterpret_cast<cudaStream_t>(stream), g_force_bn);
 }

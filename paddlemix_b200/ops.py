@@ -90,7 +90,7 @@ def init(device: int = 0):
 
 
 def make_epilogue(bias=None, row_add=None, row_gate=None, ld_row=0, rows_per_group=0, residual=None, ldr=0,
-                  act=ACT_NONE, glu=GLU_NONE, out_fp32=False, out_scale=1.0) -> Epilogue:
+                  act=ACT_NONE, glu=GLU_NONE, out_fp32=False, out_scale=1.0, residual_row_mod=0) -> Epilogue:
     e = Epilogue()
     e.bias = None if bias is None else _req(bias, torch.float32, "bias").data_ptr()
     e.row_add = None if row_add is None else _req(row_add, torch.float32, "row_add").data_ptr()
@@ -103,11 +103,12 @@ def make_epilogue(bias=None, row_add=None, row_gate=None, ld_row=0, rows_per_gro
     e.glu = int(glu)
     e.out_fp32 = 1 if out_fp32 else 0
     e.out_scale = float(out_scale)
+    e.residual_row_mod = int(residual_row_mod)
     return e
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, act=ACT_NONE, glu=GLU_NONE, residual=None, row_add=None,
-           row_gate=None, rows_per_group=0, out_fp32=False, out=None, out_scale=1.0) -> torch.Tensor:
+           row_gate=None, rows_per_group=0, out_fp32=False, out=None, out_scale=1.0, residual_row_mod=0) -> torch.Tensor:
     """out[M, N(/2)] = epilogue(a[M, K] @ w[N, K]^T). a: bf16 [..., K] (last dim contiguous), w: bf16 [N, K]."""
     _req(a, bf16, "a"), _req(w, bf16, "w")
     K = a.shape[-1]
@@ -124,11 +125,52 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, act=ACT_NONE, glu=GLU
     mod = row_add if row_add is not None else row_gate
     e = make_epilogue(bias=bias, row_add=row_add, row_gate=row_gate, ld_row=0 if mod is None else mod.stride(0),
                       rows_per_group=rows_per_group, residual=res2, ldr=0 if res2 is None else res2.stride(0), act=act,
-                      glu=glu, out_fp32=out_fp32, out_scale=out_scale)
+                      glu=glu, out_fp32=out_fp32, out_scale=out_scale, residual_row_mod=residual_row_mod)
     out2 = out.reshape(-1, n_out)
     with _Timed("igemm", 2.0 * M * N * K, "flop"):
         check(lib.b200mix_linear(_p(a2), a2.stride(0), _p(w), w.stride(0), _p(out2), out2.stride(0), M, N, K,
                                  ctypes.byref(e), _stream()), "b200mix_linear")
+    _count()
+    return out
+
+
+def linear_batched(a: torch.Tensor, w: torch.Tensor, bias=None, *, out: torch.Tensor, act=ACT_NONE, glu=GLU_NONE,
+                   residual=None, row_add=None, row_gate=None) -> torch.Tensor:
+    """a: bf16 [B, rows, K] view (last dim contiguous, arbitrary row / batch strides); out: [B, rows, N(/2)] view with
+    last dim contiguous (e.g. a token range of a joint [B, n_img+n_txt, *] buffer). Per-batch row_add / row_gate."""
+    _req(a, bf16, "a"), _req(w, bf16, "w")
+    B, rows, K = a.shape
+    N = w.shape[0]
+    assert a.stride(-1) == 1 and out.stride(-1) == 1 and out.shape[0] == B and out.shape[1] == rows
+    mod = row_add if row_add is not None else row_gate
+    e = make_epilogue(bias=bias, row_add=row_add, row_gate=row_gate, ld_row=0 if mod is None else mod.stride(0),
+                      rows_per_group=rows, residual=residual, ldr=0 if residual is None else residual.stride(1),
+                      act=act, glu=glu, out_fp32=(out.dtype == torch.float32))
+    with _Timed("igemm", 2.0 * B * rows * N * K, "flop"):
+        check(lib.b200mix_linear_batched(_p(a), a.stride(1), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(1),
+                                         out.stride(0), rows, B, N, K, ctypes.byref(e),
+                                         0 if residual is None else residual.stride(0), _stream()),
+              "b200mix_linear_batched")
+    _count()
+    return out
+
+
+def patchify(x: torch.Tensor, p: int) -> torch.Tensor:
+    B, C, H, W = x.shape
+    assert x.is_contiguous() and x.dtype in (torch.float32, bf16)
+    out = torch.empty(B, (H // p) * (W // p), C * p * p, device=x.device, dtype=bf16)
+    check(lib.b200mix_patchify(_p(x), 1 if x.dtype == torch.float32 else 0, _p(out), B, C, H, W, p, _stream()),
+          "b200mix_patchify")
+    _count()
+    return out
+
+
+def unpatchify(x: torch.Tensor, C: int, h: int, w: int, p: int, out_dtype=bf16) -> torch.Tensor:
+    B = x.shape[0]
+    assert x.is_contiguous() and x.dtype == bf16
+    out = torch.empty(B, C, h * p, w * p, device=x.device, dtype=out_dtype)
+    check(lib.b200mix_unpatchify(_p(x), _p(out), 1 if out_dtype == torch.float32 else 0, B, C, h, w, p, _stream()),
+          "b200mix_unpatchify")
     _count()
     return out
 

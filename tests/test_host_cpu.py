@@ -59,6 +59,15 @@ def test_unet_structure_matches_oracle():
     assert len(UNet2DConditionModel(**{k: O.UNET_CONFIGS["sdxl"][k] for k in keys}).attn_processors) == 140
 
 
+def test_sd3_structure_matches_oracle():
+    from oracle import sd3 as O3
+    from paddlemix_b200.ppdiffusers.transformer_sd3 import SD3Transformer2DModel
+    for name in ("sd3_medium", "tiny"):
+        cfg = O3.SD3_CONFIGS[name]
+        assert SD3Transformer2DModel(**cfg).state_dict_shapes() == O3.sd3_param_shapes(cfg)
+    assert abs(O3.sd3_flops(O3.SD3_CONFIGS["sd3_medium"], 1, 128, 128, 154) / 1e12 - 8.437) < 5e-3
+
+
 def test_config_errors_mirror_reference():
     from paddlemix_b200.ppdiffusers.unet_2d_condition import UNet2DConditionModel
     with pytest.raises(ValueError, match="same number of `down_block_types`"):

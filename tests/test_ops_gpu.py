@@ -313,3 +313,37 @@ def test_rope(ops):
     ref = xf * cos[:, None] + rot * sin[:, None]
     close(xr[..., :D], ref, 2e-2, 1e-2, "rope")
     assert torch.equal(xr[..., D:], x[..., D:])
+
+
+def test_linear_batched_strided(ops):
+    # image / text token ranges of a joint [B, n+L, *] buffer, produced and consumed in place
+    B, n, L, K, N = 3, 300, 154, 192, 256
+    S = n + L
+    xi, xt = rnd(B, n, K, seed=61), rnd(B, L, K, seed=62)
+    w, bias = rnd(N, K, seed=63, scale=K ** -0.5), rnd(N, seed=64, dtype=torch.float32)
+    joint = torch.zeros(B, S, N, device="cuda", dtype=bf16)
+    ops.linear_batched(xi, w, bias, out=joint[:, :n])
+    ops.linear_batched(xt, w, bias, out=joint[:, n:])
+    ref = torch.cat([xi.float() @ w.float().t() + bias, xt.float() @ w.float().t() + bias], 1)
+    close(joint, ref, GEMM_ATOL, GEMM_RTOL, "batched write")
+    gate, res = rnd(B, K, seed=65, dtype=torch.float32), rnd(B, L, K, seed=66)
+    w2 = rnd(K, N, seed=67, scale=N ** -0.5)
+    out = torch.empty(B, L, K, device="cuda", dtype=bf16)
+    ops.linear_batched(joint[:, n:], w2, None, out=out, row_gate=gate, residual=res)
+    ref2 = (joint[:, n:].float() @ w2.float().t()) * gate[:, None] + res.float()
+    close(out, ref2, GEMM_ATOL, GEMM_RTOL, "batched read + gate + residual")
+
+
+def test_patchify_roundtrip_and_posembed(ops):
+    B, C, H, W, p, D = 2, 16, 32, 32, 2, 128
+    x = rnd(B, C, H, W, seed=68, dtype=torch.float32)
+    rows = ops.patchify(x, p)
+    ref = torch.nn.functional.unfold(x.to(bf16).float(), p, stride=p).transpose(1, 2)  # [B, n, C*p*p] in (c, ph, pw) order
+    assert torch.equal(rows.float(), ref)
+    w, bias, pos = rnd(D, C * p * p, seed=69, scale=0.1), rnd(D, seed=70, dtype=torch.float32), rnd(256, D, seed=71)
+    y = ops.linear(rows, w, bias, residual=pos, residual_row_mod=256)
+    close(y, ref @ w.float().t() + bias + pos.float()[None], GEMM_ATOL, GEMM_RTOL, "patch embed + pos")
+    t = rnd(B, 256, p * p * C, seed=72)
+    img = ops.unpatchify(t, C, H // p, W // p, p, out_dtype=torch.float32)
+    ref_img = t.float().reshape(B, H // p, W // p, p, p, C).permute(0, 5, 1, 3, 2, 4).reshape(B, C, H, W)
+    assert torch.equal(img, ref_img)

@@ -1,0 +1,43 @@
+"""SD3 MMDiT parity on the GPU: paddlemix_b200's SD3Transformer2DModel against the CPU fp32 oracle (oracle/sd3.py)
+on identical seeded inputs and weights. Same stated bf16-vs-fp32 tolerance as tests/test_unet_gpu.py."""
+import pytest
+import torch
+
+from oracle import sd3 as O
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+
+def make(name, seed=1):
+    from paddlemix_b200.ppdiffusers.transformer_sd3 import SD3Transformer2DModel
+    cfg = O.SD3_CONFIGS[name]
+    P = O.init_sd3_params(cfg, seed)
+    return cfg, P, SD3Transformer2DModel(**cfg).load_state_dict(P, device=0)
+
+
+@pytest.mark.parametrize("B,H,L,t", [(2, 32, 20, 500.0), (3, 16, 154, 37.5)])
+def test_sd3_tiny_parity(B, H, L, t):
+    cfg, P, model = make("tiny")
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, 16, H, H, generator=g).to(bf16).float()
+    ctx = torch.randn(B, L, cfg["joint_attention_dim"], generator=g).to(bf16).float()
+    pooled = torch.randn(B, cfg["pooled_projection_dim"], generator=g).to(bf16).float()
+    ref = O.sd3_forward(cfg, P, x, ctx, pooled, torch.full((B,), t))
+    out = model(hidden_states=x.cuda(), encoder_hidden_states=ctx.cuda(), pooled_projections=pooled.cuda(),
+                timestep=torch.full((B,), t).cuda(), return_dict=False)[0]
+    assert out.shape == ref.shape and out.dtype == bf16
+    o = out.float().cpu()
+    cos = torch.nn.functional.cosine_similarity(o.flatten(), ref.flatten(), dim=0).item()
+    err = (o - ref).abs().max().item() / ref.abs().max().item()
+    assert cos >= 0.999 and err <= 0.04, (cos, err)
+    again = model(x.cuda(), ctx.cuda(), pooled.cuda(), torch.full((B,), t).cuda()).sample
+    assert torch.equal(again, out)  # determinism (test_models_transformer_sd3.py via ModelTesterMixin)
+
+
+@pytest.mark.skip(reason="covered on CPU in test_host_cpu")
+def test_sd3_structure_matches_oracle():
+    from paddlemix_b200.ppdiffusers.transformer_sd3 import SD3Transformer2DModel
+    for name in ("sd3_medium", "tiny"):
+        cfg = O.SD3_CONFIGS[name]
+        assert SD3Transformer2DModel(**cfg).state_dict_shapes() == O.sd3_param_shapes(cfg)
