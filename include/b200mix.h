@@ -174,6 +174,11 @@ int b200mix_patchify(const void* x, int32_t x_fp32, void* y, int64_t B, int64_t 
 int b200mix_unpatchify(const void* x, void* y, int32_t y_fp32, int64_t B, int64_t C, int64_t h, int64_t w, int32_t p,
                        void* stream);
 
+/* Row gather / scatter on bf16 matrices with int64 device indices: the token-embedding lookup and the
+ * `inputs_embeds[image_mask] = image_embeds` merge of Qwen2-VL (modeling_qwen2_vl.py:1443,1449-1452). dim % 8 == 0. */
+int b200mix_gather_rows(const void* table, const int64_t* ids, void* out, int64_t n, int64_t dim, void* stream);
+int b200mix_scatter_rows(const void* src, const int64_t* idx, void* dst, int64_t n, int64_t dim, void* stream);
+
 /* fp32 <-> bf16 casts (round-to-nearest-even). */
 int b200mix_cast(const void* x, void* y, int64_t n, int32_t x_fp32, int32_t y_fp32, void* stream);
 

@@ -68,6 +68,8 @@ SIGNATURES = {
                           c_float, c_float, c_void_p],
     "b200mix_euler_step": [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_int64, c_float, c_float,
                            c_void_p],
+    "b200mix_gather_rows": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p],
+    "b200mix_scatter_rows": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p],
     "b200mix_cast": [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p],
     "b200mix_rope_inplace": [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p],
 }

@@ -267,6 +267,27 @@ __global__ void unpatchify_kernel(const __nv_bfloat16* __restrict__ x, void* __r
   }
 }
 
+// out[i, :] = table[ids[i], :]   (nn.Embedding lookup, modeling_qwen2_vl.py:1443) — 16-byte vectors
+__global__ void gather_rows_kernel(const uint4* __restrict__ table, const long long* __restrict__ ids,
+                                   uint4* __restrict__ out, long long n, int DV) {
+  const long long total = n * DV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / DV;
+    out[i] = __ldg(table + ids[r] * DV + (i - r * DV));
+  }
+}
+// dst[idx[i], :] = src[i, :]   (inputs_embeds[image_mask] = image_embeds, modeling_qwen2_vl.py:1449-1452)
+__global__ void scatter_rows_kernel(const uint4* __restrict__ src, const long long* __restrict__ idx,
+                                    uint4* __restrict__ dst, long long n, int DV) {
+  const long long total = n * DV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / DV;
+    dst[idx[r] * DV + (i - r * DV)] = __ldg(src + i);
+  }
+}
+
 static inline unsigned ew_grid(long long n, int threads) {
   long long g = (n + threads - 1) / threads;
   const long long cap = 148LL * 16;
@@ -358,7 +379,10 @@ extern "C" int b200mix_conv3x3_small_cin(const void* x, int32_t x_fp32, const vo
     configured = true;
   }
   const long long total = B * H * W * (Cout / 8);
-  conv3x3_small_cin_kernel<<<ew_grid(total, 256), 256, smem, ST(stream)>>>(
+  // every block first stages the whole filter bank in shared memory: keep the grid at ~2 blocks per SM
+  unsigned grid = ew_grid(total, 256);
+  if (grid > 2u * (unsigned)num_sms()) grid = 2u * (unsigned)num_sms();
+  conv3x3_small_cin_kernel<<<grid, 256, smem, ST(stream)>>>(
       x, x_fp32, reinterpret_cast<const __nv_bfloat16*>(w), bias, reinterpret_cast<__nv_bfloat16*>(y), (int)B, (int)H,
       (int)W, (int)Cin, (int)Cout);
   B200_LAUNCH_CHECK();
@@ -401,6 +425,28 @@ extern "C" int b200mix_unpatchify(const void* x, void* y, int32_t y_fp32, int64_
   B200_CHECK_ARG(x && y && p > 0, "unpatchify: bad arguments");
   unpatchify_kernel<<<ew_grid(B * C * h * w * p * p, 256), 256, 0, ST(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), y, y_fp32, (int)B, (int)C, (int)h, (int)w, p);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_gather_rows(const void* table, const int64_t* ids, void* out, int64_t n, int64_t dim,
+                                   void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(table && ids && out && n > 0 && dim % 8 == 0, "gather_rows: bad arguments (dim %% 8 == 0)");
+  gather_rows_kernel<<<ew_grid(n * (dim / 8), 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const uint4*>(table), reinterpret_cast<const long long*>(ids), reinterpret_cast<uint4*>(out), n,
+      (int)(dim / 8));
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_scatter_rows(const void* src, const int64_t* idx, void* dst, int64_t n, int64_t dim,
+                                    void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(src && idx && dst && n > 0 && dim % 8 == 0, "scatter_rows: bad arguments (dim %% 8 == 0)");
+  scatter_rows_kernel<<<ew_grid(n * (dim / 8), 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const uint4*>(src), reinterpret_cast<const long long*>(idx), reinterpret_cast<uint4*>(dst), n,
+      (int)(dim / 8));
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -5,8 +5,13 @@
 // ring -> tcgen05.mma (bf16 x bf16 -> fp32, 128 x BN x 16 per instruction) -> double-buffered TMEM accumulators ->
 // tcgen05.ld -> fused epilogue (bias / temb row-add / activation / GEGLU|SwiGLU / AdaLN gate / residual) -> HBM.
 //
-// Roles (192 threads): warp 0 = TMA producer (1 elected lane), warp 1 = TMEM owner + MMA issuer (1 elected lane),
-// warps 2..5 = epilogue (warp%4 selects the TMEM lane quarter). The epilogue of tile i overlaps the main loop of
+// CTAs run as clusters of 2 along M: both CTAs of a cluster work on the same n-tile, and each loads one half of the
+// weight tile with TMA multicast into both CTAs' shared memory, so the L2 -> SM traffic per MAC drops from
+// (128+BN)/(128*BN) to (128+BN/2)/(128*BN) (a 128x256 tile at full tensor rate would otherwise need ~14 KB/clk from
+// L2 chip-wide, more than L2 delivers). Stage hand-back is one multicast tcgen05.commit to both CTAs' empty barriers.
+//
+// Roles (320 threads): warp 0 = TMA producer (1 elected lane), warp 1 = TMEM owner + MMA issuer (1 elected lane),
+// warps 2..9 = epilogue (two warpgroups; warp%4 selects the TMEM lane quarter, the warpgroup the column chunks). The epilogue of tile i overlaps the main loop of
 // tile i+1 through the two TMEM accumulator stages.
 //
 // Replaces (reference): F.linear / F.conv2d call sites ppdiffusers/models/lora.py:365-377,453-459,
@@ -43,14 +48,31 @@ struct IGemmParams {
   long long res_row_mod;  // > 0: residual row = flat row % res_row_mod (a [rows, N] table shared by all groups)
 };
 
-__device__ __forceinline__ float act_silu(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float act_gelu_tanh(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float u = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(u));
+// Epilogue activations. All are of the form x * sigmoid(q(x)) and cost one ex2 + one rcp on the MUFU pipe, so a
+// GEGLU / SiLU epilogue stays well inside the tensor-core time of its tile.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ float act_quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float x_sigmoid_neg_log2(float x, float neg_q_log2e) {  // x / (1 + 2^neg_q_log2e)
+  return __fdividef(x, 1.0f + ex2_approx(neg_q_log2e));
+}
+__device__ __forceinline__ float act_silu(float x) { return x_sigmoid_neg_log2(x, -1.4426950408889634f * x); }
+// Exact-erf GELU  x * Phi(x)  with  Phi(x) = sigmoid(2 x (c0 + c1 x^2 + c2 x^4)),  coefficients fitted (minimax over
+// [-7,7]) so that |gelu_fast - gelu_erf| <= 3.1e-5 absolute: 250x below the bf16 rounding of the output.
+__device__ __forceinline__ float act_gelu_erf(float x) {
+  const float k = -2.0f * 1.4426950408889634f;
+  const float c0 = 7.97627599e-01f * k, c1 = 3.69255429e-02f * k, c2 = -3.41174308e-04f * k;
+  const float x2 = x * x;
+  return x_sigmoid_neg_log2(x, x * fmaf(fmaf(c2, x2, c1), x2, c0));
+}
+// tanh-GELU: 0.5 x (1 + tanh(u)) == x * sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3)   (identity, not an approximation)
+__device__ __forceinline__ float act_gelu_tanh(float x) {
+  const float k = -2.0f * 1.4426950408889634f * 0.7978845608028654f;
+  return x_sigmoid_neg_log2(x, x * fmaf(k * 0.044715f, x * x, k));
+}
+__device__ __forceinline__ float act_quick_gelu(float x) { return x_sigmoid_neg_log2(x, -1.702f * 1.4426950408889634f * x); }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
@@ -62,22 +84,45 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// Global-memory operands of one 32-column chunk of one accumulator row, fetched ahead of the TMEM load completing.
+struct EpiOperands {
+  float4 bias[8];
+  uint4 res[4];
+  bool vec;
+};
+
+__device__ __forceinline__ void epilogue_prefetch(const IGemmParams& p, EpiOperands& eo, long long r_off, long long g,
+                                                  int n_abs) {
+  const bool full = (n_abs + 32 <= p.N);
+  eo.vec = full && p.vec_ok;
+  if (p.bias && full) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_abs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) eo.bias[j] = __ldg(b4 + j);
+  }
+  if (p.residual && eo.vec) {
+    const uint4* rs = reinterpret_cast<const uint4*>(p.residual + r_off + n_abs);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) eo.res[j] = __ldg(rs + j);
+  }
+  (void)g;
+}
+
 // One 32-column chunk of one accumulator row -> global memory.
-__device__ __forceinline__ void epilogue_chunk(const IGemmParams& p, const uint32_t (&r)[32], long long c_off,
-                                               long long r_off, long long g, int n_abs) {
+__device__ __forceinline__ void epilogue_chunk(const IGemmParams& p, const uint32_t (&r)[32], const EpiOperands& eo,
+                                               long long c_off, long long r_off, long long g, int n_abs) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
   const bool full = (n_abs + 32 <= p.N);
-  const bool vec = full && p.vec_ok;
+  const bool vec = eo.vec;
 
   if (p.bias) {
     if (full) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_abs);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 b = __ldg(b4 + j);
-        v[4 * j + 0] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
+        v[4 * j + 0] += eo.bias[j].x, v[4 * j + 1] += eo.bias[j].y, v[4 * j + 2] += eo.bias[j].z,
+            v[4 * j + 3] += eo.bias[j].w;
       }
     } else {
 #pragma unroll
@@ -135,17 +180,17 @@ __device__ __forceinline__ void epilogue_chunk(const IGemmParams& p, const uint3
       if (full || n_abs + j < p.N) v[j] *= __ldg(rg + j);
   }
   if (p.residual) {
-    const __nv_bfloat16* rs = p.residual + r_off + n_abs;
     if (vec) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        uint4 w = __ldg(reinterpret_cast<const uint4*>(rs) + j);
+        const uint4 w = eo.res[j];
         v[8 * j + 0] += bf16_lo(w.x), v[8 * j + 1] += bf16_hi(w.x);
         v[8 * j + 2] += bf16_lo(w.y), v[8 * j + 3] += bf16_hi(w.y);
         v[8 * j + 4] += bf16_lo(w.z), v[8 * j + 5] += bf16_hi(w.z);
         v[8 * j + 6] += bf16_lo(w.w), v[8 * j + 7] += bf16_hi(w.w);
       }
     } else {
+      const __nv_bfloat16* rs = p.residual + r_off + n_abs;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (n_abs + j < p.N) v[j] += __bfloat162float(rs[j]);
@@ -194,7 +239,7 @@ struct IGemmCfg {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
     igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ IGemmParams p) {
   using Cfg = IGemmCfg<BN>;
@@ -212,11 +257,11 @@ __global__ void __launch_bounds__(192, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], 2);  // one multicast commit from each CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 128);
+      mbar_init(&tempty[s], 256);
     }
     fence_barrier_init();
     prefetch_tmap(&tmA);
@@ -225,11 +270,16 @@ __global__ void __launch_bounds__(192, 1)
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // barrier inits of both CTAs visible before any multicast TMA / remote commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  const uint32_t cta_rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
-  const int total_tiles = tiles_m * p.tiles_n;
+  const int tiles_m2 = (tiles_m + 1) >> 1;            // pairs of m-tiles (the odd one out pairs with a phantom)
+  const int total_super = tiles_m2 * p.tiles_n;
   const int kblocks = p.ntaps * p.kchunks;
 
   if (warp == 0) {
@@ -237,8 +287,9 @@ __global__ void __launch_bounds__(192, 1)
       // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+      for (int st = cluster_id; st < total_super; st += num_clusters) {
+        const int mp = st / p.tiles_n, nt = st - mp * p.tiles_n;
+        const int mt = mp * 2 + (int)cta_rank;  // may be == tiles_m (phantom): its A box is out of bounds -> zeros
         const int tx = mt % p.tiles_x;
         const int ty = (mt / p.tiles_x) % p.tiles_y;
         const int tb = mt / (p.tiles_x * p.tiles_y);
@@ -251,7 +302,9 @@ __global__ void __launch_bounds__(192, 1)
             uint8_t* sB = sA + Cfg::A_BYTES;
             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             tma_load_5d(sA, &tmA, &full_bar[stage], kc * 64 + dc, x0 + dx, pp, y0 + dy, b0);
-            tma_load_2d(sB, &tmB, &full_bar[stage], tap * p.Kc + kc * 64, n0);
+            // my half of the weight tile, delivered to both CTAs of the cluster
+            tma_load_2d_mcast(sB + cta_rank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], tap * p.Kc + kc * 64,
+                              n0 + (int)cta_rank * (BN / 2), (uint16_t)0x3);
             if (++stage == STAGES) stage = 0, phase ^= 1;
           }
         }
@@ -265,7 +318,7 @@ __global__ void __launch_bounds__(192, 1)
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int st = cluster_id; st < total_super; st += num_clusters) {
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
@@ -280,7 +333,7 @@ __global__ void __launch_bounds__(192, 1)
             const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
             umma_bf16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          umma_commit_mcast(&empty_bar[stage], (uint16_t)0x3);  // frees this stage in both CTAs
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
         umma_commit(&tfull[as]);
@@ -289,21 +342,24 @@ __global__ void __launch_bounds__(192, 1)
       }
     }
   } else {
-    // ===== epilogue warps =====
+    // ===== epilogue: two warpgroups (warps 2-5 and 6-9), each covering all four TMEM lane quarters; warpgroup g
+    // handles the 32-column chunks c == g (mod 2), so every SM sub-partition has two epilogue warps in flight =====
     const int q = warp & 3;
+    const int wg = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int tw = row % p.TW;
     const int th = (row / p.TW) % p.TH;
     const int tbb = row / (p.TW * p.TH);
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+    for (int st = cluster_id; st < total_super; st += num_clusters) {
+      const int mp = st / p.tiles_n, nt = st - mp * p.tiles_n;
+      const int mt = mp * 2 + (int)cta_rank;
       const int tx = mt % p.tiles_x;
       const int ty = (mt / p.tiles_x) % p.tiles_y;
       const int tb = mt / (p.tiles_x * p.tiles_y);
       const int x = tx * p.TW + tw, y = ty * p.TH + th, b = tb * p.TB + tbb;
-      const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.Bn);
+      const bool valid = (mt < tiles_m) && (x < p.Wo) && (y < p.Ho) && (b < p.Bn);
       const long long gm = (static_cast<long long>(b) * p.Ho + y) * p.Wo + x;
       long long g, c_off, r_off;
       if (p.c_bstride) {  // batched-strided: group == batch
@@ -320,11 +376,16 @@ __global__ void __launch_bounds__(192, 1)
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = wg; c < BN / 32; c += 2) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c * 32, r);
+        const int n_abs = n0 + c * 32;
+        const bool active = valid && n_abs < p.N;
+        // global operands of this chunk are requested before the TMEM load is waited for, so their latency overlaps
+        EpiOperands eo;
+        if (active) epilogue_prefetch(p, eo, r_off, g, n_abs);
         tmem_wait_ld();
-        if (valid && n0 + c * 32 < p.N) epilogue_chunk(p, r, c_off, r_off, g, n0 + c * 32);
+        if (active) epilogue_chunk(p, r, eo, c_off, r_off, g, n_abs);
       }
       tc_fence_before();
       mbar_arrive(&tempty[as]);
@@ -335,6 +396,7 @@ __global__ void __launch_bounds__(192, 1)
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer may still multicast into my smem / arrive on my barriers until it is done too
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -350,26 +412,41 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IG
     B200_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
-  const int total = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
-  int grid = num_sms();
-  if (grid > total) grid = total;
-  igemm_kernel<BN, STAGES><<<grid, 192, smem_bytes, stream>>>(tmA, tmB, p);
-  B200_LAUNCH_CHECK();
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int total_super = ((tiles_m + 1) / 2) * p.tiles_n;
+  int clusters = num_sms() / 2;
+  if (clusters > total_super) clusters = total_super;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, STAGES>, tmA, tmB, p));
   return 0;
 }
 
 static int pick_bn(long long tiles_m, long long N, int glu) {
+  // cost = waves x time per tile; time per tile ~ BN / efficiency(BN). Efficiencies are the measured mainloop rates of
+  // each tile width relative to BN=256 (tools/gemm_bench.py: a 128-wide tile is shared-memory-bandwidth bound on its
+  // operand reads, 8 KB per 64-cycle MMA), so narrower tiles are only chosen when they avoid wave / N-padding waste.
   const int cands[5] = {256, 160, 128, 64, 32};
+  const double eff[5] = {1.00, 0.86, 0.80, 0.50, 0.30};
   double best = 1e30;
-  int best_bn = 128;
-  const int sms = num_sms();
+  int best_bn = 256;
+  const int clusters = num_sms() / 2;
   for (int i = 0; i < 5; ++i) {
     const int bn = cands[i];
     const long long tn = (N + bn - 1) / bn;
-    const long long waves = (tiles_m * tn + sms - 1) / sms;
-    const double per_tile = (2 * bn > 128 + bn) ? 2.0 * bn : 128.0 + bn;  // MMA-bound vs smem-read-bound
-    const double cost = double(waves) * per_tile + 0.02 * per_tile;       // slight preference for fewer, larger tiles
-    if (cost < best) best = cost, best_bn = bn;
+    const long long waves = (((tiles_m + 1) / 2) * tn + clusters - 1) / clusters;
+    const double cost = double(waves) * (bn / eff[i]);
+    if (cost < best * 0.999) best = cost, best_bn = bn;
   }
   (void)glu;
   return best_bn;
@@ -384,7 +461,7 @@ static int dispatch_igemm(const CUtensorMap& tmA, const void* W, long long ldw, 
   {
     uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)p.N};
     uint64_t strides[1] = {(uint64_t)ldw * 2};
-    uint32_t box[2] = {64, (uint32_t)bn};
+    uint32_t box[2] = {64, (uint32_t)(bn / 2)};  // each CTA of the cluster loads (and multicasts) one half
     int rc = encode_tmap_bf16_sw128(&tmB, W, 2, dims, strides, box);
     if (rc) return rc;
   }

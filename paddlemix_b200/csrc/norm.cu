@@ -50,7 +50,20 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
     float s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = 0.0f, q[i] = 0.0f;
-    for (long long pix = p_begin + pl; pix < p_end; pix += PPB) {
+    long long pix = p_begin + pl;
+    for (; pix + 3LL * PPB < p_end; pix += 4LL * PPB) {  // 4 independent 16-byte loads in flight per thread
+      uint4 w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) w[u] = __ldg(reinterpret_cast<const uint4*>(src + (pix + (long long)u * PPB) * ld + cc));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(w[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += f[i], q[i] += f[i] * f[i];
+      }
+    }
+    for (; pix < p_end; pix += PPB) {
       const uint4 w = __ldg(reinterpret_cast<const uint4*>(src + pix * ld + cc));
       float f[8];
       unpack8(w, f);
@@ -118,7 +131,24 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
   __nv_bfloat16* dst = y + static_cast<long long>(b) * HW * C + c0;
   const long long p_begin = static_cast<long long>(blockIdx.x) * pix_per_cta;
   const long long p_end = min(HW, p_begin + pix_per_cta);
-  for (long long pix = p_begin + pl; pix < p_end; pix += PPB) {
+  long long pix = p_begin + pl;
+  for (; pix + 3LL * PPB < p_end; pix += 4LL * PPB) {
+    uint4 w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) w[u] = __ldg(reinterpret_cast<const uint4*>(src + (pix + (long long)u * PPB) * ld + cc));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(w[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = fmaf(f[i], a[i], sh[i]);
+        f[i] = silu ? silu_f(v) : v;
+      }
+      *reinterpret_cast<uint4*>(dst + (pix + (long long)u * PPB) * C) = pack8(f);
+    }
+  }
+  for (; pix < p_end; pix += PPB) {
     const uint4 w = __ldg(reinterpret_cast<const uint4*>(src + pix * ld + cc));
     float f[8];
     unpack8(w, f);
@@ -152,100 +182,130 @@ struct LNParams {
   int rms;
 };
 
-template <int VPL>
-__global__ void __launch_bounds__(256) layernorm_kernel(const LNParams p) {
+// Each warp normalises ROWS consecutive rows at once: all ROWS*VPL 16-byte loads of a lane are issued before the
+// first reduction, which is what keeps enough bytes in flight per SM to approach HBM bandwidth on short rows.
+template <int VPL, int ROWS>
+__global__ void __launch_bounds__(256, (VPL * ROWS > 12) ? 1 : 2) layernorm_kernel(const LNParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
-  if (row >= p.M) return;
+  const long long row0 = (static_cast<long long>(blockIdx.x) * 8 + warp) * ROWS;
+  if (row0 >= p.M) return;
   const int NV = p.N >> 3;
-  const long long g = row / p.rows_per_group;
-  const __nv_bfloat16* xr = p.x + row * p.N;
-  float v[VPL][8];
-  float sum = 0.0f;
+  float v[ROWS][VPL][8];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + 32 * i;
-    if (vi < NV) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + vi), v[i]);
-      if (p.delta) {
+  for (int r = 0; r < ROWS; ++r) {
+    const long long row = row0 + r;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + 32 * i;
+      if (row < p.M && vi < NV) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p.x + row * p.N) + vi), v[r][i]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[r][i][k] = 0.0f;
+      }
+    }
+  }
+  if (p.delta) {
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = row0 + r;
+      if (row >= p.M) continue;
+      const long long g = row / p.rows_per_group;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi >= NV) continue;
         float d[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(p.delta + row * p.N) + vi), d);
         if (p.gate) {
           const float* gp = p.gate + g * p.ld_mod + vi * 8;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[i][k] = fmaf(__ldg(gp + k), d[k], v[i][k]);
+          for (int k = 0; k < 8; ++k) v[r][i][k] = fmaf(__ldg(gp + k), d[k], v[r][i][k]);
         } else {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[i][k] += d[k];
+          for (int k = 0; k < 8; ++k) v[r][i][k] += d[k];
         }
         if (p.resid_out) {
           // the residual stream is stored in bf16: normalise the rounded value so both outputs agree
-          uint4 w = pack8(v[i]);
+          uint4 w = pack8(v[r][i]);
           *(reinterpret_cast<uint4*>(p.resid_out + row * p.N) + vi) = w;
-          unpack8(w, v[i]);
+          unpack8(w, v[r][i]);
         }
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) sum += v[i][k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[i][k] = 0.0f;
     }
   }
-  float mean = 0.0f;
-  if (!p.rms) {
+  float mean[ROWS], rstd[ROWS];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    mean = sum / p.N;
+  for (int r = 0; r < ROWS; ++r) {
+    mean[r] = 0.0f;
+    if (!p.rms) {
+      float s = 0.0f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[r][i][k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      mean[r] = s / p.N;
+    }
   }
-  float sq = 0.0f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + 32 * i;
-    if (vi < NV) {
+  for (int r = 0; r < ROWS; ++r) {
+    float sq = 0.0f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float d = v[i][k] - mean;
-        sq += d * d;
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < NV) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float d = v[r][i][k] - mean[r];
+          sq += d * d;
+        }
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / p.N + p.eps);
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    rstd[r] = rsqrtf(sq / p.N + p.eps);
+  }
 
-  __nv_bfloat16* yr = p.y + row * p.N;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + 32 * i;
-    if (vi < NV) {
-      float o[8];
+  for (int r = 0; r < ROWS; ++r) {
+    const long long row = row0 + r;
+    if (row >= p.M) continue;
+    const long long g = row / p.rows_per_group;
+    __nv_bfloat16* yr = p.y + row * p.N;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = (v[i][k] - mean) * rstd;
-      if (p.rms && p.weight) {
-        // Qwen2RMSNorm: normalised value is cast to the activation dtype first, then multiplied by the weight
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < NV) {
+        float o[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          o[k] = __bfloat162float(__float2bfloat16(o[k])) * __ldg(p.weight + vi * 8 + k);
-      } else if (p.weight) {
+        for (int k = 0; k < 8; ++k) o[k] = (v[r][i][k] - mean[r]) * rstd[r];
+        if (p.rms && p.weight) {
+          // Qwen2RMSNorm: normalised value is cast to the activation dtype first, then multiplied by the weight
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] *= __ldg(p.weight + vi * 8 + k);
+          for (int k = 0; k < 8; ++k)
+            o[k] = __bfloat162float(__float2bfloat16(o[k])) * __ldg(p.weight + vi * 8 + k);
+        } else if (p.weight) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] *= __ldg(p.weight + vi * 8 + k);
+        }
+        if (p.bias) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] += __ldg(p.bias + vi * 8 + k);
+        }
+        if (p.scale) {
+          const float* sp = p.scale + g * p.ld_mod + vi * 8;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] *= (1.0f + __ldg(sp + k));
+        }
+        if (p.shift) {
+          const float* sp = p.shift + g * p.ld_mod + vi * 8;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] += __ldg(sp + k);
+        }
+        *(reinterpret_cast<uint4*>(yr) + vi) = pack8(o);
       }
-      if (p.bias) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] += __ldg(p.bias + vi * 8 + k);
-      }
-      if (p.scale) {
-        const float* sp = p.scale + g * p.ld_mod + vi * 8;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] *= (1.0f + __ldg(sp + k));
-      }
-      if (p.shift) {
-        const float* sp = p.shift + g * p.ld_mod + vi * 8;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] += __ldg(sp + k);
-      }
-      *(reinterpret_cast<uint4*>(yr) + vi) = pack8(o);
     }
   }
 }
@@ -309,14 +369,19 @@ extern "C" int b200mix_layernorm(const void* x, const void* delta, const float* 
   p.rows_per_group = rows_per_group > 0 ? rows_per_group : M;
   p.M = M, p.N = (int)N, p.eps = eps, p.rms = rms;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const unsigned grid = (unsigned)((M + 7) / 8);
   const int nv = (int)(N / 8);
-  if (nv <= 64) layernorm_kernel<2><<<grid, 256, 0, st>>>(p);
-  else if (nv <= 128) layernorm_kernel<4><<<grid, 256, 0, st>>>(p);
-  else if (nv <= 192) layernorm_kernel<6><<<grid, 256, 0, st>>>(p);
-  else if (nv <= 256) layernorm_kernel<8><<<grid, 256, 0, st>>>(p);
-  else if (nv <= 512) layernorm_kernel<16><<<grid, 256, 0, st>>>(p);
-  else layernorm_kernel<32><<<grid, 256, 0, st>>>(p);
+#define LN_LAUNCH(VPL, ROWS) \
+  layernorm_kernel<VPL, ROWS><<<(unsigned)((M + 8 * ROWS - 1) / (8 * ROWS)), 256, 0, st>>>(p)
+  if (nv <= 32) LN_LAUNCH(1, 8);
+  else if (nv <= 64) LN_LAUNCH(2, 4);
+  else if (nv <= 96) LN_LAUNCH(3, 4);
+  else if (nv <= 128) LN_LAUNCH(4, 2);
+  else if (nv <= 160) LN_LAUNCH(5, 2);
+  else if (nv <= 192) LN_LAUNCH(6, 2);
+  else if (nv <= 256) LN_LAUNCH(8, 1);
+  else if (nv <= 512) LN_LAUNCH(16, 1);
+  else LN_LAUNCH(32, 1);
+#undef LN_LAUNCH
   B200_LAUNCH_CHECK();
   return 0;
 }

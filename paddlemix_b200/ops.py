@@ -375,3 +375,22 @@ def rope_inplace(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, rot_dim:
           "b200mix_rope_inplace")
     _count()
     return x
+
+
+def gather_rows(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """table bf16 [V, D], ids int64 [n] (device) -> bf16 [n, D]."""
+    _req(table, bf16, "table"), _req(ids, torch.int64, "ids")
+    n, D = ids.numel(), table.shape[1]
+    out = torch.empty(n, D, device=table.device, dtype=bf16)
+    check(lib.b200mix_gather_rows(_p(table), _p(ids), _p(out), n, D, _stream()), "b200mix_gather_rows")
+    _count()
+    return out
+
+
+def scatter_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[idx[i]] = src[i]; src bf16 [n, D], idx int64 [n] (device), dst bf16 [*, D] (in place)."""
+    _req(src, bf16, "src"), _req(idx, torch.int64, "idx"), _req(dst, bf16, "dst")
+    check(lib.b200mix_scatter_rows(_p(src), _p(idx), _p(dst), idx.numel(), src.shape[-1], _stream()),
+          "b200mix_scatter_rows")
+    _count()
+    return dst

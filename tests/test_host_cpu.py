@@ -68,6 +68,25 @@ def test_sd3_structure_matches_oracle():
     assert abs(O3.sd3_flops(O3.SD3_CONFIGS["sd3_medium"], 1, 128, 128, 154) / 1e12 - 8.437) < 5e-3
 
 
+def test_qwen2vl_structure_and_rope_index_match_oracle():
+    from oracle import qwen2vl as OQ
+    from paddlemix_b200.qwen2_vl import Qwen2VLForConditionalGeneration
+    for name in ("qwen2vl_7b", "tiny"):
+        cfg = OQ.QWEN2VL_CONFIGS[name]
+        assert Qwen2VLForConditionalGeneration(cfg).state_dict_shapes() == OQ.qwen2vl_param_shapes(cfg)
+    cfg = OQ.QWEN2VL_CONFIGS["qwen2vl_7b"]
+    m = Qwen2VLForConditionalGeneration(cfg)
+    g = torch.Generator().manual_seed(0)
+    grid = [[1, 32, 32]] * 2  # BASELINE config C4: 448x448 image -> 1024 patches -> 256 merged tokens + 510 text
+    rows = [[cfg["vision_start_token_id"]] + [cfg["image_token_id"]] * 256 + [cfg["vision_end_token_id"]] +
+            torch.randint(0, 151643, (510,), generator=g).tolist() for _ in range(2)]
+    ids = torch.tensor(rows)
+    po, do = OQ.get_rope_index(cfg, ids, grid)
+    pm, dm = m.get_rope_index(ids, torch.tensor(grid))
+    assert ids.shape == (2, 768) and torch.equal(po, pm) and torch.equal(do, dm)
+    assert torch.equal(m.rot_pos_emb(grid), OQ.rot_pos_emb(cfg, grid))
+
+
 def test_config_errors_mirror_reference():
     from paddlemix_b200.ppdiffusers.unet_2d_condition import UNet2DConditionModel
     with pytest.raises(ValueError, match="same number of `down_block_types`"):

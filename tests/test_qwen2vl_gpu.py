@@ -1,0 +1,48 @@
+"""Qwen2-VL prefill parity on the GPU: paddlemix_b200.qwen2_vl against the CPU fp32 oracle (itself cross-checked
+against HF transformers in tests/test_oracle_qwen2vl_vs_hf.py). Stated tolerance (bf16 pipeline vs fp32): cosine
+>= 0.999 on the logits and max |err| <= 4 % of the logit range."""
+import pytest
+import torch
+
+from oracle import qwen2vl as O
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+
+def _inputs(cfg, grid, n_text, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    m2 = cfg["vision"]["spatial_merge_size"] ** 2
+    T = sum(t * h * w for t, h, w in grid)
+    pv = torch.randn(T, 3 * 2 * 14 * 14, generator=g).to(bf16).float()
+    rows = []
+    for (t, h, w), nt in zip(grid, n_text):
+        rows.append([cfg["vision_start_token_id"]] + [cfg["image_token_id"]] * (t * h * w // m2) +
+                    [cfg["vision_end_token_id"]] + torch.randint(0, 1000, (nt,), generator=g).tolist())
+    return torch.tensor(rows), pv
+
+
+@pytest.mark.parametrize("grid,n_text", [([[1, 8, 8], [1, 4, 8]], [20, 28]), ([[1, 16, 16]], [62])])
+def test_qwen2vl_tiny_prefill_parity(grid, n_text):
+    from paddlemix_b200.qwen2_vl import Qwen2VLForConditionalGeneration
+    cfg = O.QWEN2VL_CONFIGS["tiny"]
+    P = O.init_qwen2vl_params(cfg, seed=1)
+    model = Qwen2VLForConditionalGeneration(cfg).load_state_dict(P, device=0)
+    assert model.state_dict_shapes() == O.qwen2vl_param_shapes(cfg)
+    input_ids, pv = _inputs(cfg, grid, n_text)
+    ref = O.qwen2vl_prefill(cfg, P, input_ids, pv, grid)
+    out = model(input_ids=input_ids, attention_mask=torch.ones_like(input_ids), pixel_values=pv.cuda(),
+                image_grid_thw=torch.tensor(grid))
+    assert out.logits.shape == ref.shape and out.logits.dtype == torch.float32
+    o = out.logits.cpu()
+    cos = torch.nn.functional.cosine_similarity(o.flatten(), ref.flatten(), dim=0).item()
+    err = (o - ref).abs().max().item() / ref.abs().max().item()
+    assert cos >= 0.999 and err <= 0.04, (cos, err)
+    pos_o, d_o = O.get_rope_index(cfg, input_ids, grid)
+    pos_m, d_m = model.get_rope_index(input_ids, torch.tensor(grid))
+    assert torch.equal(pos_o, pos_m) and torch.equal(d_o, d_m)  # integer index math: bit-exact
+    # text-only prefill (no image): 1-D RoPE degenerates from M-RoPE
+    ids2 = input_ids[:, -16:].contiguous()
+    ref2 = O.qwen2vl_prefill(cfg, P, ids2, None, None, position_ids=torch.arange(16).reshape(1, 1, -1).expand(3, ids2.shape[0], -1))
+    out2 = model(input_ids=ids2).logits.cpu()
+    assert torch.nn.functional.cosine_similarity(out2.flatten(), ref2.flatten(), dim=0).item() >= 0.999
