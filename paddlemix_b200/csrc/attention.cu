@@ -45,15 +45,30 @@ __device__ __forceinline__ void tma_load_rows(void* dst, const CUtensorMap* m, u
   tma_load_4d(dst, m, bar, c[0], c[1], c[2], c[3]);
 }
 
+// Per-head-dim configuration. D = 64 (the SD / SDXL / SD3 case) is limited by the exponential (MUFU) rate, not by the
+// tensor cores, so it runs TWO CTAs per SM (single S buffer, 2-deep K/V ring, 256 TMEM columns): while one CTA's
+// softmax warps exponentiate, the other CTA's MMAs use the tensor cores. D >= 128 keeps one CTA per SM with a
+// double-buffered S so QK^T(j+1) overlaps softmax(j) inside the CTA.
 template <int D>
-__global__ void __launch_bounds__(192, 1)
+struct AttnCfg {
+  static constexpr int SB = (D == 64) ? 1 : 2;                      // S accumulator buffers in TMEM
+  static constexpr int KS = (D == 192) ? 1 : 2;                     // K/V ring depth
+  static constexpr int TMEM_COLS = (D == 64) ? 256 : 512;           // SB*128 (S) + D (O), rounded to a power of 2
+  static constexpr int MIN_CTAS = (D == 64) ? 2 : 1;
+  // dynamic smem is declared __align__(1024) (128B-swizzle atoms), so no alignment slack: two D=64 CTAs fit one SM
+  static constexpr int SMEM = (1 + 2 * KS) * 128 * D * 2 + 128 * 128 * 2 + 256;
+};
+
+template <int D>
+__global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
     attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
   constexpr int DC = D / 64;               // 64-wide head-dim chunks (one 128B swizzle atom each)
   constexpr int TILE_BYTES = 128 * D * 2;  // one 128-row tile of Q / K / V
-  constexpr int KS = (D == 64) ? 3 : (D == 128 ? 2 : 1);  // K/V ring depth
+  constexpr int KS = AttnCfg<D>::KS;
+  constexpr int SB = AttnCfg<D>::SB;
   constexpr int P_BYTES = 128 * 128 * 2;
-  constexpr uint32_t TM_S = 0, TM_O = 256;
+  constexpr uint32_t TM_S = 0, TM_O = SB * 128;
 
   // ---- which tile am I? (uniform across the CTA) ----
   int qt = blockIdx.x;
@@ -92,8 +107,7 @@ __global__ void __launch_bounds__(192, 1)
   const int n_tiles = (n_kv + 127) >> 7;
   const int hk = h / (p.Hq / p.Hkv);
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + TILE_BYTES;
   uint8_t* sV = sK + KS * TILE_BYTES;
@@ -107,7 +121,8 @@ __global__ void __launch_bounds__(192, 1)
   uint64_t* s_full = v_empty + KS;    // 2
   uint64_t* p_full = s_full + 2;      // 1
   uint64_t* pv_done = p_full + 1;     // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint64_t* s_empty = pv_done + 1;    // 1 (used when SB == 1: softmax has drained S into registers)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -122,12 +137,13 @@ __global__ void __launch_bounds__(192, 1)
     mbar_init(&s_full[1], 1);
     mbar_init(p_full, 128);
     mbar_init(pv_done, 1);
+    mbar_init(s_empty, 128);
     fence_barrier_init();
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc<AttnCfg<D>::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -164,7 +180,7 @@ __global__ void __launch_bounds__(192, 1)
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
       auto issue_qk = [&](int j, int st) {
         const uint32_t k_addr = smem_u32(sK + st * TILE_BYTES);
-        const uint32_t d_tmem = tmem_base + TM_S + (j & 1) * 128;
+        const uint32_t d_tmem = tmem_base + TM_S + (j % SB) * 128;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
@@ -186,10 +202,11 @@ __global__ void __launch_bounds__(192, 1)
       for (int j = 0; j < n_tiles; ++j) {
         if (j + 1 < n_tiles) {
           mbar_wait(&k_full[kst], kph);
+          if (SB == 1) mbar_wait(s_empty, j & 1);  // softmax(j) has copied S out of TMEM
           tc_fence_after();
           issue_qk(j + 1, kst);
           umma_commit(&k_empty[kst]);
-          umma_commit(&s_full[(j + 1) & 1]);
+          umma_commit(&s_full[(j + 1) % SB]);
           if (++kst == KS) kst = 0, kph ^= 1;
         }
         mbar_wait(p_full, j & 1);
@@ -218,12 +235,16 @@ __global__ void __launch_bounds__(192, 1)
     const int sw = row & 7;
 
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&s_full[j % SB], (j / SB) & 1);
       tc_fence_after();
       uint32_t sv[4][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(lane_base + TM_S + (j & 1) * 128 + c * 32, sv[c]);
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(lane_base + TM_S + (j % SB) * 128 + c * 32, sv[c]);
       tmem_wait_ld();
+      if (SB == 1) {
+        tc_fence_before();
+        mbar_arrive(s_empty);
+      }
 
       const int limit = min(kv_len, row_limit_base) - j * 128;  // columns [0, limit) of this tile are visible
       float mx = -INFINITY;
@@ -252,22 +273,8 @@ __global__ void __launch_bounds__(192, 1)
       }
       const float m_scaled = (m == -INFINITY) ? 0.0f : m * p.scale_log2;
 
-      // exponentiate, accumulate the row sum in fp32, pack P to bf16
-      uint32_t pk[64];
-      float sum = 0.0f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float e0 = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_scaled));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, -m_scaled));
-          sum += e0 + e1;
-          pk[c * 16 + (i >> 1)] = pack_bf16x2(e0, e1);
-        }
-      l += sum;
-
       if (j > 0) {
-        // O (and the P buffer) are free once PV_{j-1} has completed
+        // O (and the single P buffer) are free once PV_{j-1} has completed
         mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, grow)) {
@@ -283,13 +290,24 @@ __global__ void __launch_bounds__(192, 1)
           tmem_wait_st();
         }
       }
-      // P -> smem in the K-major SW128 layout the MMA expects (16-byte unit u of row r lives at u ^ (r & 7))
+      // exponentiate (row sum in fp32), pack P to bf16 and stream it into the K-major SW128 layout the second MMA
+      // expects (16-byte unit u of row r lives at u ^ (r & 7)); 8 columns at a time keeps the register footprint low
+      float sum = 0.0f;
 #pragma unroll
       for (int g8 = 0; g8 < 16; ++g8) {
+        uint32_t w[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int col = g8 * 8 + t * 2;
+          const float e0 = fast_exp2(fmaf(__uint_as_float(sv[col >> 5][col & 31]), p.scale_log2, -m_scaled));
+          const float e1 = fast_exp2(fmaf(__uint_as_float(sv[col >> 5][(col & 31) + 1]), p.scale_log2, -m_scaled));
+          sum += e0 + e1;
+          w[t] = pack_bf16x2(e0, e1);
+        }
         const int chunk = g8 >> 3, u = g8 & 7;
-        uint4 w = make_uint4(pk[g8 * 4 + 0], pk[g8 * 4 + 1], pk[g8 * 4 + 2], pk[g8 * 4 + 3]);
-        *reinterpret_cast<uint4*>(p_row + chunk * 16384 + ((u ^ sw) << 4)) = w;
+        *reinterpret_cast<uint4*>(p_row + chunk * 16384 + ((u ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
+      l += sum;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
@@ -326,7 +344,7 @@ __global__ void __launch_bounds__(192, 1)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<AttnCfg<D>::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -360,8 +378,7 @@ static int make_attn_tmap(CUtensorMap* tm, const void* ptr, int64_t D, int64_t S
 template <int D>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        dim3 grid, cudaStream_t stream) {
-  constexpr int KS = (D == 64) ? 3 : (D == 128 ? 2 : 1);
-  constexpr int smem_bytes = (1 + 2 * KS) * 128 * D * 2 + 128 * 128 * 2 + 1024 + 256;
+  constexpr int smem_bytes = AttnCfg<D>::SMEM;
   static bool configured = false;
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

@@ -87,29 +87,42 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
   }
 }
 
+// One block per batch element: (sum, sumsq) partials of all CTAs -> (mean, rstd) per group, fixed summation order.
+__global__ void gn_finalize_kernel(const double* __restrict__ partial, float* __restrict__ mr, int gx, int groups,
+                                   double n, float eps) {
+  __shared__ double sh[256][2];
+  const int b = blockIdx.x;
+  const int per = blockDim.x / groups;  // threads cooperating on one group (host guarantees >= 1)
+  const int g = threadIdx.x / per, j = threadIdx.x % per;
+  double su = 0.0, sq = 0.0;
+  if (g < groups) {
+    const double* src = partial + (static_cast<long long>(b) * gx * groups + g) * 2;
+    for (int i = j; i < gx; i += per) su += src[static_cast<size_t>(i) * groups * 2], sq += src[static_cast<size_t>(i) * groups * 2 + 1];
+  }
+  sh[threadIdx.x][0] = su, sh[threadIdx.x][1] = sq;
+  __syncthreads();
+  if (g < groups && j == 0) {
+    double a = 0.0, c = 0.0;
+    for (int t = 0; t < per; ++t) a += sh[threadIdx.x + t][0], c += sh[threadIdx.x + t][1];
+    const double mean = a / n;
+    double var = c / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mr[(b * groups + g) * 2 + 0] = static_cast<float>(mean);
+    mr[(b * groups + g) * 2 + 1] = rsqrtf(static_cast<float>(var) + eps);
+  }
+}
+
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2,
                                 int C2, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                __nv_bfloat16* __restrict__ y, const double* __restrict__ partial, long long HW,
-                                int groups, float eps, int silu, int PPB, int pix_per_cta) {
-  extern __shared__ float sm[];  // [groups][2] = (mean, rstd)
+                                __nv_bfloat16* __restrict__ y, const float* __restrict__ mr, long long HW,
+                                int groups, int silu, int PPB, int pix_per_cta) {
   const int C = C1 + C2;
   const int CV = C >> 3;
   const int cv = threadIdx.x % CV;
   const int pl = threadIdx.x / CV;
   const int b = blockIdx.y;
   const int cpg = C / groups;
-  const double n = static_cast<double>(HW) * cpg;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    double su = 0.0, sq = 0.0;
-    const double* src = partial + (static_cast<long long>(b) * gridDim.x * groups + g) * 2;
-    for (unsigned i = 0; i < gridDim.x; ++i) su += src[static_cast<size_t>(i) * groups * 2], sq += src[static_cast<size_t>(i) * groups * 2 + 1];
-    const double mean = su / n;
-    double var = sq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    sm[2 * g] = static_cast<float>(mean);
-    sm[2 * g + 1] = rsqrtf(static_cast<float>(var) + eps);
-  }
-  __syncthreads();
+  const float* sm = mr + static_cast<long long>(b) * groups * 2;  // (mean, rstd) per group
   if (pl >= PPB) return;
   const int c0 = cv * 8;
   float a[8], sh[8];
@@ -117,8 +130,8 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
   for (int i = 0; i < 8; ++i) {
     const int c = c0 + i;
     const int g = c / cpg;
-    a[i] = sm[2 * g + 1] * gamma[c];
-    sh[i] = beta[c] - sm[2 * g] * a[i];
+    a[i] = __ldg(sm + 2 * g + 1) * gamma[c];
+    sh[i] = beta[c] - __ldg(sm + 2 * g) * a[i];
   }
   const __nv_bfloat16* src;
   long long ld;
@@ -210,7 +223,7 @@ __global__ void __launch_bounds__(256, (VPL * ROWS > 12) ? 1 : 2) layernorm_kern
     for (int r = 0; r < ROWS; ++r) {
       const long long row = row0 + r;
       if (row >= p.M) continue;
-      const long long g = row / p.rows_per_group;
+      const long long g = static_cast<long long>(static_cast<unsigned>(row) / static_cast<unsigned>(p.rows_per_group));
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         const int vi = lane + 32 * i;
@@ -268,44 +281,56 @@ __global__ void __launch_bounds__(256, (VPL * ROWS > 12) ? 1 : 2) layernorm_kern
     rstd[r] = rsqrtf(sq / p.N + p.eps);
   }
 
+  // output: columns are the same for all ROWS rows of a lane, so the affine vectors are loaded once (16-byte loads)
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
-    const long long row = row0 + r;
-    if (row >= p.M) continue;
-    const long long g = row / p.rows_per_group;
-    __nv_bfloat16* yr = p.y + row * p.N;
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi >= NV) continue;
+    float wv[8], bv[8];
+    if (p.weight) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p.weight) + 2 * vi);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.weight) + 2 * vi + 1);
+      wv[0] = a.x, wv[1] = a.y, wv[2] = a.z, wv[3] = a.w, wv[4] = b.x, wv[5] = b.y, wv[6] = b.z, wv[7] = b.w;
+    }
+    if (p.bias) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p.bias) + 2 * vi);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + 2 * vi + 1);
+      bv[0] = a.x, bv[1] = a.y, bv[2] = a.z, bv[3] = a.w, bv[4] = b.x, bv[5] = b.y, bv[6] = b.z, bv[7] = b.w;
+    }
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int vi = lane + 32 * i;
-      if (vi < NV) {
-        float o[8];
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = row0 + r;
+      if (row >= p.M) continue;
+      float o[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = (v[r][i][k] - mean[r]) * rstd[r];
-        if (p.rms && p.weight) {
-          // Qwen2RMSNorm: normalised value is cast to the activation dtype first, then multiplied by the weight
+      for (int k = 0; k < 8; ++k) o[k] = (v[r][i][k] - mean[r]) * rstd[r];
+      if (p.rms && p.weight) {
+        // Qwen2RMSNorm: normalised value is cast to the activation dtype first, then multiplied by the weight
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            o[k] = __bfloat162float(__float2bfloat16(o[k])) * __ldg(p.weight + vi * 8 + k);
-        } else if (p.weight) {
+        for (int k = 0; k < 8; ++k) o[k] = __bfloat162float(__float2bfloat16(o[k])) * wv[k];
+      } else if (p.weight) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] *= __ldg(p.weight + vi * 8 + k);
-        }
-        if (p.bias) {
+        for (int k = 0; k < 8; ++k) o[k] *= wv[k];
+      }
+      if (p.bias) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] += __ldg(p.bias + vi * 8 + k);
-        }
+        for (int k = 0; k < 8; ++k) o[k] += bv[k];
+      }
+      if (p.scale || p.shift) {
+        const long long g = static_cast<long long>(static_cast<unsigned>(row) / static_cast<unsigned>(p.rows_per_group));
         if (p.scale) {
-          const float* sp = p.scale + g * p.ld_mod + vi * 8;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] *= (1.0f + __ldg(sp + k));
+          const float4* sp = reinterpret_cast<const float4*>(p.scale + g * p.ld_mod) + 2 * vi;
+          const float4 a = __ldg(sp), b = __ldg(sp + 1);
+          o[0] *= 1.0f + a.x, o[1] *= 1.0f + a.y, o[2] *= 1.0f + a.z, o[3] *= 1.0f + a.w;
+          o[4] *= 1.0f + b.x, o[5] *= 1.0f + b.y, o[6] *= 1.0f + b.z, o[7] *= 1.0f + b.w;
         }
         if (p.shift) {
-          const float* sp = p.shift + g * p.ld_mod + vi * 8;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] += __ldg(sp + k);
+          const float4* sp = reinterpret_cast<const float4*>(p.shift + g * p.ld_mod) + 2 * vi;
+          const float4 a = __ldg(sp), b = __ldg(sp + 1);
+          o[0] += a.x, o[1] += a.y, o[2] += a.z, o[3] += a.w, o[4] += b.x, o[5] += b.y, o[6] += b.z, o[7] += b.w;
         }
-        *(reinterpret_cast<uint4*>(yr) + vi) = pack8(o);
       }
+      *(reinterpret_cast<uint4*>(p.y + row * p.N) + vi) = pack8(o);
     }
   }
 }
@@ -334,16 +359,24 @@ extern "C" int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2
   if (pix_per_cta < PPB) pix_per_cta = PPB;
   const unsigned gx = (unsigned)((HW + pix_per_cta - 1) / pix_per_cta);
   double* dstats = reinterpret_cast<double*>(stats);
-  B200_CHECK_ARG((long long)gx * B * groups * 2 * 8 <= stats_bytes,
-                 "groupnorm: stats scratch too small (%lld bytes needed)", (long long)gx * B * groups * 16);
+  B200_CHECK_ARG((long long)gx * B * groups * 2 * 8 + (long long)B * groups * 2 * 4 <= stats_bytes,
+                 "groupnorm: stats scratch too small (%lld bytes needed)", (long long)gx * B * groups * 16 + B * groups * 8);
+  B200_CHECK_ARG(groups <= 256, "groupnorm: at most 256 groups");
+  float* mr = reinterpret_cast<float*>(dstats + (long long)gx * B * groups * 2);
   dim3 grid(gx, (unsigned)B);
   gn_stats_kernel<<<grid, threads, (size_t)PPB * 2 * C * sizeof(float), st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x1), (int)C1, reinterpret_cast<const __nv_bfloat16*>(x2), (int)C2, dstats,
       HW, groups, PPB, (int)pix_per_cta);
   B200_LAUNCH_CHECK();
-  gn_apply_kernel<<<grid, threads, 2 * groups * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(x1), (int)C1,
+  {
+    int fthreads = 256 / groups * groups;  // a whole number of threads per group
+    gn_finalize_kernel<<<(unsigned)B, fthreads, 0, st>>>(dstats, mr, (int)gx, groups,
+                                                         static_cast<double>(HW) * (double)(C / groups), eps);
+    B200_LAUNCH_CHECK();
+  }
+  gn_apply_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x1), (int)C1,
                                             reinterpret_cast<const __nv_bfloat16*>(x2), (int)C2, gamma, beta,
-                                            reinterpret_cast<__nv_bfloat16*>(y), dstats, HW, groups, eps, silu, PPB,
+                                            reinterpret_cast<__nv_bfloat16*>(y), mr, HW, groups, silu, PPB,
                                             (int)pix_per_cta);
   B200_LAUNCH_CHECK();
   return 0;

@@ -247,7 +247,7 @@ def groupnorm_nhwc(x1: torch.Tensor, gamma, beta, *, x2=None, groups=32, eps=1e-
     with _Timed("groupnorm", 2.0 * 2 * B * HW * (C1 + C2), "byte"):  # algorithmic: read once + write once (bf16)
         check(lib.b200mix_groupnorm_nhwc(_p(x1), C1, _p(x2), C2, _p(gamma), _p(beta), _p(out), _p(st), st.numel() * 8, B,
                                          HW, groups, float(eps), 1 if silu else 0, _stream()), "b200mix_groupnorm_nhwc")
-    _count(2)
+    _count(3)
     return out
 
 

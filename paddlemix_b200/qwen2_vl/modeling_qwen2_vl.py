@@ -308,8 +308,6 @@ class Qwen2VLForConditionalGeneration:
                 pixel_values=None, pixel_values_videos=None, image_grid_thw=None, video_grid_thw=None,
                 rope_deltas=None):
         """Same signature as the reference (:1382-1399). Prefill only: no KV cache in / out, attention_mask all ones."""
-        from .. import ops
-        from .._lib import GLU_SWIGLU
         if self.device is None:
             raise RuntimeError("load_state_dict() must be called before forward()")
         for name, val in (("past_key_values", past_key_values), ("labels", labels), ("pixel_values_videos", pixel_values_videos),
@@ -320,21 +318,35 @@ class Qwen2VLForConditionalGeneration:
             raise NotImplementedError("use_cache / output_attentions / output_hidden_states are outside the prefill hot path")
         if attention_mask is not None and not bool((attention_mask == 1).all()):
             raise NotImplementedError("padded batches are outside the prefill hot path (attention_mask must be all ones)")
-        c, dev, hd = self.config, self.device, self.head_dim
-        H, nh, nkv = c.hidden_size, c.num_attention_heads, c.num_key_value_heads
+        c, dev = self.config, self.device
         ids_host = input_ids.cpu()
         B, S = ids_host.shape
         ids_dev = ids_host.to(dev).reshape(-1).contiguous()
-        x = ops.gather_rows(self.embed, ids_dev)  # [B*S, H]  (embed_tokens, :1443)
+        image_idx = None
         if pixel_values is not None:
-            image_embeds = self.visual(pixel_values, image_grid_thw)
-            idx = (ids_host.reshape(-1) == c.image_token_id).nonzero().reshape(-1)
-            if idx.numel() != image_embeds.shape[0]:
-                raise ValueError(f"Image features and image tokens do not match: tokens: {idx.numel()}, features {image_embeds.shape[0]}")
-            ops.scatter_rows(image_embeds, idx.to(dev), x)  # inputs_embeds[image_mask] = image_embeds (:1449-1452)
+            image_idx = (ids_host.reshape(-1) == c.image_token_id).nonzero().reshape(-1).to(dev)
         if position_ids is None:
             position_ids, rope_deltas = self.get_rope_index(ids_host, image_grid_thw, None, attention_mask)
         cos, sin = self._mrope_tables(position_ids.cpu())
+        logits = self.prefill_device(ids_dev, B, S, cos, sin, pixel_values, image_grid_thw, image_idx)
+        if return_dict is False:
+            return (logits,)
+        return Qwen2VLCausalLMOutputWithPast(logits=logits, rope_deltas=rope_deltas)
+
+    def prefill_device(self, ids_dev, B, S, cos, sin, pixel_values=None, image_grid_thw=None, image_idx=None):
+        """The device part of forward(): everything below is kernel launches on the current stream (no host sync).
+        ids_dev int64 [B*S]; cos/sin fp32 [B*S, head_dim] (M-RoPE tables); image_idx int64 [n_image_tokens]."""
+        from .. import ops
+        from .._lib import GLU_SWIGLU
+        c, hd = self.config, self.head_dim
+        nh, nkv = c.num_attention_heads, c.num_key_value_heads
+        x = ops.gather_rows(self.embed, ids_dev)  # [B*S, H]  (embed_tokens, :1443)
+        if pixel_values is not None:
+            image_embeds = self.visual(pixel_values, image_grid_thw)
+            if image_idx.numel() != image_embeds.shape[0]:
+                raise ValueError(f"Image features and image tokens do not match: tokens: {image_idx.numel()}, "
+                                 f"features {image_embeds.shape[0]}")
+            ops.scatter_rows(image_embeds, image_idx, x)  # inputs_embeds[image_mask] = image_embeds (:1449-1452)
         qd, kvd = nh * hd, nkv * hd
         for L in self.layers:
             h1 = ops.layernorm(x, L["ln1"], None, eps=c.rms_norm_eps, rms=True)
@@ -350,9 +362,6 @@ class Qwen2VLForConditionalGeneration:
             g = ops.linear(h2, L["gu"], glu=GLU_SWIGLU)  # silu(gate) * up
             x = ops.linear(g, L["down"], residual=x)
         hN = ops.layernorm(x, self.norm_w, None, eps=c.rms_norm_eps, rms=True)
-        logits = ops.linear(hN, self.lm_head, out_fp32=True).reshape(B, S, c.vocab_size)  # fp32 (:1474-1475)
-        if return_dict is False:
-            return (logits,)
-        return Qwen2VLCausalLMOutputWithPast(logits=logits, rope_deltas=rope_deltas)
+        return ops.linear(hN, self.lm_head, out_fp32=True).reshape(B, S, c.vocab_size)  # fp32 logits (:1474-1475)
 
     __call__ = forward
