@@ -101,11 +101,13 @@ int b200mix_conv3x3_small_cin(const void* x, int32_t x_fp32, const void* w, cons
  * (batch, seq, head). D in {64, 128, 192}; heads with other sizes are zero-padded by the shim at weight-load time.
  * Hq % Hkv == 0 (GQA, modeling_qwen2_vl.py:497-506). cu_seqlens (int32 device [nseq+1], may be NULL) switches on the
  * varlen block-diagonal mode of the Qwen2-VL ViT (modeling_qwen2_vl.py:354-381): then B must be 1 and both q and k
- * are packed along seq. kv_len (<= Sk) masks the key tail (cross-attention with 77 text tokens). */
+ * are packed along seq. kv_lens (int32 device [B], may be NULL) gives the number of valid keys per batch element
+ * (the block-diagonal text mask of STDiT2's MultiHeadCrossAttention, Open-Sora layers/blocks.py:275-331). */
 int b200mix_sdpa(const void* q, const void* k, const void* v, void* o, int64_t B, int64_t Hq, int64_t Hkv, int64_t Sq,
                  int64_t Sk, int64_t D, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t k_sb, int64_t k_ss,
                  int64_t k_sh, int64_t v_sb, int64_t v_ss, int64_t v_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh,
-                 float scale, int32_t causal, const int32_t* cu_seqlens, int32_t nseq, void* stream);
+                 float scale, int32_t causal, const int32_t* cu_seqlens, int32_t nseq, const int32_t* kv_lens,
+                 void* stream);
 
 /* ---- HBM-bound normalisation / modulation kernels (coalesced 16-byte accesses, fp32 statistics) -------------- */
 
@@ -178,6 +180,28 @@ int b200mix_unpatchify(const void* x, void* y, int32_t y_fp32, int64_t B, int64_
  * `inputs_embeds[image_mask] = image_embeds` merge of Qwen2-VL (modeling_qwen2_vl.py:1443,1449-1452). dim % 8 == 0. */
 int b200mix_gather_rows(const void* table, const int64_t* ids, void* out, int64_t n, int64_t dim, void* stream);
 int b200mix_scatter_rows(const void* src, const int64_t* idx, void* dst, int64_t n, int64_t dim, void* stream);
+
+/* ---- Open-Sora STDiT2 helpers (ppdiffusers/examples/Open-Sora/models) ----------------------------------------- */
+
+/* out[b,g,:] = x[b,:] + table[g,:] (fp32): scale_shift_table[None] + t.reshape(B,6,C), stdit/stdit2.py:121-126. */
+int b200mix_broadcast_add(const float* x, const float* table, float* out, int64_t B, int64_t G, int64_t N,
+                          void* stream);
+/* In-place RMSNorm over the first d channels of every head of x[rows, H, ld_head] (q_norm / k_norm = LlamaRMSNorm,
+ * layers/blocks.py:46-68,214). */
+int b200mix_head_rmsnorm_inplace(void* x, int64_t rows, int64_t H, int64_t d, int64_t ld_row, int64_t ld_head,
+                                 const float* weight, float eps, void* stream);
+/* Temporal self-attention of STDiT2Block (stdit2.py:160-171; Attention.forward, blocks.py:200-241): sequences of
+ * length T <= 32 along the frame axis of the token-major qkv buffer [B, T, S, 3, H, d] (row = (b*T+t)*S+s), with
+ * interleaved-pair RoPE (cos/sin fp32 [T, d/2], blocks.py:566-591) and optional q/k RMSNorm, out [B, T, S, H*d]. */
+int b200mix_small_attention(const void* qkv, void* out, int64_t B, int64_t T, int64_t S, int64_t H, int64_t d,
+                            int64_t ld_row, int64_t ld_out, const float* rope_cos, const float* rope_sin,
+                            const float* q_norm_w, const float* k_norm_w, float eps, float scale, void* stream);
+/* PatchEmbed3D with patch (1,p,p) as a row gather (blocks.py:94-164) and STDiT2.unpatchify (stdit2.py:450-474):
+ * x [B,C,T,H,W] -> rows [B*T*(H/p)*(W/p), C*p*p] bf16;  rows [B*T*h*w, p*p*C] -> fp32 [B,C,T,h*p,w*p]. */
+int b200mix_patchify3d(const void* x, int32_t x_fp32, void* y, int64_t B, int64_t C, int64_t T, int64_t H, int64_t W,
+                       int32_t p, void* stream);
+int b200mix_unpatchify3d(const void* x, float* y, int64_t B, int64_t C, int64_t T, int64_t h, int64_t w, int32_t p,
+                         void* stream);
 
 /* fp32 <-> bf16 casts (round-to-nearest-even). */
 int b200mix_cast(const void* x, void* y, int64_t n, int32_t x_fp32, int32_t y_fp32, void* stream);

@@ -52,7 +52,7 @@ SIGNATURES = {
     "b200mix_conv3x3_small_cin": [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                                   c_int64, c_void_p],
     "b200mix_sdpa": [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 6 + [c_int64] * 12 +
-                    [c_float, c_int32, c_void_p, c_int32, c_void_p],
+                    [c_float, c_int32, c_void_p, c_int32, c_void_p, c_void_p],
     "b200mix_groupnorm_nhwc": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                c_int64, c_int64, c_int32, c_float, c_int32, c_void_p],
     "b200mix_layernorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -70,6 +70,12 @@ SIGNATURES = {
                            c_void_p],
     "b200mix_gather_rows": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p],
     "b200mix_scatter_rows": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p],
+    "b200mix_broadcast_add": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],
+    "b200mix_head_rmsnorm_inplace": [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_float, c_void_p],
+    "b200mix_small_attention": [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p],
+    "b200mix_patchify3d": [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p],
+    "b200mix_unpatchify3d": [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p],
     "b200mix_cast": [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p],
     "b200mix_rope_inplace": [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p],
 }

@@ -24,6 +24,7 @@ struct AttnParams {
   int causal;
   const int* cu;
   int nseq;
+  const int* kv_lens;  // optional per-batch number of valid keys (<= Sk)
   int q_pos[3], k_pos[3], v_pos[3];  // tensor-map coordinate slot (1..3) of (seq, head, batch)
   __nv_bfloat16* o;
   long long o_sb, o_ss, o_sh;
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
     q_begin = qt * 128;
     q_end = p.Sq;
     kv_begin = 0;
-    kv_end = p.Sk;
+    kv_end = p.kv_lens ? min(p.Sk, p.kv_lens[b]) : p.Sk;
     q_rel0 = q_begin;
     causal_off = p.Sk - p.Sq;
   }
@@ -397,7 +398,7 @@ extern "C" int b200mix_sdpa(const void* q, const void* k, const void* v, void* o
                             int64_t Sq, int64_t Sk, int64_t D, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t k_sb,
                             int64_t k_ss, int64_t k_sh, int64_t v_sb, int64_t v_ss, int64_t v_sh, int64_t o_sb,
                             int64_t o_ss, int64_t o_sh, float scale, int32_t causal, const int32_t* cu_seqlens,
-                            int32_t nseq, void* stream) {
+                            int32_t nseq, const int32_t* kv_lens, void* stream) {
   if (int rc = ensure_device()) return rc;
   B200_CHECK_ARG(q && k && v && o, "sdpa: null pointer");
   B200_CHECK_ARG(D == 64 || D == 128 || D == 192,
@@ -418,6 +419,7 @@ extern "C" int b200mix_sdpa(const void* q, const void* k, const void* v, void* o
   p.causal = causal;
   p.cu = cu_seqlens;
   p.nseq = nseq;
+  p.kv_lens = kv_lens;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.o_sb = o_sb, p.o_ss = o_ss, p.o_sh = o_sh;
   CUtensorMap tq, tk, tv;

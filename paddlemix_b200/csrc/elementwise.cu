@@ -468,3 +468,239 @@ extern "C" int b200mix_rope_inplace(void* x, int64_t T, int64_t H, int64_t D, in
   B200_LAUNCH_CHECK();
   return 0;
 }
+
+// ================================================================================================================
+// STDiT2 helpers (Open-Sora): short-sequence temporal attention, per-head RMSNorm, table broadcast, 3-D (un)patchify
+// ================================================================================================================
+namespace b200 {
+
+// out[b, g, n] = x[b, n] + table[g, n]   (scale_shift_table[None] + t.reshape(B, 6, C), stdit2.py:121-126)
+__global__ void broadcast_add_kernel(const float* __restrict__ x, const float* __restrict__ table,
+                                     float* __restrict__ out, int B, int G, int N) {
+  const long long total = (long long)B * G * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    const long long r = i / N;
+    const int g = (int)(r % G);
+    const long long b = r / G;
+    out[i] = x[b * N + n] + table[(long long)g * N + n];
+  }
+}
+
+// In-place RMSNorm over the first d channels of every head (LlamaRMSNorm as q_norm / k_norm, blocks.py:62-68,214):
+// one warp per (row, head).
+__global__ void head_rmsnorm_kernel(__nv_bfloat16* __restrict__ x, long long rows, int H, int d, long long ld_row,
+                                    long long ld_head, const float* __restrict__ w, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (wid >= rows * H) return;
+  const long long r = wid / H;
+  const int h = (int)(wid % H);
+  __nv_bfloat16* p = x + r * ld_row + h * ld_head;
+  float v[4];
+  float ss = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < d ? __bfloat162float(p[c]) : 0.0f;
+    ss += v[i] * v[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rs = rsqrtf(ss / d + eps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = lane + 32 * i;
+    // hidden_states.to(input_dtype) then * weight (blocks.py:67-68)
+    if (c < d) p[c] = __float2bfloat16(__bfloat162float(__float2bfloat16(v[i] * rs)) * w[c]);
+  }
+}
+
+// Temporal self-attention of STDiT2 (stdit2.py:160-171): sequences of length T <= 32 taken along the frame axis of a
+// token-major [B, T, S, 3, H, d] qkv buffer (row = (b*T + t)*S + s), with interleaved-pair RoPE (blocks.py:566-591)
+// and optional q/k RMSNorm applied in the reference order (rope, then norm). One CTA (128 threads) per (b, s, head):
+// the work per sequence (16x16x72) is far below one tensor-core tile, so this is a plain fp32 CUDA-core kernel bound
+// by the qkv / output traffic.
+__global__ void __launch_bounds__(128) small_attention_kernel(
+    const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int S, int H, int d,
+    long long ld_row, long long ld_out, const float* __restrict__ rope_cos, const float* __restrict__ rope_sin,
+    const float* __restrict__ qw, const float* __restrict__ kw, float eps, float scale) {
+  extern __shared__ float sm[];  // q[T][d] k[T][d] v[T][d] p[T][T]
+  float* sq = sm;
+  float* sk = sq + T * d;
+  float* sv = sk + T * d;
+  float* sp = sv + T * d;
+  const int h = blockIdx.x % H;
+  const long long bs = blockIdx.x / H;  // b*S + s
+  const long long b = bs / S, s = bs % S;
+  const int tid = threadIdx.x;
+  const int half = d >> 1;
+  // load with RoPE on pairs (2i, 2i+1)
+  for (int idx = tid; idx < T * half; idx += blockDim.x) {
+    const int t = idx / half, i = idx % half;
+    const __nv_bfloat16* row = qkv + ((b * T + t) * S + s) * ld_row + h * d;
+    const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(row + 2 * i);
+    const __nv_bfloat162 k2 = *reinterpret_cast<const __nv_bfloat162*>(row + (long long)H * d + 2 * i);
+    const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(row + 2LL * H * d + 2 * i);
+    float q0 = __low2float(q2), q1 = __high2float(q2), k0 = __low2float(k2), k1 = __high2float(k2);
+    if (rope_cos) {
+      const float c = rope_cos[t * half + i], sn = rope_sin[t * half + i];
+      const float a0 = q0 * c - q1 * sn, a1 = q1 * c + q0 * sn;
+      const float b0 = k0 * c - k1 * sn, b1 = k1 * c + k0 * sn;
+      // apply_rotary_emb runs with autocast off but returns the input dtype: round to bf16 like the reference
+      q0 = __bfloat162float(__float2bfloat16(a0)), q1 = __bfloat162float(__float2bfloat16(a1));
+      k0 = __bfloat162float(__float2bfloat16(b0)), k1 = __bfloat162float(__float2bfloat16(b1));
+    }
+    sq[t * d + 2 * i] = q0, sq[t * d + 2 * i + 1] = q1;
+    sk[t * d + 2 * i] = k0, sk[t * d + 2 * i + 1] = k1;
+    sv[t * d + 2 * i] = __low2float(v2), sv[t * d + 2 * i + 1] = __high2float(v2);
+  }
+  __syncthreads();
+  if (qw) {  // q_norm / k_norm: one warp per row, rows 0..T-1 = q, T..2T-1 = k
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < 2 * T; r += (blockDim.x >> 5)) {
+      float* rowp = (r < T ? sq + r * d : sk + (r - T) * d);
+      const float* w = r < T ? qw : kw;
+      float ss = 0.0f;
+      for (int c = lane; c < d; c += 32) ss += rowp[c] * rowp[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rs = rsqrtf(ss / d + eps);
+      for (int c = lane; c < d; c += 32) rowp[c] = __bfloat162float(__float2bfloat16(rowp[c] * rs)) * w[c];
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < T * T; idx += blockDim.x) {
+    const int i = idx / T, j = idx % T;
+    float acc = 0.0f;
+    for (int c = 0; c < d; ++c) acc = fmaf(sq[i * d + c], sk[j * d + c], acc);
+    sp[idx] = acc * scale;
+  }
+  __syncthreads();
+  if (tid < T) {  // softmax of row tid
+    float m = -INFINITY;
+    for (int j = 0; j < T; ++j) m = fmaxf(m, sp[tid * T + j]);
+    float l = 0.0f;
+    for (int j = 0; j < T; ++j) {
+      const float e = __expf(sp[tid * T + j] - m);
+      sp[tid * T + j] = e;
+      l += e;
+    }
+    const float inv = 1.0f / l;
+    for (int j = 0; j < T; ++j) sp[tid * T + j] *= inv;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < T * half; idx += blockDim.x) {
+    const int t = idx / half, i = idx % half;
+    float o0 = 0.0f, o1 = 0.0f;
+    for (int j = 0; j < T; ++j) {
+      const float pj = sp[t * T + j];
+      o0 = fmaf(pj, sv[j * d + 2 * i], o0);
+      o1 = fmaf(pj, sv[j * d + 2 * i + 1], o1);
+    }
+    __nv_bfloat16* orow = out + ((b * T + t) * S + s) * ld_out + h * d;
+    *reinterpret_cast<__nv_bfloat162*>(orow + 2 * i) = __floats2bfloat162_rn(o0, o1);
+  }
+}
+
+// x NCTHW (fp32|bf16) -> rows [B*T*(H/p)*(W/p), C*p*p] bf16, column order (c, ph, pw): PatchEmbed3D with patch
+// (1, p, p) (blocks.py:94-164); and the inverse head: rows [B*T*h*w, p*p*C] in (ph, pw, c) order -> [B,C,T,h*p,w*p].
+__global__ void patchify3d_kernel(const void* __restrict__ x, int x_fp32, __nv_bfloat16* __restrict__ y, int B, int C,
+                                  int T, int H, int W, int p) {
+  const int h = H / p, w = W / p, K = C * p * p;
+  const long long total = (long long)B * T * h * w * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    long long r = i / K;
+    const int pw = k % p, ph = (k / p) % p, c = k / (p * p);
+    const int ww = (int)(r % w);
+    r /= w;
+    const int hh = (int)(r % h);
+    r /= h;
+    const int t = (int)(r % T);
+    const long long b = r / T;
+    const long long src = (((b * C + c) * T + t) * H + hh * p + ph) * W + ww * p + pw;
+    y[i] = __float2bfloat16(load_any(x, src, x_fp32));
+  }
+}
+__global__ void unpatchify3d_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int C, int T,
+                                    int h, int w, int p) {
+  const int H = h * p, W = w * p;
+  const long long total = (long long)B * C * T * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W);
+    long long r = i / W;
+    const int Y = (int)(r % H);
+    r /= H;
+    const int t = (int)(r % T);
+    r /= T;
+    const int c = (int)(r % C);
+    const long long b = r / C;
+    const int hh = Y / p, ph = Y % p, ww = X / p, pw = X % p;
+    y[i] = __bfloat162float(x[(((b * T + t) * h + hh) * w + ww) * (long long)(p * p * C) + (ph * p + pw) * C + c]);
+  }
+}
+
+}  // namespace b200
+
+extern "C" int b200mix_broadcast_add(const float* x, const float* table, float* out, int64_t B, int64_t G, int64_t N,
+                                     void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(x && table && out && B > 0 && G > 0 && N > 0, "broadcast_add: bad arguments");
+  broadcast_add_kernel<<<ew_grid(B * G * N, 256), 256, 0, ST(stream)>>>(x, table, out, (int)B, (int)G, (int)N);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_head_rmsnorm_inplace(void* x, int64_t rows, int64_t H, int64_t d, int64_t ld_row, int64_t ld_head,
+                                            const float* weight, float eps, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(x && weight && d > 0 && d <= 128, "head_rmsnorm: d must be in (0, 128]");
+  const long long warps = rows * H;
+  head_rmsnorm_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(x), rows, (int)H, (int)d, ld_row, ld_head, weight, eps);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_small_attention(const void* qkv, void* out, int64_t B, int64_t T, int64_t S, int64_t H, int64_t d,
+                                       int64_t ld_row, int64_t ld_out, const float* rope_cos, const float* rope_sin,
+                                       const float* q_norm_w, const float* k_norm_w, float eps, float scale,
+                                       void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(qkv && out, "small_attention: null pointer");
+  B200_CHECK_ARG(T > 0 && T <= 32 && d > 0 && d <= 128 && d % 2 == 0, "small_attention: T <= 32, even d <= 128");
+  B200_CHECK_ARG((rope_cos == nullptr) == (rope_sin == nullptr) && (q_norm_w == nullptr) == (k_norm_w == nullptr),
+                 "small_attention: rope / norm tables come in pairs");
+  const size_t smem = (size_t)(3 * T * d + T * T) * sizeof(float);
+  const long long ctas = B * S * H;
+  B200_CHECK_ARG(ctas < (1ll << 31), "small_attention: too many sequences");
+  small_attention_kernel<<<(unsigned)ctas, 128, smem, ST(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), (int)T, (int)S, (int)H, (int)d,
+      ld_row, ld_out, rope_cos, rope_sin, q_norm_w, k_norm_w, eps, scale);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_patchify3d(const void* x, int32_t x_fp32, void* y, int64_t B, int64_t C, int64_t T, int64_t H,
+                                  int64_t W, int32_t p, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(x && y && p > 0 && H % p == 0 && W % p == 0, "patchify3d: bad arguments");
+  patchify3d_kernel<<<ew_grid(B * C * T * H * W, 256), 256, 0, ST(stream)>>>(
+      x, x_fp32, reinterpret_cast<__nv_bfloat16*>(y), (int)B, (int)C, (int)T, (int)H, (int)W, p);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_unpatchify3d(const void* x, float* y, int64_t B, int64_t C, int64_t T, int64_t h, int64_t w,
+                                    int32_t p, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(x && y && p > 0, "unpatchify3d: bad arguments");
+  unpatchify3d_kernel<<<ew_grid(B * C * T * h * w * p * p, 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), y, (int)B, (int)C, (int)T, (int)h, (int)w, p);
+  B200_LAUNCH_CHECK();
+  return 0;
+}

@@ -206,7 +206,8 @@ def conv3x3_small_cin(x: torch.Tensor, w: torch.Tensor, bias=None) -> torch.Tens
 
 
 def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[float] = None, causal=False,
-         cu_seqlens: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         cu_seqlens: Optional[torch.Tensor] = None, kv_lens: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q: [B,Sq,Hq,D], k/v: [B,Sk,Hkv,D] bf16 views (head_dim contiguous; other strides arbitrary multiples of 8).
     Returns [B,Sq,Hq,D] (the reference layout of scaled_dot_product_attention_)."""
     _req(q, bf16, "q"), _req(k, bf16, "k"), _req(v, bf16, "v")
@@ -222,7 +223,7 @@ def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[f
         check(lib.b200mix_sdpa(_p(q), _p(k), _p(v), _p(out), B, Hq, Hkv, Sq, Sk, D, q.stride(0), q.stride(1),
                                q.stride(2), k.stride(0), k.stride(1), k.stride(2), v.stride(0), v.stride(1),
                                v.stride(2), out.stride(0), out.stride(1), out.stride(2), float(scale),
-                               1 if causal else 0, _p(cu_seqlens), nseq, _stream()), "b200mix_sdpa")
+                               1 if causal else 0, _p(cu_seqlens), nseq, _p(kv_lens), _stream()), "b200mix_sdpa")
     _count()
     return out
 
@@ -394,3 +395,56 @@ def scatter_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> tor
           "b200mix_scatter_rows")
     _count()
     return dst
+
+
+def broadcast_add(x: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    """x fp32 [B, N], table fp32 [G, N] -> fp32 [B, G, N]."""
+    _req(x, torch.float32, "x"), _req(table, torch.float32, "table")
+    B, N = x.shape
+    G = table.shape[0]
+    out = torch.empty(B, G, N, device=x.device, dtype=torch.float32)
+    check(lib.b200mix_broadcast_add(_p(x), _p(table), _p(out), B, G, N, _stream()), "b200mix_broadcast_add")
+    _count()
+    return out
+
+
+def head_rmsnorm_inplace(x: torch.Tensor, weight: torch.Tensor, d: int, eps: float = 1e-6) -> torch.Tensor:
+    """x bf16 [rows, H, Dpad] view (last dim contiguous): RMSNorm over the first d channels of every head."""
+    _req(x, bf16, "x"), _req(weight, torch.float32, "weight")
+    rows, H, _ = x.shape
+    check(lib.b200mix_head_rmsnorm_inplace(_p(x), rows, H, d, x.stride(0), x.stride(1), _p(weight), float(eps), _stream()),
+          "b200mix_head_rmsnorm_inplace")
+    _count()
+    return x
+
+
+def small_attention(qkv: torch.Tensor, B: int, T: int, S: int, H: int, d: int, *, scale: float, rope_cos=None,
+                    rope_sin=None, q_norm_w=None, k_norm_w=None, eps: float = 1e-6) -> torch.Tensor:
+    """qkv bf16 [B*T*S, 3*H*d] (row = (b*T+t)*S+s) -> bf16 [B*T*S, H*d]; attention along the T axis."""
+    _req(qkv, bf16, "qkv")
+    out = torch.empty(qkv.shape[0], H * d, device=qkv.device, dtype=bf16)
+    with _Timed("small_attention", 2.0 * 2 * qkv.shape[0] * 4 * H * d, "byte"):
+        check(lib.b200mix_small_attention(_p(qkv), _p(out), B, T, S, H, d, qkv.stride(0), out.stride(0), _p(rope_cos),
+                                          _p(rope_sin), _p(q_norm_w), _p(k_norm_w), float(eps), float(scale), _stream()),
+              "b200mix_small_attention")
+    _count()
+    return out
+
+
+def patchify3d(x: torch.Tensor, p: int) -> torch.Tensor:
+    B, C, T, H, W = x.shape
+    assert x.is_contiguous() and x.dtype in (torch.float32, bf16)
+    out = torch.empty(B, T * (H // p) * (W // p), C * p * p, device=x.device, dtype=bf16)
+    check(lib.b200mix_patchify3d(_p(x), 1 if x.dtype == torch.float32 else 0, _p(out), B, C, T, H, W, p, _stream()),
+          "b200mix_patchify3d")
+    _count()
+    return out
+
+
+def unpatchify3d(x: torch.Tensor, C: int, T: int, h: int, w: int, p: int) -> torch.Tensor:
+    B = x.shape[0]
+    assert x.is_contiguous() and x.dtype == bf16
+    out = torch.empty(B, C, T, h * p, w * p, device=x.device, dtype=torch.float32)
+    check(lib.b200mix_unpatchify3d(_p(x), _p(out), B, C, T, h, w, p, _stream()), "b200mix_unpatchify3d")
+    _count()
+    return out

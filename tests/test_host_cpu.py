@@ -87,6 +87,15 @@ def test_qwen2vl_structure_and_rope_index_match_oracle():
     assert torch.equal(m.rot_pos_emb(grid), OQ.rot_pos_emb(cfg, grid))
 
 
+def test_stdit2_structure_matches_oracle():
+    from oracle import stdit2 as OS2
+    from paddlemix_b200.opensora import STDiT2
+    for name in ("stdit2_xl", "tiny"):
+        cfg = OS2.STDIT2_CONFIGS[name]
+        assert STDiT2(cfg).state_dict_shapes() == OS2.stdit2_param_shapes(cfg)
+    assert abs(OS2.stdit2_flops(OS2.STDIT2_CONFIGS["stdit2_xl"], 1, 16, 1024, 120) / 1e12 - 24.4) < 0.1
+
+
 def test_config_errors_mirror_reference():
     from paddlemix_b200.ppdiffusers.unet_2d_condition import UNet2DConditionModel
     with pytest.raises(ValueError, match="same number of `down_block_types`"):

@@ -347,3 +347,58 @@ def test_patchify_roundtrip_and_posembed(ops):
     img = ops.unpatchify(t, C, H // p, W // p, p, out_dtype=torch.float32)
     ref_img = t.float().reshape(B, H // p, W // p, p, p, C).permute(0, 5, 1, 3, 2, 4).reshape(B, C, H, W)
     assert torch.equal(img, ref_img)
+
+
+def test_sdpa_kv_lens(ops):
+    B, Sq, Sk, H, D = 3, 256, 120, 2, 128
+    q, k, v = rnd(B, Sq, H, D, seed=73), rnd(B, Sk, H, D, seed=74), rnd(B, Sk, H, D, seed=75)
+    lens = [120, 77, 9]
+    out = ops.sdpa(q, k, v, kv_lens=torch.tensor(lens, dtype=torch.int32, device="cuda"))
+    for b, n in enumerate(lens):
+        ref = ref_sdpa(q[b:b + 1], k[b:b + 1, :n], v[b:b + 1, :n], D ** -0.5)
+        close(out[b:b + 1], ref, ATT_ATOL, ATT_RTOL, f"kv_lens b{b}")
+
+
+def test_small_attention_rope_qknorm(ops):
+    B, T, S, H, d = 2, 16, 24, 3, 72
+    qkv = rnd(B * T * S, 3 * H * d, seed=76)
+    qw, kw = 1 + 0.1 * rnd(d, seed=77, dtype=torch.float32), 1 + 0.1 * rnd(d, seed=78, dtype=torch.float32)
+    freqs = 1.0 / 10000 ** (torch.arange(0, d, 2).float() / d)
+    ang = torch.outer(torch.arange(T).float(), freqs).cuda()  # [T, d/2]
+    out = ops.small_attention(qkv, B, T, S, H, d, scale=d ** -0.5, rope_cos=ang.cos().contiguous(), rope_sin=ang.sin().contiguous(),
+                              q_norm_w=qw, k_norm_w=kw)
+    x = qkv.float().reshape(B, T, S, 3, H, d).permute(3, 0, 2, 4, 1, 5)  # [3, B, S, H, T, d]
+    q, k, v = x[0], x[1], x[2]
+
+    def rope(t):
+        t2 = t.reshape(*t.shape[:-1], -1, 2)
+        rot = torch.stack((-t2[..., 1], t2[..., 0]), -1).flatten(-2)
+        f = ang.repeat_interleave(2, -1)
+        return t * f.cos() + rot * f.sin()
+
+    def rms(t, w):
+        return w * (t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6))
+    q, k = rms(rope(q), qw), rms(rope(k), kw)
+    a = torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5, -1) @ v  # [B, S, H, T, d]
+    ref = a.permute(0, 3, 1, 2, 4).reshape(B * T * S, H * d)
+    close(out, ref, 2e-2, 2e-2, "small attention")
+
+
+def test_stdit_helpers(ops):
+    x, table = rnd(3, 40, seed=79, dtype=torch.float32), rnd(5, 40, seed=80, dtype=torch.float32)
+    assert torch.equal(ops.broadcast_add(x, table), x[:, None] + table[None])
+    h = rnd(50, 4, 128, seed=81)
+    w = 1 + 0.1 * rnd(72, seed=82, dtype=torch.float32)
+    ref = h.float().clone()
+    r = ref[..., :72]
+    ref[..., :72] = (r * torch.rsqrt(r.pow(2).mean(-1, keepdim=True) + 1e-6)).to(bf16).float() * w
+    got = ops.head_rmsnorm_inplace(h.clone(), w, 72)
+    close(got, ref, 2e-2, 1e-2, "head rmsnorm")
+    vid = rnd(2, 4, 3, 8, 8, seed=83, dtype=torch.float32)
+    rows = ops.patchify3d(vid, 2)
+    ref_rows = torch.nn.functional.unfold(vid.to(bf16).float().permute(0, 2, 1, 3, 4).reshape(6, 4, 8, 8), 2, stride=2).transpose(1, 2).reshape(2, 3 * 16, 16)
+    assert torch.equal(rows.float(), ref_rows)
+    t = rnd(2, 3 * 16, 2 * 2 * 8, seed=84)
+    vol = ops.unpatchify3d(t, 8, 3, 4, 4, 2)
+    ref_vol = t.float().reshape(2, 3, 4, 4, 2, 2, 8).permute(0, 6, 1, 2, 4, 3, 5).reshape(2, 8, 3, 8, 8)
+    assert torch.equal(vol, ref_vol)
