@@ -704,3 +704,35 @@ extern "C" int b200mix_unpatchify3d(const void* x, float* y, int64_t B, int64_t 
   B200_LAUNCH_CHECK();
   return 0;
 }
+
+// Microbenchmark (debug, not in the public header): MUFU throughput of ex2.approx.f32 vs ex2.approx.f16x2, used to
+// decide how the attention kernel exponentiates. mode 0: f32, mode 1: f16x2.
+namespace b200 {
+__global__ void mufu_bench_kernel(float* out, int iters, int mode) {
+  float a = threadIdx.x * 1e-3f, b = a + 0.5f, c = a - 0.25f, d = a + 0.125f;
+  uint32_t ha, hb, hc, hd;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(ha) : "f"(a), "f"(b));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hb) : "f"(c), "f"(d));
+  hc = ha ^ 0x00010001u, hd = hb ^ 0x00010001u;
+  for (int i = 0; i < iters; ++i) {
+    if (mode == 0) {
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a));
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(b));
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(c));
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(d));
+    } else {
+      asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(ha));
+      asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(hb));
+      asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(hc));
+      asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(hd));
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a + b + c + d + __uint_as_float(ha ^ hb ^ hc ^ hd);
+}
+}  // namespace b200
+extern "C" int b200mix_debug_mufu_bench(float* out, int blocks, int threads, int iters, int mode, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  mufu_bench_kernel<<<blocks, threads, 0, ST(stream)>>>(out, iters, mode);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
