@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
   constexpr int P_BYTES = 128 * 128 * 2;
   constexpr uint32_t TM_S = 0, TM_O = SB * 128;
 
+  // cu_seqlens / kv_lens are read right away: if they are given, wait for the previous kernel first
+  if (p.cu || p.kv_lens) pdl_wait();
   // ---- which tile am I? (uniform across the CTA) ----
   int qt = blockIdx.x;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -149,6 +151,8 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -385,8 +389,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
     B200_CUDA(cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
-  attn_kernel<D><<<grid, 192, smem_bytes, stream>>>(tq, tk, tv, p);
-  B200_LAUNCH_CHECK();
+  B200_CUDA(launch_pdl(attn_kernel<D>, grid, dim3(192), smem_bytes, stream, 1, tq, tk, tv, p));
   return 0;
 }
 

@@ -1,6 +1,7 @@
 // Error channel, device checks and tensor-map encoding for libb200mix.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -41,6 +42,11 @@ int ensure_device() {
 }
 
 int num_sms() { return g_sms > 0 ? g_sms : 148; }
+
+bool pdl_enabled() {
+  static const bool on = (getenv("B200MIX_NO_PDL") == nullptr);
+  return on;
+}
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

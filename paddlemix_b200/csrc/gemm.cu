@@ -273,6 +273,9 @@ __global__ void __launch_bounds__(320, 1)
   cluster_sync_all();  // barrier inits of both CTAs visible before any multicast TMA / remote commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above overlapped the tail of the previous kernel; from here on we touch its outputs
+  pdl_wait();
+  pdl_launch_dependents();
 
   const uint32_t cta_rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
@@ -416,19 +419,7 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IG
   const int total_super = ((tiles_m + 1) / 2) * p.tiles_n;
   int clusters = num_sms() / 2;
   if (clusters > total_super) clusters = total_super;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(320);
-  cfg.dynamicSmemBytes = smem_bytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, STAGES>, tmA, tmB, p));
+  B200_CUDA(launch_pdl(igemm_kernel<BN, STAGES>, dim3(2 * clusters), dim3(320), smem_bytes, stream, 2, tmA, tmB, p));
   return 0;
 }
 

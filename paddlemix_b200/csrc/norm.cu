@@ -30,6 +30,8 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
                                 int C2, double* __restrict__ partial, long long HW, int groups, int PPB,
                                 int pix_per_cta) {
   extern __shared__ float sm[];  // [PPB][2][C]
+  pdl_wait();
+  pdl_launch_dependents();
   const int C = C1 + C2;
   const int CV = C >> 3;
   const int cv = threadIdx.x % CV;
@@ -91,6 +93,8 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
 __global__ void gn_finalize_kernel(const double* __restrict__ partial, float* __restrict__ mr, int gx, int groups,
                                    double n, float eps) {
   __shared__ double sh[256][2];
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x;
   const int per = blockDim.x / groups;  // threads cooperating on one group (host guarantees >= 1)
   const int g = threadIdx.x / per, j = threadIdx.x % per;
@@ -116,6 +120,8 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
                                 int C2, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 __nv_bfloat16* __restrict__ y, const float* __restrict__ mr, long long HW,
                                 int groups, int silu, int PPB, int pix_per_cta) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int C = C1 + C2;
   const int CV = C >> 3;
   const int cv = threadIdx.x % CV;
@@ -199,6 +205,8 @@ struct LNParams {
 // first reduction, which is what keeps enough bytes in flight per SM to approach HBM bandwidth on short rows.
 template <int VPL, int ROWS>
 __global__ void __launch_bounds__(256, (VPL * ROWS > 12) ? 1 : 2) layernorm_kernel(const LNParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = (static_cast<long long>(blockIdx.x) * 8 + warp) * ROWS;
   if (row0 >= p.M) return;
@@ -364,21 +372,18 @@ extern "C" int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2
   B200_CHECK_ARG(groups <= 256, "groupnorm: at most 256 groups");
   float* mr = reinterpret_cast<float*>(dstats + (long long)gx * B * groups * 2);
   dim3 grid(gx, (unsigned)B);
-  gn_stats_kernel<<<grid, threads, (size_t)PPB * 2 * C * sizeof(float), st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x1), (int)C1, reinterpret_cast<const __nv_bfloat16*>(x2), (int)C2, dstats,
-      HW, groups, PPB, (int)pix_per_cta);
-  B200_LAUNCH_CHECK();
+  B200_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(threads), (size_t)PPB * 2 * C * sizeof(float), st, 1,
+                       reinterpret_cast<const __nv_bfloat16*>(x1), (int)C1, reinterpret_cast<const __nv_bfloat16*>(x2),
+                       (int)C2, dstats, (long long)HW, (int)groups, PPB, (int)pix_per_cta));
   {
     int fthreads = 256 / groups * groups;  // a whole number of threads per group
-    gn_finalize_kernel<<<(unsigned)B, fthreads, 0, st>>>(dstats, mr, (int)gx, groups,
-                                                         static_cast<double>(HW) * (double)(C / groups), eps);
-    B200_LAUNCH_CHECK();
+    B200_CUDA(launch_pdl(gn_finalize_kernel, dim3((unsigned)B), dim3(fthreads), 0, st, 1, (const double*)dstats, mr,
+                         (int)gx, (int)groups, static_cast<double>(HW) * (double)(C / groups), eps));
   }
-  gn_apply_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x1), (int)C1,
-                                            reinterpret_cast<const __nv_bfloat16*>(x2), (int)C2, gamma, beta,
-                                            reinterpret_cast<__nv_bfloat16*>(y), mr, HW, groups, silu, PPB,
-                                            (int)pix_per_cta);
-  B200_LAUNCH_CHECK();
+  B200_CUDA(launch_pdl(gn_apply_kernel, grid, dim3(threads), 0, st, 1, reinterpret_cast<const __nv_bfloat16*>(x1),
+                       (int)C1, reinterpret_cast<const __nv_bfloat16*>(x2), (int)C2, gamma, beta,
+                       reinterpret_cast<__nv_bfloat16*>(y), (const float*)mr, (long long)HW, (int)groups, (int)silu, PPB,
+                       (int)pix_per_cta));
   return 0;
 }
 
@@ -403,8 +408,9 @@ extern "C" int b200mix_layernorm(const void* x, const void* delta, const float* 
   p.M = M, p.N = (int)N, p.eps = eps, p.rms = rms;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nv = (int)(N / 8);
-#define LN_LAUNCH(VPL, ROWS) \
-  layernorm_kernel<VPL, ROWS><<<(unsigned)((M + 8 * ROWS - 1) / (8 * ROWS)), 256, 0, st>>>(p)
+#define LN_LAUNCH(VPL, ROWS)                                                                                      \
+  B200_CUDA(launch_pdl(layernorm_kernel<VPL, ROWS>, dim3((unsigned)((M + 8 * ROWS - 1) / (8 * ROWS))), dim3(256), 0, \
+                       st, 1, p))
   if (nv <= 32) LN_LAUNCH(1, 8);
   else if (nv <= 64) LN_LAUNCH(2, 4);
   else if (nv <= 96) LN_LAUNCH(3, 4);
@@ -415,6 +421,5 @@ extern "C" int b200mix_layernorm(const void* x, const void* delta, const float* 
   else if (nv <= 512) LN_LAUNCH(16, 1);
   else LN_LAUNCH(32, 1);
 #undef LN_LAUNCH
-  B200_LAUNCH_CHECK();
   return 0;
 }

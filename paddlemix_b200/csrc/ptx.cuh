@@ -205,6 +205,14 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with the PDL attribute may start (prologue: barrier init, TMEM
+// alloc, descriptor prefetch) while the previous kernel in the stream drains; pdl_wait() blocks until the previous
+// kernel has completed and its memory is visible; pdl_launch_dependents() lets the next kernel start its own prologue.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // misc
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
