@@ -427,12 +427,12 @@ static int pick_bn(long long tiles_m, long long N, int glu) {
   // cost = waves x time per tile; time per tile ~ BN / efficiency(BN). Efficiencies are the measured mainloop rates of
   // each tile width relative to BN=256 (tools/gemm_bench.py: a 128-wide tile is shared-memory-bandwidth bound on its
   // operand reads, 8 KB per 64-cycle MMA), so narrower tiles are only chosen when they avoid wave / N-padding waste.
-  const int cands[5] = {256, 160, 128, 64, 32};
-  const double eff[5] = {1.00, 0.86, 0.80, 0.50, 0.30};
+  const int cands[7] = {256, 224, 192, 160, 128, 64, 32};
+  const double eff[7] = {1.00, 0.95, 0.90, 0.86, 0.80, 0.50, 0.30};
   double best = 1e30;
   int best_bn = 256;
   const int clusters = num_sms() / 2;
-  for (int i = 0; i < 5; ++i) {
+  for (int i = 0; i < 7; ++i) {
     const int bn = cands[i];
     const long long tn = (N + bn - 1) / bn;
     const long long waves = (((tiles_m + 1) / 2) * tn + clusters - 1) / clusters;
@@ -458,6 +458,8 @@ static int dispatch_igemm(const CUtensorMap& tmA, const void* W, long long ldw, 
   }
   switch (bn) {
     case 256: return launch_igemm<256, 4>(tmA, tmB, p, stream);
+    case 224: return launch_igemm<224, 5>(tmA, tmB, p, stream);
+    case 192: return launch_igemm<192, 5>(tmA, tmB, p, stream);
     case 160: return launch_igemm<160, 6>(tmA, tmB, p, stream);
     case 128: return launch_igemm<128, 6>(tmA, tmB, p, stream);
     case 64: return launch_igemm<64, 8>(tmA, tmB, p, stream);

@@ -36,7 +36,7 @@ GEMM_RTOL, GEMM_ATOL = 1.0e-2, 2e-2
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 640, 320), (8, 1280, 320), (1000, 328, 200), (4096, 1920, 640),
                                    (77, 64, 2048), (300, 40, 1176)])
-@pytest.mark.parametrize("bn", [0, 32, 64, 128, 160, 256])
+@pytest.mark.parametrize("bn", [0, 32, 64, 128, 160, 192, 224, 256])
 def test_linear_plain(ops, M, N, K, bn):
     from paddlemix_b200._lib import lib
     a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)

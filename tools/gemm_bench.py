@@ -44,7 +44,7 @@ LIN = [("ff1_640 geglu", 32768, 5120, 640, True), ("ff2_640", 32768, 640, 2560, 
        ("qkv_1280", 8192, 3840, 1280, False), ("out_1280", 8192, 1280, 1280, False), ("big 8192^3", 8192, 8192, 8192, False)]
 CONV = [("conv 320@128", 8, 128, 128, 320, 320), ("conv 640@64", 8, 64, 64, 640, 640), ("conv 1280@32", 8, 32, 32, 1280, 1280),
         ("conv 2560->1280@32", 8, 32, 32, 2560, 1280), ("conv 960->320@128", 8, 128, 128, 960, 320)]
-bns = [int(b) for b in os.environ.get("BNS", "0,128,160,256").split(",")]
+bns = [int(b) for b in os.environ.get("BNS", "0,160,192,224,256").split(",")]
 print(f"{'shape':24s}" + "".join(f"{('bn=%d' % b) if b else 'auto':>12s}" for b in bns) + "   (TFLOP/s)")
 for name, M, N, K, glu in LIN:
     a, w, bias = rnd(M, K), rnd(N, K), torch.zeros(N, device="cuda")
