@@ -1,13 +1,13 @@
-"""The denoising loop of StableDiffusionPipeline / StableDiffusionXLPipeline
+"""The denoising loops of StableDiffusionPipeline / StableDiffusionXLPipeline / StableDiffusion3Pipeline
 (ppdiffusers/pipelines/stable_diffusion/pipeline_stable_diffusion.py:858-908,
- ppdiffusers/pipelines/stable_diffusion_xl/pipeline_stable_diffusion_xl.py:1040-1082) on the B200-native UNet.
+ ppdiffusers/pipelines/stable_diffusion_xl/pipeline_stable_diffusion_xl.py:1040-1082,
+ ppdiffusers/pipelines/stable_diffusion_3/pipeline_stable_diffusion_3.py:794-866) on the B200-native denoisers.
 
 Text encoders and the VAE run before / after the loop and are out of scope: the pipelines here take
 `prompt_embeds` (and `negative_prompt_embeds`) exactly as the reference pipelines accept them and return latents
-(`output_type="latent"`). One timestep = UNet forward on [uncond | cond] rows + fused CFG/DDIM kernel; the whole
-timestep is captured once into a CUDA graph (host cost of ~1.5k launches -> one graph launch) and replayed with the
-four DDIM scalars passed through a small device buffer... scalars change per step, so the scheduler kernel is
-launched outside the graph.
+(`output_type="latent"`). One timestep = denoiser forward on [uncond | cond] rows + one fused CFG + scheduler kernel.
+For the UNet the forward is captured once into a CUDA graph (~1.5 k launches -> one graph launch; the timestep lives
+in a device tensor) and replayed; the scheduler kernel, whose fp32 scalars change every step, is launched outside it.
 
 Multi-GPU (data parallel over images): each rank takes a contiguous slice of the batch, replicates the
 weights, runs the loop with zero per-step communication, and `all_gather`s the finished latents once over NCCL.
@@ -156,6 +156,70 @@ class StableDiffusionPipeline:
                 self.scheduler.step(eps[:B], t, latents, model_output_cond=eps[B:], guidance_scale=guidance_scale, out=nxt)
             else:
                 self.scheduler.step(eps, t, latents, out=nxt)
+            latents, nxt = nxt, latents
+            if callback_on_step_end is not None:
+                callback_on_step_end(self, i, t, {"latents": latents})
+        return latents
+
+
+class StableDiffusion3Pipeline:
+    """Loop-only mirror of ppdiffusers.StableDiffusion3Pipeline.__call__ (pipeline_stable_diffusion_3.py:794-866):
+    FlowMatchEuler timesteps, SD3Transformer2DModel on [uncond | cond] rows, CFG combine fused with the Euler step.
+    The reference's INFERENCE_OPTIMIZE_BP mode (:803-839) splits the CFG pair over 2 GPUs with 4 scatters + 1
+    all_gather PER STEP; here images (with their CFG pair) are sharded once and only the finished latents are gathered
+    (`shard_batch` / `all_gather_latents`)."""
+
+    def __init__(self, transformer, scheduler):
+        self.transformer, self.scheduler = transformer, scheduler
+
+    @torch.no_grad()
+    def __call__(self, prompt=None, height: Optional[int] = None, width: Optional[int] = None,
+                 num_inference_steps: int = 28, guidance_scale: float = 7.0, latents: Optional[torch.Tensor] = None,
+                 prompt_embeds: Optional[torch.Tensor] = None, negative_prompt_embeds: Optional[torch.Tensor] = None,
+                 pooled_prompt_embeds: Optional[torch.Tensor] = None,
+                 negative_pooled_prompt_embeds: Optional[torch.Tensor] = None, output_type: str = "latent",
+                 callback_on_step_end=None, generator: Optional[torch.Generator] = None):
+        if prompt is not None:
+            raise NotImplementedError("text encoders are outside the hot path: pass prompt_embeds / pooled_prompt_embeds")
+        if prompt_embeds is None or pooled_prompt_embeds is None:
+            raise ValueError("If `prompt_embeds` are provided, `pooled_prompt_embeds` also have to be passed.")
+        if output_type != "latent":
+            raise NotImplementedError("the VAE decoder is outside the hot path: use output_type='latent'")
+        tr = self.transformer
+        dev = tr.device
+        B = prompt_embeds.shape[0]
+        do_cfg = guidance_scale > 1  # pipeline_stable_diffusion_3.py:640-642
+        if latents is None:
+            if height is None or width is None:
+                raise ValueError("height/width (or latents) are required")
+            g = generator or torch.Generator().manual_seed(0)
+            latents = torch.randn(B, tr.config.in_channels, height // 8, width // 8, generator=g)
+        latents = latents.to(device=dev, dtype=torch.float32).contiguous()
+        ctx, pooled = prompt_embeds.to(device=dev, dtype=bf16), pooled_prompt_embeds.to(device=dev, dtype=bf16)
+        if do_cfg:
+            if negative_prompt_embeds is None:
+                negative_prompt_embeds = torch.zeros_like(prompt_embeds)
+            if negative_pooled_prompt_embeds is None:
+                negative_pooled_prompt_embeds = torch.zeros_like(pooled_prompt_embeds)
+            ctx = torch.cat([negative_prompt_embeds.to(device=dev, dtype=bf16), ctx], 0)
+            pooled = torch.cat([negative_pooled_prompt_embeds.to(device=dev, dtype=bf16), pooled], 0)
+        self.scheduler.set_timesteps(num_inference_steps)
+        rows = 2 * B if do_cfg else B
+        model_in = torch.empty((rows,) + tuple(latents.shape[1:]), device=dev, dtype=torch.float32)
+        nxt = torch.empty_like(latents)
+        for i, t in enumerate(self.scheduler.timesteps):
+            if do_cfg:  # latent_model_input = concat([latents] * 2) (:798)
+                model_in[:B].copy_(latents)
+                model_in[B:].copy_(latents)
+            else:
+                model_in = latents
+            timestep = torch.full((rows,), float(t), device=dev, dtype=torch.float32)  # t.expand(batch) (:799)
+            v = tr(hidden_states=model_in, timestep=timestep, encoder_hidden_states=ctx, pooled_projections=pooled,
+                   return_dict=False)[0]
+            if do_cfg:  # noise_pred_uncond + s * (noise_pred_text - noise_pred_uncond) (:843-846), fused with the step
+                self.scheduler.step(v[:B], t, latents, model_output_cond=v[B:], guidance_scale=guidance_scale, out=nxt)
+            else:
+                self.scheduler.step(v, t, latents, out=nxt)
             latents, nxt = nxt, latents
             if callback_on_step_end is not None:
                 callback_on_step_end(self, i, t, {"latents": latents})

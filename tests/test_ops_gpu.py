@@ -402,3 +402,49 @@ def test_stdit_helpers(ops):
     vol = ops.unpatchify3d(t, 8, 3, 4, 4, 2)
     ref_vol = t.float().reshape(2, 3, 4, 4, 2, 2, 8).permute(0, 6, 1, 2, 4, 3, 5).reshape(2, 8, 3, 8, 8)
     assert torch.equal(vol, ref_vol)
+
+
+def test_llama_decoder_layer_from_ops(ops):
+    """LLaVA's language backbone (PaddleNLP LlamaDecoderLayer: RMSNorm -> q/k/v without bias -> 1-D RoPE -> causal
+    attention -> o_proj -> RMSNorm -> SwiGLU MLP; PaddleNLP/paddlenlp/transformers/llama/modeling.py:386-420,534-555,
+    618-…) is the same block shape as Qwen2-VL's decoder minus bias / M-RoPE / GQA: composed here from the same
+    kernels and checked against a plain fp32 evaluation."""
+    from paddlemix_b200._lib import GLU_SWIGLU
+    B, S, H, hd, I = 2, 200, 4, 128, 1024
+    D = H * hd
+    x = rnd(B * S, D, seed=90)
+    wq, wk, wv, wo = (rnd(D, D, seed=91 + i, scale=D ** -0.5) for i in range(4))
+    wg, wu, wd = rnd(I, D, seed=95, scale=D ** -0.5), rnd(I, D, seed=96, scale=D ** -0.5), rnd(D, I, seed=97, scale=I ** -0.5)
+    n1, n2 = 1 + 0.1 * rnd(D, seed=98, dtype=torch.float32), 1 + 0.1 * rnd(D, seed=99, dtype=torch.float32)
+    inv = 1.0 / 10000 ** (torch.arange(0, hd, 2).float() / hd)
+    ang = torch.outer(torch.arange(S).float(), inv)
+    cos = torch.cat([ang.cos(), ang.cos()], -1).repeat(B, 1).contiguous().cuda()
+    sin = torch.cat([ang.sin(), ang.sin()], -1).repeat(B, 1).contiguous().cuda()
+    # --- kernels ---
+    h1 = ops.layernorm(x, n1, None, eps=1e-6, rms=True)
+    qkv = ops.linear(h1, torch.cat([wq, wk, wv], 0).contiguous())
+    q, k, v = (qkv[:, i * D:(i + 1) * D].unflatten(-1, (H, hd)) for i in range(3))
+    ops.rope_inplace(q, cos, sin), ops.rope_inplace(k, cos, sin)
+    a = ops.sdpa(q.unflatten(0, (B, S)), k.unflatten(0, (B, S)), v.unflatten(0, (B, S)), causal=True)
+    y = ops.linear(a.reshape(B * S, D), wo, residual=x)
+    h2 = ops.layernorm(y, n2, None, eps=1e-6, rms=True)
+    gu = torch.stack([wu, wg], 1).reshape(2 * I, D).contiguous()
+    out = ops.linear(ops.linear(h2, gu, glu=GLU_SWIGLU), wd, residual=y)
+    # --- fp32 reference ---
+    xf = x.float()
+
+    def rms(t, w):
+        return t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+
+    def rope(t):  # [B*S, H, hd]
+        rot = torch.cat([-t[..., hd // 2:], t[..., :hd // 2]], -1)
+        return t * cos[:, None] + rot * sin[:, None]
+    r1 = rms(xf, n1)
+    qf, kf, vf = (r1 @ w.float().t() for w in (wq, wk, wv))
+    qf, kf = rope(qf.unflatten(-1, (H, hd))), rope(kf.unflatten(-1, (H, hd)))
+    sp = lambda t: t.reshape(B, S, H, hd).transpose(1, 2)
+    att = torch.nn.functional.scaled_dot_product_attention(sp(qf), sp(kf), sp(vf.unflatten(-1, (H, hd))), is_causal=True)
+    yf = xf + att.transpose(1, 2).reshape(B * S, D) @ wo.float().t()
+    r2 = rms(yf, n2)
+    ref = yf + (torch.nn.functional.silu(r2 @ wg.float().t()) * (r2 @ wu.float().t())) @ wd.float().t()
+    close(out, ref, 6e-2, 3e-2, "llama decoder layer")

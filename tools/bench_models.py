@@ -36,7 +36,7 @@ def sd3():
     pooled, t = torch.randn(B, 2048, device="cuda").to(bf), torch.full((B,), 500.0, device="cuda")
     ms, n = timeit(lambda: m(x, ctx, pooled, t))
     print(f"SD3-medium MMDiT  B={B} 1024^2 (4096+154 tokens): {ms:8.2f} ms/forward, {B / ms * 1e3:7.1f} sample-forwards/s, "
-          f"{8.437 * B / ms:6.1f} TFLOP/s, {n} launches")
+          f"{8.437 * B / ms * 1e3:6.1f} TFLOP/s, {n} launches")
     del m
     torch.cuda.empty_cache()
 
@@ -51,7 +51,7 @@ def stdit2():
     t = torch.full((B,), 500.0, device="cuda")
     ms, n = timeit(lambda: m(x, t, y, **kw))
     print(f"STDiT2-XL        B={B} 16x512^2 (16x1024 tokens):  {ms:8.2f} ms/forward, {B / ms * 1e3:7.1f} sample-forwards/s, "
-          f"{24.39 * B / ms:6.1f} TFLOP/s, {n} launches")
+          f"{24.39 * B / ms * 1e3:6.1f} TFLOP/s, {n} launches")
     del m
     torch.cuda.empty_cache()
 
@@ -63,7 +63,7 @@ def sd15():
         x, ctx = torch.randn(B, 4, 64, 64, device="cuda"), torch.randn(B, 77, 768, device="cuda").to(bf)
         ms, n = timeit(lambda: m(x, 981, ctx))
         print(f"SD1.5 UNet       B={B} 512^2:                       {ms:8.2f} ms/forward, {B / ms * 1e3:7.1f} sample-forwards/s, "
-              f"{0.803 * B / ms:6.1f} TFLOP/s, {n} launches (eager, launch-bound at B=1)")
+              f"{0.803 * B / ms * 1e3:6.1f} TFLOP/s, {n} launches (eager, launch-bound at B=1)")
     del m
     torch.cuda.empty_cache()
 
