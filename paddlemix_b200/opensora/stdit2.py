@@ -175,12 +175,13 @@ class STDiT2:
         return self
 
     # ------------------------------------------------------------------------------------------------------------
-    def _embed_scalar(self, pair, s):
-        """TimestepEmbedder / SizeEmbedder MLP on a flat fp32 vector s (dit_llama.py:68-89)."""
+    def _embed_scalar(self, pair, s, residual=None):
+        """TimestepEmbedder / SizeEmbedder MLP on a flat fp32 vector s (dit_llama.py:68-89); `residual` [rows, D] is
+        added in the second GEMM's epilogue (the reference's `t + data_info`, `fl + fps` adds, stdit2.py:357,370-371)."""
         from .. import ops
         from .._lib import ACT_SILU
         f = ops.timestep_embedding(s.contiguous(), 256, flip_sin_to_cos=True, downscale_freq_shift=0.0)  # [cos | sin]
-        return ops.linear(ops.linear(f, *pair[0], act=ACT_SILU), *pair[1])
+        return ops.linear(ops.linear(f, *pair[0], act=ACT_SILU), *pair[1], residual=residual)
 
     def _pos_embed(self, H, W, scale, base_size):
         """PositionEmbedding2D (blocks.py:487-545) -> bf16 [S, D], host-computed once per latent size."""
@@ -231,12 +232,14 @@ class STDiT2:
         csize = self._embed_scalar(self.size_emb["csize_embedder"], hw).reshape(B, 2 * d3)
         ar_e = self._embed_scalar(self.size_emb["ar_embedder"], ar)
         fl = self._embed_scalar(self.size_emb["fl_embedder"], num_frames)
-        fps_e = self._embed_scalar(self.size_emb["fps_embedder"], fps)
-        t = self._embed_scalar(self.t_emb, f32(timestep).reshape(-1).expand(B).contiguous())
-        # t_spc = t + [csize | ar], t_tmp = t + fl + fps  (tiny [B, D] adds: done with the cast kernels' fp32 path)
-        data_info = torch.cat([csize, ar_e], 1)
-        t_spc = ops.linear(ops.activation(_add(t, data_info), ACT_SILU), *self.t_block, out_fp32=True)        # [B, 6D]
-        t_tmp = ops.linear(ops.activation(_add(_add(t, fl), fps_e), ACT_SILU), *self.t_block_temp, out_fp32=True)  # [B, 3D]
+        fl = self._embed_scalar(self.size_emb["fps_embedder"], fps, residual=fl)  # fl + fps_embedder(fps) (:357)
+        ts = f32(timestep).reshape(-1).expand(B).contiguous()
+        t = self._embed_scalar(self.t_emb, ts)
+        data_info = torch.cat([csize, ar_e], 1).contiguous()
+        t_spc_in = self._embed_scalar(self.t_emb, ts, residual=data_info)  # t + data_info (:370), add fused in the GEMM
+        t_tmp_in = self._embed_scalar(self.t_emb, ts, residual=fl)         # t + fl (:371)
+        t_spc = ops.linear(ops.activation(t_spc_in, ACT_SILU), *self.t_block, out_fp32=True)       # [B, 6D]
+        t_tmp = ops.linear(ops.activation(t_tmp_in, ACT_SILU), *self.t_block_temp, out_fp32=True)  # [B, 3D]
         mod_s = ops.broadcast_add(t_spc, self.tab_spc)      # [B, depth, 6D]
         mod_t = ops.broadcast_add(t_tmp, self.tab_tmp)      # [B, depth, 3D]
         mod_f = ops.broadcast_add(ops.cast(t, torch.float32).repeat(1, 2), self.tab_final)[:, 0]  # [B, 2D]: table + t[:, None]
@@ -298,7 +301,3 @@ class STDiT2:
 
     __call__ = forward
 
-
-def _add(a, b):
-    """[B, D] bf16 embedding adds of the conditioning path (B*D elements per forward)."""
-    return (a.float() + b.float()).to(bf16)
