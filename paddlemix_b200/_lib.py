@@ -8,7 +8,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200mix.so")
+# B200MIX_LIB selects an alternative build of the same library (A/B kernel experiments); never a different backend
+LIB_PATH = os.environ.get("B200MIX_LIB") or os.path.join(_HERE, "libb200mix.so")
 
 
 class B200MixError(RuntimeError):
@@ -97,6 +98,8 @@ def _load():
         getattr(lib, name).argtypes = []
     lib.b200mix_debug_force_bn.argtypes = [c_int]
     lib.b200mix_debug_force_bn.restype = None
+    lib.b200mix_debug_ln_register_only.argtypes = [c_int]
+    lib.b200mix_debug_ln_register_only.restype = None
     return lib
 
 

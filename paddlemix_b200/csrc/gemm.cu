@@ -85,9 +85,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 // Global-memory operands of one 32-column chunk of one accumulator row, fetched ahead of the TMEM load completing.
-struct EpiOperands {
+struct EpiOperands {  // direct (row-per-thread) path: GLU / fp32 output / unaligned or partial chunks
   float4 bias[8];
-  uint4 res[4];
   bool vec;
 };
 
@@ -100,12 +99,7 @@ __device__ __forceinline__ void epilogue_prefetch(const IGemmParams& p, EpiOpera
 #pragma unroll
     for (int j = 0; j < 8; ++j) eo.bias[j] = __ldg(b4 + j);
   }
-  if (p.residual && eo.vec) {
-    const uint4* rs = reinterpret_cast<const uint4*>(p.residual + r_off + n_abs);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) eo.res[j] = __ldg(rs + j);
-  }
-  (void)g;
+  (void)g, (void)r_off;
 }
 
 // One 32-column chunk of one accumulator row -> global memory.
@@ -181,9 +175,10 @@ __device__ __forceinline__ void epilogue_chunk(const IGemmParams& p, const uint3
   }
   if (p.residual) {
     if (vec) {
+      const uint4* rs4 = reinterpret_cast<const uint4*>(p.residual + r_off + n_abs);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint4 w = eo.res[j];
+        const uint4 w = __ldg(rs4 + j);
         v[8 * j + 0] += bf16_lo(w.x), v[8 * j + 1] += bf16_hi(w.x);
         v[8 * j + 2] += bf16_lo(w.y), v[8 * j + 3] += bf16_hi(w.y);
         v[8 * j + 4] += bf16_lo(w.z), v[8 * j + 5] += bf16_hi(w.z);
@@ -229,6 +224,104 @@ __device__ __forceinline__ void epilogue_chunk(const IGemmParams& p, const uint3
   }
 }
 
+// ---- coalesced epilogue (bf16 output, no GLU, aligned full chunk) -------------------------------------------------
+// tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns = 64 bytes of bf16). Writing / reading
+// global memory in that shape makes each lane of a 16-byte access hit a different 128-byte line (32 L1 wavefronts per
+// instruction). The chunk is therefore transposed through a 2 KB per-warp shared-memory buffer so that a warp's
+// global access covers 8 rows x 64 contiguous bytes (8 wavefronts): 4 lanes per row, lane L -> row s*8 + L/4,
+// 16-byte piece L%4. The buffer is XOR-swizzled (piece ^ ((row >> 1) & 3)) so both access patterns are conflict-free.
+struct RowMap {          // global offsets (16-byte units) of the 4 rows this lane touches in the transposed pattern
+  uint32_t c16[4];
+  uint32_t r16[4];
+  uint32_t valid;        // bit s4 set = row s4 exists
+};
+
+__device__ __forceinline__ uint32_t stage_addr(int row, int piece) {
+  return static_cast<uint32_t>(row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
+}
+
+__device__ __forceinline__ void epilogue_prefetch_staged(const IGemmParams& p, uint4 (&resv)[4], const RowMap& rm,
+                                                         int lane, int n_abs) {
+  if (p.residual) {
+    const uint4* base = reinterpret_cast<const uint4*>(p.residual + n_abs) + (lane & 3);
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4)
+      resv[s4] = ((rm.valid >> s4) & 1u) ? __ldg(base + rm.r16[s4]) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+__device__ __forceinline__ void epilogue_chunk_staged(const IGemmParams& p, const uint32_t (&r)[32], const uint4 (&resv)[4],
+                                                      const RowMap& rm, uint8_t* stage, int lane, long long g,
+                                                      int n_abs) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_abs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 a = __ldg(b4 + j);
+      v[4 * j + 0] += a.x, v[4 * j + 1] += a.y, v[4 * j + 2] += a.z, v[4 * j + 3] += a.w;
+    }
+  }
+  if (p.row_add) {
+    const float4* ra = reinterpret_cast<const float4*>(p.row_add + g * p.ld_row + n_abs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 a = __ldg(ra + j);
+      v[4 * j + 0] += a.x, v[4 * j + 1] += a.y, v[4 * j + 2] += a.z, v[4 * j + 3] += a.w;
+    }
+  }
+  if (p.act != B200MIX_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+  }
+  if (p.row_gate) {
+    const float4* rg = reinterpret_cast<const float4*>(p.row_gate + g * p.ld_row + n_abs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 a = __ldg(rg + j);
+      v[4 * j + 0] *= a.x, v[4 * j + 1] *= a.y, v[4 * j + 2] *= a.z, v[4 * j + 3] *= a.w;
+    }
+  }
+  const int piece = lane & 3;
+  if (p.residual) {
+    // transposed (coalesced) residual pieces -> smem -> this thread's own row
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4)
+      *reinterpret_cast<uint4*>(stage + stage_addr(s4 * 8 + (lane >> 2), piece)) = resv[s4];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 w = *reinterpret_cast<const uint4*>(stage + stage_addr(lane, j));
+      v[8 * j + 0] += bf16_lo(w.x), v[8 * j + 1] += bf16_hi(w.x);
+      v[8 * j + 2] += bf16_lo(w.y), v[8 * j + 3] += bf16_hi(w.y);
+      v[8 * j + 4] += bf16_lo(w.z), v[8 * j + 5] += bf16_hi(w.z);
+      v[8 * j + 6] += bf16_lo(w.w), v[8 * j + 7] += bf16_hi(w.w);
+    }
+    __syncwarp();
+  }
+  if (p.out_scale != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+  }
+  // own row -> smem -> transposed (coalesced) global stores
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 w = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+    *reinterpret_cast<uint4*>(stage + stage_addr(lane, j)) = w;
+  }
+  __syncwarp();
+  uint4* cbase = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + n_abs) + piece;
+#pragma unroll
+  for (int s4 = 0; s4 < 4; ++s4) {
+    const uint4 w = *reinterpret_cast<const uint4*>(stage + stage_addr(s4 * 8 + (lane >> 2), piece));
+    if ((rm.valid >> s4) & 1u) cbase[rm.c16[s4]] = w;
+  }
+  __syncwarp();
+}
+
 template <int BN>
 struct IGemmCfg {
   static constexpr int A_BYTES = 128 * 128;  // 128 rows x 64 bf16 (128 B per row, SW128)
@@ -250,6 +343,7 @@ __global__ void __launch_bounds__(320, 1)
   uint64_t* tfull = empty_bar + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* stage_all = smem + STAGES * Cfg::STAGE_BYTES + 256;  // 8 epilogue warps x 2 KB transpose buffers
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -349,6 +443,8 @@ __global__ void __launch_bounds__(320, 1)
     // handles the 32-column chunks c == g (mod 2), so every SM sub-partition has two epilogue warps in flight =====
     const int q = warp & 3;
     const int wg = (warp - 2) >> 2;
+    uint8_t* stage = stage_all + (warp - 2) * 2048;
+    const bool staged_ok = p.vec_ok && !p.glu && !p.out_fp32 && ((p.c_bstride | p.r_bstride) & 7) == 0;
     const int row = q * 32 + lane;
     const int tw = row % p.TW;
     const int th = (row / p.TW) % p.TH;
@@ -375,6 +471,23 @@ __global__ void __launch_bounds__(320, 1)
         r_off = (p.res_row_mod > 0 ? gm % p.res_row_mod : gm) * p.ldr;
       }
       const int n0 = nt * BN;
+      RowMap rm;  // offsets are multiples of 8 elements whenever staged_ok (vec_ok: 16-byte aligned rows)
+      rm.valid = 0;
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const int src = s4 * 8 + (lane >> 2);
+        rm.c16[s4] = __shfl_sync(0xffffffffu, static_cast<uint32_t>(c_off >> 3), src);
+        rm.r16[s4] = __shfl_sync(0xffffffffu, static_cast<uint32_t>(r_off >> 3), src);
+        rm.valid |= (__shfl_sync(0xffffffffu, valid ? 1u : 0u, src) & 1u) << s4;
+      }
+      // residual pieces are fetched one chunk ahead (the first chunk's even before the accumulators are ready), so
+      // their L2 latency overlaps the previous chunk's work instead of sitting on the critical path of each chunk
+#ifndef EPI_PIPE
+#define EPI_PIPE 0  // measured: prefetching the residual a chunk ahead costs ~2% (register pressure), keep it off
+#endif
+      uint4 res_cur[4];
+      bool st_cur = staged_ok && n0 + wg * 32 + 32 <= p.N;
+      if (EPI_PIPE && st_cur) epilogue_prefetch_staged(p, res_cur, rm, lane, n0 + wg * 32);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
@@ -383,12 +496,30 @@ __global__ void __launch_bounds__(320, 1)
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c * 32, r);
         const int n_abs = n0 + c * 32;
-        const bool active = valid && n_abs < p.N;
-        // global operands of this chunk are requested before the TMEM load is waited for, so their latency overlaps
-        EpiOperands eo;
-        if (active) epilogue_prefetch(p, eo, r_off, g, n_abs);
-        tmem_wait_ld();
-        if (active) epilogue_chunk(p, r, eo, c_off, r_off, g, n_abs);
+        if (st_cur) {  // warp-uniform: coalesced path through the transpose buffer
+#if EPI_PIPE
+          uint4 res_next[4];
+          const bool st_next = (c + 2 < BN / 32) && (n_abs + 96 <= p.N);
+          if (st_next) epilogue_prefetch_staged(p, res_next, rm, lane, n_abs + 64);
+          tmem_wait_ld();
+          epilogue_chunk_staged(p, r, res_cur, rm, stage, lane, g, n_abs);
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) res_cur[s4] = res_next[s4];
+          st_cur = st_next;
+#else
+          epilogue_prefetch_staged(p, res_cur, rm, lane, n_abs);
+          tmem_wait_ld();
+          epilogue_chunk_staged(p, r, res_cur, rm, stage, lane, g, n_abs);
+          st_cur = (c + 2 < BN / 32) && (n_abs + 96 <= p.N);
+#endif
+        } else {
+          // global operands of this chunk are requested before the TMEM load is waited for, so their latency overlaps
+          const bool active = valid && n_abs < p.N;
+          EpiOperands eo;
+          if (active) epilogue_prefetch(p, eo, r_off, g, n_abs);
+          tmem_wait_ld();
+          if (active) epilogue_chunk(p, r, eo, c_off, r_off, g, n_abs);
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty[as]);
@@ -409,7 +540,7 @@ __global__ void __launch_bounds__(320, 1)
 template <int BN, int STAGES>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IGemmParams& p, cudaStream_t stream) {
   using Cfg = IGemmCfg<BN>;
-  constexpr int smem_bytes = STAGES * Cfg::STAGE_BYTES + 1024 + 256;
+  constexpr int smem_bytes = STAGES * Cfg::STAGE_BYTES + 1024 + 256 + 8 * 2048;  // + epilogue transpose buffers
   static bool configured = false;
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -457,10 +588,13 @@ static int dispatch_igemm(const CUtensorMap& tmA, const void* W, long long ldw, 
     if (rc) return rc;
   }
   switch (bn) {
-    case 256: return launch_igemm<256, 4>(tmA, tmB, p, stream);
-    case 224: return launch_igemm<224, 5>(tmA, tmB, p, stream);
+#ifndef BN256_STAGES
+#define BN256_STAGES 4
+#endif
+    case 256: return launch_igemm<256, BN256_STAGES>(tmA, tmB, p, stream);
+    case 224: return launch_igemm<224, 4>(tmA, tmB, p, stream);
     case 192: return launch_igemm<192, 5>(tmA, tmB, p, stream);
-    case 160: return launch_igemm<160, 6>(tmA, tmB, p, stream);
+    case 160: return launch_igemm<160, 5>(tmA, tmB, p, stream);
     case 128: return launch_igemm<128, 6>(tmA, tmB, p, stream);
     case 64: return launch_igemm<64, 8>(tmA, tmB, p, stream);
     case 32: return launch_igemm<32, 8>(tmA, tmB, p, stream);

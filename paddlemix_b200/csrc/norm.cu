@@ -201,29 +201,26 @@ struct LNParams {
   int rms;
 };
 
-// Each warp normalises ROWS consecutive rows at once: all ROWS*VPL 16-byte loads of a lane are issued before the
-// first reduction, which is what keeps enough bytes in flight per SM to approach HBM bandwidth on short rows.
+// Each warp normalises ROWS consecutive rows at once. The rows are kept PACKED (bf16 pairs, one uint4 per 8 channels)
+// so that all ROWS*VPL 16-byte loads of a lane can be in flight together within the register budget; values are
+// unpacked transiently for the two reductions and for the output.
 template <int VPL, int ROWS>
-__global__ void __launch_bounds__(256, (VPL * ROWS > 12) ? 1 : 2) layernorm_kernel(const LNParams p) {
+__global__ void __launch_bounds__(256, (VPL * ROWS > 16) ? 1 : 2) layernorm_kernel(const LNParams p) {
   pdl_wait();
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = (static_cast<long long>(blockIdx.x) * 8 + warp) * ROWS;
   if (row0 >= p.M) return;
   const int NV = p.N >> 3;
-  float v[ROWS][VPL][8];
+  uint4 raw[ROWS][VPL];
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
     const long long row = row0 + r;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = lane + 32 * i;
-      if (row < p.M && vi < NV) {
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p.x + row * p.N) + vi), v[r][i]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[r][i][k] = 0.0f;
-      }
+      raw[r][i] = (row < p.M && vi < NV) ? __ldg(reinterpret_cast<const uint4*>(p.x + row * p.N) + vi)
+                                          : make_uint4(0u, 0u, 0u, 0u);
     }
   }
   if (p.delta) {
@@ -236,22 +233,20 @@ __global__ void __launch_bounds__(256, (VPL * ROWS > 12) ? 1 : 2) layernorm_kern
       for (int i = 0; i < VPL; ++i) {
         const int vi = lane + 32 * i;
         if (vi >= NV) continue;
-        float d[8];
+        float v[8], d[8];
+        unpack8(raw[r][i], v);
         unpack8(__ldg(reinterpret_cast<const uint4*>(p.delta + row * p.N) + vi), d);
         if (p.gate) {
           const float* gp = p.gate + g * p.ld_mod + vi * 8;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[r][i][k] = fmaf(__ldg(gp + k), d[k], v[r][i][k]);
+          for (int k = 0; k < 8; ++k) v[k] = fmaf(__ldg(gp + k), d[k], v[k]);
         } else {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[r][i][k] += d[k];
+          for (int k = 0; k < 8; ++k) v[k] += d[k];
         }
-        if (p.resid_out) {
-          // the residual stream is stored in bf16: normalise the rounded value so both outputs agree
-          uint4 w = pack8(v[r][i]);
-          *(reinterpret_cast<uint4*>(p.resid_out + row * p.N) + vi) = w;
-          unpack8(w, v[r][i]);
-        }
+        // the residual stream is stored in bf16: the rounded value is what gets normalised, so both outputs agree
+        raw[r][i] = pack8(v);
+        if (p.resid_out) *(reinterpret_cast<uint4*>(p.resid_out + row * p.N) + vi) = raw[r][i];
       }
     }
   }
@@ -262,9 +257,12 @@ __global__ void __launch_bounds__(256, (VPL * ROWS > 12) ? 1 : 2) layernorm_kern
     if (!p.rms) {
       float s = 0.0f;
 #pragma unroll
-      for (int i = 0; i < VPL; ++i)
+      for (int i = 0; i < VPL; ++i) {
+        float v[8];
+        unpack8(raw[r][i], v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += v[r][i][k];
+        for (int k = 0; k < 8; ++k) s += v[k];
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       mean[r] = s / p.N;
@@ -277,9 +275,11 @@ __global__ void __launch_bounds__(256, (VPL * ROWS > 12) ? 1 : 2) layernorm_kern
     for (int i = 0; i < VPL; ++i) {
       const int vi = lane + 32 * i;
       if (vi < NV) {
+        float v[8];
+        unpack8(raw[r][i], v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float d = v[r][i][k] - mean[r];
+          const float d = v[k] - mean[r];
           sq += d * d;
         }
       }
@@ -310,8 +310,9 @@ __global__ void __launch_bounds__(256, (VPL * ROWS > 12) ? 1 : 2) layernorm_kern
       const long long row = row0 + r;
       if (row >= p.M) continue;
       float o[8];
+      unpack8(raw[r][i], o);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = (v[r][i][k] - mean[r]) * rstd[r];
+      for (int k = 0; k < 8; ++k) o[k] = (o[k] - mean[r]) * rstd[r];
       if (p.rms && p.weight) {
         // Qwen2RMSNorm: normalised value is cast to the activation dtype first, then multiplied by the weight
 #pragma unroll
@@ -387,6 +388,151 @@ extern "C" int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2
   return 0;
 }
 
+// Large inputs: block-resident variant. Each CTA owns a contiguous block of rows, fetched into shared memory by four
+// 1-D bulk copies (one mbarrier each) so the whole block is in flight at once and no registers hold row data: the grid
+// is sized to exactly fill the machine (2 CTAs per SM, a whole number of waves). Each warp then normalises two rows
+// per iteration out of shared memory with the same per-lane accumulation order as layernorm_kernel (bit-identical).
+constexpr int LN_BLOCK_SMEM_CAP = 104 * 1024;
+
+__global__ void __launch_bounds__(512, 2) layernorm_block_kernel(const LNParams p, int rows_per_cta, int rows_per_chunk) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  __shared__ uint64_t bars[4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const int nrows = static_cast<int>(min(static_cast<long long>(rows_per_cta), p.M - r0));
+  const uint32_t row_bytes = static_cast<uint32_t>(p.N) * 2u;
+  uint8_t* sx = ln_smem;
+  uint8_t* sd = ln_smem + static_cast<size_t>(rows_per_cta) * row_bytes;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) mbar_init(&bars[c], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < 4; ++c) {
+      const int cr0 = c * rows_per_chunk;
+      if (cr0 >= nrows) break;
+      const uint32_t bytes = static_cast<uint32_t>(min(rows_per_chunk, nrows - cr0)) * row_bytes;
+      mbar_expect_tx(&bars[c], p.delta ? 2 * bytes : bytes);
+      bulk_load_1d(sx + static_cast<size_t>(cr0) * row_bytes, p.x + (r0 + cr0) * p.N, bytes, &bars[c]);
+      if (p.delta) bulk_load_1d(sd + static_cast<size_t>(cr0) * row_bytes, p.delta + (r0 + cr0) * p.N, bytes, &bars[c]);
+    }
+  }
+  const int NV = p.N >> 3;
+  for (int r = 2 * warp; r < nrows; r += 32) {  // rows_per_chunk is even: a row pair never straddles two chunks
+    mbar_wait(&bars[r / rows_per_chunk], 0);
+    const int nr = (r + 1 < nrows) ? 2 : 1;
+    uint4* srow[2] = {reinterpret_cast<uint4*>(sx + static_cast<size_t>(r) * row_bytes),
+                      reinterpret_cast<uint4*>(sx + static_cast<size_t>(r + 1) * row_bytes)};
+    float mean[2] = {0.0f, 0.0f}, rstd[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      if (rr >= nr) break;
+      const long long row = r0 + r + rr;
+      if (p.delta) {
+        const uint4* drow = reinterpret_cast<const uint4*>(sd + static_cast<size_t>(r + rr) * row_bytes);
+        const long long g = static_cast<long long>(static_cast<unsigned>(row) / static_cast<unsigned>(p.rows_per_group));
+        for (int vi = lane; vi < NV; vi += 32) {
+          float v[8], d[8];
+          unpack8(srow[rr][vi], v);
+          unpack8(drow[vi], d);
+          if (p.gate) {
+            const float* gp = p.gate + g * p.ld_mod + vi * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fmaf(__ldg(gp + k), d[k], v[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += d[k];
+          }
+          const uint4 packed = pack8(v);  // bf16 residual stream: the rounded value is what gets normalised
+          srow[rr][vi] = packed;          // only this lane reads these 16 bytes again
+          if (p.resid_out) *(reinterpret_cast<uint4*>(p.resid_out + row * p.N) + vi) = packed;
+        }
+      }
+      if (!p.rms) {
+        float s = 0.0f;
+        for (int vi = lane; vi < NV; vi += 32) {
+          float v[8];
+          unpack8(srow[rr][vi], v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s += v[k];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        mean[rr] = s / p.N;
+      }
+      float sq = 0.0f;
+      for (int vi = lane; vi < NV; vi += 32) {
+        float v[8];
+        unpack8(srow[rr][vi], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float d = v[k] - mean[rr];
+          sq += d * d;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      rstd[rr] = rsqrtf(sq / p.N + p.eps);
+    }
+    for (int vi = lane; vi < NV; vi += 32) {
+      float wv[8], bv[8];
+      if (p.weight) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.weight) + 2 * vi);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.weight) + 2 * vi + 1);
+        wv[0] = a.x, wv[1] = a.y, wv[2] = a.z, wv[3] = a.w, wv[4] = b.x, wv[5] = b.y, wv[6] = b.z, wv[7] = b.w;
+      }
+      if (p.bias) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.bias) + 2 * vi);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + 2 * vi + 1);
+        bv[0] = a.x, bv[1] = a.y, bv[2] = a.z, bv[3] = a.w, bv[4] = b.x, bv[5] = b.y, bv[6] = b.z, bv[7] = b.w;
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        if (rr >= nr) break;
+        const long long row = r0 + r + rr;
+        float o[8];
+        unpack8(srow[rr][vi], o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = (o[k] - mean[rr]) * rstd[rr];
+        if (p.rms && p.weight) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = __bfloat162float(__float2bfloat16(o[k])) * wv[k];
+        } else if (p.weight) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] *= wv[k];
+        }
+        if (p.bias) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] += bv[k];
+        }
+        if (p.scale || p.shift) {
+          const long long g = static_cast<long long>(static_cast<unsigned>(row) / static_cast<unsigned>(p.rows_per_group));
+          if (p.scale) {
+            const float4* sp = reinterpret_cast<const float4*>(p.scale + g * p.ld_mod) + 2 * vi;
+            const float4 a = __ldg(sp), b = __ldg(sp + 1);
+            o[0] *= 1.0f + a.x, o[1] *= 1.0f + a.y, o[2] *= 1.0f + a.z, o[3] *= 1.0f + a.w;
+            o[4] *= 1.0f + b.x, o[5] *= 1.0f + b.y, o[6] *= 1.0f + b.z, o[7] *= 1.0f + b.w;
+          }
+          if (p.shift) {
+            const float4* sp = reinterpret_cast<const float4*>(p.shift + g * p.ld_mod) + 2 * vi;
+            const float4 a = __ldg(sp), b = __ldg(sp + 1);
+            o[0] += a.x, o[1] += a.y, o[2] += a.z, o[3] += a.w, o[4] += b.x, o[5] += b.y, o[6] += b.z, o[7] += b.w;
+          }
+        }
+        *(reinterpret_cast<uint4*>(p.y + row * p.N) + vi) = pack8(o);
+      }
+    }
+  }
+}
+
+// Test hook (not part of the public header): 1 = always use the register-resident kernel.
+static int g_ln_register_only = 0;
+extern "C" void b200mix_debug_ln_register_only(int on) { g_ln_register_only = on; }
+
 extern "C" int b200mix_layernorm(const void* x, const void* delta, const float* gate, void* resid_out, void* y,
                                  const float* weight, const float* bias, const float* scale, const float* shift,
                                  int64_t ld_mod, int64_t rows_per_group, int64_t M, int64_t N, float eps, int32_t rms,
@@ -408,16 +554,40 @@ extern "C" int b200mix_layernorm(const void* x, const void* delta, const float* 
   p.M = M, p.N = (int)N, p.eps = eps, p.rms = rms;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nv = (int)(N / 8);
+  {
+    // block-resident kernel for inputs big enough to fill the machine (same results bit for bit)
+    const long long row_bytes = N * 2 * (delta ? 2 : 1);
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (!delta || reinterpret_cast<uintptr_t>(delta) % 16 == 0);
+    const long long slots = 2ll * num_sms();
+    // only when the whole input is resident in one wave: with several waves the register kernel overlaps better
+    if (!g_ln_register_only && aligned && M * row_bytes >= (4ll << 20) && M * row_bytes <= slots * LN_BLOCK_SMEM_CAP) {
+      const long long waves = 1;
+      long long rpc = (M + slots * waves - 1) / (slots * waves);
+      rpc = (rpc + 1) & ~1ll;
+      if (rpc * row_bytes > LN_BLOCK_SMEM_CAP) rpc = (LN_BLOCK_SMEM_CAP / row_bytes) & ~1ll;
+      long long rchunk = (((rpc + 3) / 4) + 1) & ~1ll;
+      const size_t smem = (size_t)(rpc * row_bytes);
+      static bool configured = false;
+      if (!configured) {
+        B200_CUDA(cudaFuncSetAttribute(layernorm_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       LN_BLOCK_SMEM_CAP));
+        configured = true;
+      }
+      B200_CUDA(launch_pdl(layernorm_block_kernel, dim3((unsigned)((M + rpc - 1) / rpc)), dim3(512), smem, st, 1, p,
+                           (int)rpc, (int)rchunk));
+      return 0;
+    }
+  }
 #define LN_LAUNCH(VPL, ROWS)                                                                                      \
   B200_CUDA(launch_pdl(layernorm_kernel<VPL, ROWS>, dim3((unsigned)((M + 8 * ROWS - 1) / (8 * ROWS))), dim3(256), 0, \
                        st, 1, p))
   if (nv <= 32) LN_LAUNCH(1, 8);
-  else if (nv <= 64) LN_LAUNCH(2, 4);
+  else if (nv <= 64) LN_LAUNCH(2, 8);
   else if (nv <= 96) LN_LAUNCH(3, 4);
-  else if (nv <= 128) LN_LAUNCH(4, 2);
-  else if (nv <= 160) LN_LAUNCH(5, 2);
+  else if (nv <= 128) LN_LAUNCH(4, 4);
+  else if (nv <= 160) LN_LAUNCH(5, 3);
   else if (nv <= 192) LN_LAUNCH(6, 2);
-  else if (nv <= 256) LN_LAUNCH(8, 1);
+  else if (nv <= 256) LN_LAUNCH(8, 2);
   else if (nv <= 512) LN_LAUNCH(16, 1);
   else LN_LAUNCH(32, 1);
 #undef LN_LAUNCH

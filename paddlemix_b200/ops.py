@@ -37,14 +37,15 @@ def profile_begin():
     _prof = []
 
 
-def profile_end():
-    """Returns {kind: dict(ms, work, unit, calls)} for the launches since profile_begin()."""
+def profile_end(by_tag=False):
+    """Returns {kind: dict(ms, work, unit, calls)} for the launches since profile_begin(); by_tag=True keys the table
+    by the per-call shape tag ("lin 8192x1280x640 b+res", ...) instead of the kernel family."""
     global _prof
     recs, _prof = _prof, None
     torch.cuda.synchronize()
     out = {}
-    for kind, work, unit, e0, e1 in recs:
-        d = out.setdefault(kind, dict(ms=0.0, work=0.0, unit=unit, calls=0))
+    for kind, tag, work, unit, e0, e1 in recs:
+        d = out.setdefault((tag or kind) if by_tag else kind, dict(ms=0.0, work=0.0, unit=unit, calls=0))
         d["ms"] += e0.elapsed_time(e1)
         d["work"] += work
         d["calls"] += 1
@@ -52,10 +53,10 @@ def profile_end():
 
 
 class _Timed:
-    __slots__ = ("kind", "work", "unit", "e0")
+    __slots__ = ("kind", "work", "unit", "e0", "tag")
 
-    def __init__(self, kind, work, unit):
-        self.kind, self.work, self.unit = kind, work, unit
+    def __init__(self, kind, work, unit, tag=None):
+        self.kind, self.work, self.unit, self.tag = kind, work, unit, tag
 
     def __enter__(self):
         if _prof is not None:
@@ -66,7 +67,7 @@ class _Timed:
         if _prof is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            _prof.append((self.kind, self.work, self.unit, self.e0, e1))
+            _prof.append((self.kind, self.tag() if callable(self.tag) else self.tag, self.work, self.unit, self.e0, e1))
 
 
 def _stream():
@@ -107,6 +108,12 @@ def make_epilogue(bias=None, row_add=None, row_gate=None, ld_row=0, rows_per_gro
     return e
 
 
+def _epi_tag(e) -> str:
+    parts = [n for n, on in (("bias", e.bias), ("radd", e.row_add), ("gate", e.row_gate), ("res", e.residual),
+                             (f"act{e.act}", e.act), (f"glu{e.glu}", e.glu), ("f32", e.out_fp32)) if on]
+    return (" " + "+".join(parts)) if parts else ""
+
+
 def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, act=ACT_NONE, glu=GLU_NONE, residual=None, row_add=None,
            row_gate=None, rows_per_group=0, out_fp32=False, out=None, out_scale=1.0, residual_row_mod=0) -> torch.Tensor:
     """out[M, N(/2)] = epilogue(a[M, K] @ w[N, K]^T). a: bf16 [..., K] (last dim contiguous), w: bf16 [N, K]."""
@@ -127,7 +134,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, act=ACT_NONE, glu=GLU
                       rows_per_group=rows_per_group, residual=res2, ldr=0 if res2 is None else res2.stride(0), act=act,
                       glu=glu, out_fp32=out_fp32, out_scale=out_scale, residual_row_mod=residual_row_mod)
     out2 = out.reshape(-1, n_out)
-    with _Timed("igemm", 2.0 * M * N * K, "flop"):
+    with _Timed("igemm", 2.0 * M * N * K, "flop", lambda: f"lin {M}x{N}x{K}" + _epi_tag(e)):
         check(lib.b200mix_linear(_p(a2), a2.stride(0), _p(w), w.stride(0), _p(out2), out2.stride(0), M, N, K,
                                  ctypes.byref(e), _stream()), "b200mix_linear")
     _count()
@@ -146,7 +153,7 @@ def linear_batched(a: torch.Tensor, w: torch.Tensor, bias=None, *, out: torch.Te
     e = make_epilogue(bias=bias, row_add=row_add, row_gate=row_gate, ld_row=0 if mod is None else mod.stride(0),
                       rows_per_group=rows, residual=residual, ldr=0 if residual is None else residual.stride(1),
                       act=act, glu=glu, out_fp32=(out.dtype == torch.float32))
-    with _Timed("igemm", 2.0 * B * rows * N * K, "flop"):
+    with _Timed("igemm", 2.0 * B * rows * N * K, "flop", lambda: f"linb {B}*{rows}x{N}x{K}" + _epi_tag(e)):
         check(lib.b200mix_linear_batched(_p(a), a.stride(1), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(1),
                                          out.stride(0), rows, B, N, K, ctypes.byref(e),
                                          0 if residual is None else residual.stride(0), _stream()),
@@ -187,7 +194,8 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, bias=None, *, stride=1, row_add=No
         out = torch.empty(B, Ho, Wo, Cout, device=x.device, dtype=bf16)
     e = make_epilogue(bias=bias, row_add=row_add, ld_row=0 if row_add is None else row_add.stride(0),
                       rows_per_group=Ho * Wo, residual=residual, ldr=Cout, act=act, out_scale=out_scale)
-    with _Timed("igemm", 2.0 * B * Ho * Wo * Cout * 9 * Cin, "flop"):
+    with _Timed("igemm", 2.0 * B * Ho * Wo * Cout * 9 * Cin, "flop",
+                lambda: f"conv{stride} {B * Ho * Wo}x{Cout}x{9 * Cin}" + _epi_tag(e)):
         check(lib.b200mix_conv3x3(_p(x), _p(w), _p(out), B, H, W, Cin, Cout, stride, ctypes.byref(e), _stream()),
               "b200mix_conv3x3")
     _count()
@@ -219,7 +227,8 @@ def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[f
     if scale is None:
         scale = D ** -0.5
     nseq = 0 if cu_seqlens is None else cu_seqlens.numel() - 1
-    with _Timed("attention", 4.0 * B * Hq * Sq * Sk * D * (0.5 if causal else 1.0), "flop"):
+    with _Timed("attention", 4.0 * B * Hq * Sq * Sk * D * (0.5 if causal else 1.0), "flop",
+                lambda: f"attn B{B} H{Hq} Sq{Sq} Sk{Sk} D{D}" + (" causal" if causal else "")):
         check(lib.b200mix_sdpa(_p(q), _p(k), _p(v), _p(out), B, Hq, Hkv, Sq, Sk, D, q.stride(0), q.stride(1),
                                q.stride(2), k.stride(0), k.stride(1), k.stride(2), v.stride(0), v.stride(1),
                                v.stride(2), out.stride(0), out.stride(1), out.stride(2), float(scale),
@@ -245,7 +254,7 @@ def groupnorm_nhwc(x1: torch.Tensor, gamma, beta, *, x2=None, groups=32, eps=1e-
     if st is None:
         st = torch.empty((1024 + B) * groups * 2, device=x1.device, dtype=torch.float64)
         _gn_scratch[key] = st
-    with _Timed("groupnorm", 2.0 * 2 * B * HW * (C1 + C2), "byte"):  # algorithmic: read once + write once (bf16)
+    with _Timed("groupnorm", 2.0 * 2 * B * HW * (C1 + C2), "byte", lambda: f"gn {B}x{HW}x{C1 + C2}"):  # algorithmic: read once + write once (bf16)
         check(lib.b200mix_groupnorm_nhwc(_p(x1), C1, _p(x2), C2, _p(gamma), _p(beta), _p(out), _p(st), st.numel() * 8, B,
                                          HW, groups, float(eps), 1 if silu else 0, _stream()), "b200mix_groupnorm_nhwc")
     _count(3)
@@ -267,7 +276,7 @@ def layernorm(x: torch.Tensor, weight=None, bias=None, *, eps=1e-5, rms=False, d
     mod = gate if gate is not None else (scale if scale is not None else shift)
     ld_mod = 0 if mod is None else mod.stride(0)
     nbytes = 2.0 * M * N * (2 + (1 if delta is not None else 0) + (1 if resid is not None else 0))
-    with _Timed("layernorm", nbytes, "byte"):
+    with _Timed("layernorm", nbytes, "byte", lambda: f"ln {M}x{N}" + (" +delta" if delta is not None else "")):
         check(lib.b200mix_layernorm(_p(x2), _p(delta), _p(gate), _p(resid), _p(out), _p(weight), _p(bias), _p(scale),
                                     _p(shift), ld_mod, rows_per_group, M, N, float(eps), 1 if rms else 0, _stream()),
               "b200mix_layernorm")

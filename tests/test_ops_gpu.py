@@ -240,6 +240,54 @@ def test_layernorm_adaln_fused(ops):
     close(y, y_ref, 3e-2, 1.5e-2, "adaln y")
 
 
+@pytest.mark.parametrize("M,N,mode", [(8192, 1280, "affine"), (4099, 640, "affine"), (3 * 1367, 1536, "adaln"),
+                                      (2 * 2048, 1152, "adaln_noresid"), (3000, 3584, "rms"), (20001, 128, "affine")])
+def test_layernorm_block_kernel_matches_register_kernel(ops, M, N, mode):
+    """Inputs >= 4 MB take the shared-memory block kernel (bulk-copy row blocks); it must agree BIT FOR BIT with the
+    register-resident kernel (same accumulation order) and with the fp32 torch reference within bf16 tolerance."""
+    from paddlemix_b200._lib import lib
+    x = (rnd(M, N, seed=61) + 0.25).to(bf16)
+    kw = dict(eps=1e-6)
+    args = (None, None)
+    if mode == "affine":
+        args = (rnd(N, seed=62, dtype=torch.float32), rnd(N, seed=63, dtype=torch.float32))
+    elif mode == "rms":
+        args = (rnd(N, seed=62, dtype=torch.float32), None)
+        kw["rms"] = True
+    else:
+        G = 3 if mode == "adaln" else 2
+        S = M // G
+        kw.update(delta=rnd(M, N, seed=64), gate=rnd(G, N, seed=65, dtype=torch.float32),
+                  scale=rnd(G, N, seed=66, dtype=torch.float32), shift=rnd(G, N, seed=67, dtype=torch.float32),
+                  rows_per_group=S, want_resid=(mode == "adaln"))
+
+    def run():
+        o = ops.layernorm(x, *args, **kw)
+        return o if isinstance(o, tuple) else (o,)
+
+    blk = run()
+    lib.b200mix_debug_ln_register_only(1)
+    try:
+        reg = run()
+    finally:
+        lib.b200mix_debug_ln_register_only(0)
+    for a, b in zip(blk, reg):
+        assert torch.equal(a, b), f"block vs register layernorm differ ({mode} {M}x{N})"
+    xf = x.float()
+    if mode == "affine":
+        close(blk[0], F.layer_norm(xf, (N,), args[0], args[1], 1e-6), 2e-2, 1e-2, "block layernorm")
+    elif mode == "rms":
+        ref = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).to(bf16).float() * args[0]
+        close(blk[0], ref, 2e-2, 1e-2, "block rmsnorm")
+    else:
+        G, S = kw["gate"].shape[0], kw["rows_per_group"]
+        r = (xf.view(G, S, N) + kw["gate"][:, None] * kw["delta"].float().view(G, S, N)).to(bf16).float()
+        y_ref = F.layer_norm(r, (N,), None, None, 1e-6) * (1 + kw["scale"][:, None]) + kw["shift"][:, None]
+        close(blk[-1].view(G, S, N), y_ref, 3e-2, 1.5e-2, "block adaln y")
+        if mode == "adaln":
+            close(blk[0].view(G, S, N), r, 2e-2, 1e-2, "block adaln resid")
+
+
 def test_rmsnorm(ops):
     M, N = 300, 3584
     x, w = rnd(M, N, seed=52), rnd(N, seed=53, dtype=torch.float32)
