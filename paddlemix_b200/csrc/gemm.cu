@@ -322,20 +322,23 @@ __device__ __forceinline__ void epilogue_chunk_staged(const IGemmParams& p, cons
   __syncwarp();
 }
 
-template <int BN>
+// PAIR = the two CTAs of a cluster run ONE 256 x BN MMA (tcgen05 cta_group::2): each CTA stages its own 128 rows of A and
+// only BN/2 rows of B, so a pipeline stage is 1/3 smaller and the B operand is read from shared memory once per pair.
+// !PAIR = each CTA runs its own 128 x BN MMA and the two halves of the B tile are multicast to both.
+template <int BN, bool PAIR>
 struct IGemmCfg {
   static constexpr int A_BYTES = 128 * 128;  // 128 rows x 64 bf16 (128 B per row, SW128)
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(320, 1)
     igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ IGemmParams p) {
-  using Cfg = IGemmCfg<BN>;
+  using Cfg = IGemmCfg<BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -351,17 +354,20 @@ __global__ void __launch_bounds__(320, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 2);  // one multicast commit from each CTA of the cluster
+      mbar_init(&empty_bar[s], PAIR ? 1 : 2);  // one multicast commit from each MMA-issuing CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 256);
+      mbar_init(&tempty[s], PAIR ? 512 : 256);  // PAIR: the leader's barrier collects both CTAs' epilogue threads
     }
     fence_barrier_init();
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // barrier inits of both CTAs visible before any multicast TMA / remote commit
@@ -397,26 +403,35 @@ __global__ void __launch_bounds__(320, 1)
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sB = sA + Cfg::A_BYTES;
-            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_5d(sA, &tmA, &full_bar[stage], kc * 64 + dc, x0 + dx, pp, y0 + dy, b0);
-            // my half of the weight tile, delivered to both CTAs of the cluster
-            tma_load_2d_mcast(sB + cta_rank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], tap * p.Kc + kc * 64,
-                              n0 + (int)cta_rank * (BN / 2), (uint16_t)0x3);
+            if (PAIR) {
+              // both CTAs' boxes complete on the LEADER's barrier (it alone issues the MMA): my A rows, my half of B
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              const uint32_t lbar = mapa_smem(&full_bar[stage], 0);
+              tma_load_5d_pair(sA, &tmA, lbar, kc * 64 + dc, x0 + dx, pp, y0 + dy, b0);
+              tma_load_2d_pair(sB, &tmB, lbar, tap * p.Kc + kc * 64, n0 + (int)cta_rank * (BN / 2));
+            } else {
+              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              tma_load_5d(sA, &tmA, &full_bar[stage], kc * 64 + dc, x0 + dx, pp, y0 + dy, b0);
+              // my half of the weight tile, delivered to both CTAs of the cluster
+              tma_load_2d_mcast(sB + cta_rank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], tap * p.Kc + kc * 64,
+                                n0 + (int)cta_rank * (BN / 2), (uint16_t)0x3);
+            }
             if (++stage == STAGES) stage = 0, phase ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    if (lane == 0 && (!PAIR || cta_rank == 0)) {
+      // ===== MMA issuer (PAIR: the leader CTA drives the tensor cores of both SMs) =====
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       for (int st = cluster_id; st < total_super; st += num_clusters) {
-        mbar_wait(&tempty[as], aphase ^ 1);
+        if (PAIR) mbar_wait_cluster(&tempty[as], aphase ^ 1);
+        else mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
         for (int kb = 0; kb < kblocks; ++kb) {
@@ -428,12 +443,16 @@ __global__ void __launch_bounds__(320, 1)
           for (int k = 0; k < 4; ++k) {
             const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) umma_bf16_ss_pair(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit_mcast(&empty_bar[stage], (uint16_t)0x3);  // frees this stage in both CTAs
+          // frees this stage in both CTAs
+          if (PAIR) umma_commit_pair_mcast(&empty_bar[stage], (uint16_t)0x3);
+          else umma_commit_mcast(&empty_bar[stage], (uint16_t)0x3);
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
-        umma_commit(&tfull[as]);
+        if (PAIR) umma_commit_pair_mcast(&tfull[as], (uint16_t)0x3);  // accumulators of both CTAs are ready
+        else umma_commit(&tfull[as]);
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -522,7 +541,8 @@ __global__ void __launch_bounds__(320, 1)
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[as]);
+      if (PAIR) mbar_arrive_cluster(mapa_smem(&tempty[as], 0));
+      else mbar_arrive(&tempty[as]);
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
@@ -533,33 +553,47 @@ __global__ void __launch_bounds__(320, 1)
   cluster_sync_all();  // the peer may still multicast into my smem / arrive on my barriers until it is done too
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
-template <int BN, int STAGES>
+static int g_max_clusters = 0;  // measurement hook: cap the persistent grid (0 = all SMs)
+
+template <int BN, int STAGES, bool PAIR>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IGemmParams& p, cudaStream_t stream) {
-  using Cfg = IGemmCfg<BN>;
+  using Cfg = IGemmCfg<BN, PAIR>;
   constexpr int smem_bytes = STAGES * Cfg::STAGE_BYTES + 1024 + 256 + 8 * 2048;  // + epilogue transpose buffers
+  static_assert(smem_bytes <= 227 * 1024, "stage count does not fit shared memory");
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    B200_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   smem_bytes));
     configured = true;
   }
   const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
   const int total_super = ((tiles_m + 1) / 2) * p.tiles_n;
   int clusters = num_sms() / 2;
+  if (g_max_clusters > 0 && clusters > g_max_clusters) clusters = g_max_clusters;
   if (clusters > total_super) clusters = total_super;
-  B200_CUDA(launch_pdl(igemm_kernel<BN, STAGES>, dim3(2 * clusters), dim3(320), smem_bytes, stream, 2, tmA, tmB, p));
+  B200_CUDA(launch_pdl(igemm_kernel<BN, STAGES, PAIR>, dim3(2 * clusters), dim3(320), smem_bytes, stream, 2, tmA, tmB,
+                       p));
   return 0;
 }
 
+// Test / measurement hook (see b200mix_debug_gemm_pair): 1 = CTA-pair MMA (default), 0 = per-CTA MMA + multicast B.
+#ifndef GEMM_PAIR_DEFAULT
+#define GEMM_PAIR_DEFAULT 1
+#endif
+static int g_gemm_pair = GEMM_PAIR_DEFAULT;
+
 static int pick_bn(long long tiles_m, long long N, int glu) {
-  // cost = waves x time per tile; time per tile ~ BN / efficiency(BN). Efficiencies are the measured mainloop rates of
-  // each tile width relative to BN=256 (tools/gemm_bench.py: a 128-wide tile is shared-memory-bandwidth bound on its
-  // operand reads, 8 KB per 64-cycle MMA), so narrower tiles are only chosen when they avoid wave / N-padding waste.
+  // cost = waves x time per tile; time per tile ~ BN / rate(BN). Rates are the measured mainloop rates of each tile
+  // width relative to BN=256 in CTA-pair mode (tools/bn_sweep.py, 16384x8192x2048: 1541 / 1448 / 1331 / 1202 / 1032 /
+  // 530 / 270 TFLOP/s): the per-SM operand fill (A tile + B half per k-chunk, ~60 B/clk) does not shrink with BN as
+  // fast as the MMA time does, so narrower tiles are only chosen when they avoid wave / N-padding waste.
   const int cands[7] = {256, 224, 192, 160, 128, 64, 32};
-  const double eff[7] = {1.00, 0.95, 0.90, 0.86, 0.80, 0.50, 0.30};
+  const double eff[7] = {1.00, 0.94, 0.87, 0.79, 0.68, 0.35, 0.18};
   double best = 1e30;
   int best_bn = 256;
   const int clusters = num_sms() / 2;
@@ -587,17 +621,26 @@ static int dispatch_igemm(const CUtensorMap& tmA, const void* W, long long ldw, 
     int rc = encode_tmap_bf16_sw128(&tmB, W, 2, dims, strides, box);
     if (rc) return rc;
   }
-  switch (bn) {
-#ifndef BN256_STAGES
-#define BN256_STAGES 4
-#endif
-    case 256: return launch_igemm<256, BN256_STAGES>(tmA, tmB, p, stream);
-    case 224: return launch_igemm<224, 4>(tmA, tmB, p, stream);
-    case 192: return launch_igemm<192, 5>(tmA, tmB, p, stream);
-    case 160: return launch_igemm<160, 5>(tmA, tmB, p, stream);
-    case 128: return launch_igemm<128, 6>(tmA, tmB, p, stream);
-    case 64: return launch_igemm<64, 8>(tmA, tmB, p, stream);
-    case 32: return launch_igemm<32, 8>(tmA, tmB, p, stream);
+  if (g_gemm_pair) {  // one 256 x BN MMA per CTA pair (the default)
+    switch (bn) {
+      case 256: return launch_igemm<256, 6, true>(tmA, tmB, p, stream);
+      case 224: return launch_igemm<224, 6, true>(tmA, tmB, p, stream);
+      case 192: return launch_igemm<192, 7, true>(tmA, tmB, p, stream);
+      case 160: return launch_igemm<160, 8, true>(tmA, tmB, p, stream);
+      case 128: return launch_igemm<128, 8, true>(tmA, tmB, p, stream);
+      case 64: return launch_igemm<64, 8, true>(tmA, tmB, p, stream);
+      case 32: return launch_igemm<32, 8, true>(tmA, tmB, p, stream);
+      default: set_error("unsupported BN %d", bn); return B200MIX_ERR_INVALID;
+    }
+  }
+  switch (bn) {  // two 128 x BN MMAs per cluster with a multicast B tile (kept for A/B measurements)
+    case 256: return launch_igemm<256, 4, false>(tmA, tmB, p, stream);
+    case 224: return launch_igemm<224, 4, false>(tmA, tmB, p, stream);
+    case 192: return launch_igemm<192, 5, false>(tmA, tmB, p, stream);
+    case 160: return launch_igemm<160, 5, false>(tmA, tmB, p, stream);
+    case 128: return launch_igemm<128, 6, false>(tmA, tmB, p, stream);
+    case 64: return launch_igemm<64, 8, false>(tmA, tmB, p, stream);
+    case 32: return launch_igemm<32, 8, false>(tmA, tmB, p, stream);
     default: set_error("unsupported BN %d", bn); return B200MIX_ERR_INVALID;
   }
 }
@@ -636,6 +679,8 @@ using namespace b200;
 // Test hook: force a tile width (0 = heuristic). Not part of the public header.
 static int g_force_bn = 0;
 extern "C" void b200mix_debug_force_bn(int bn) { g_force_bn = bn; }
+extern "C" void b200mix_debug_gemm_pair(int on) { b200::g_gemm_pair = on; }
+extern "C" void b200mix_debug_max_clusters(int n) { b200::g_max_clusters = n; }
 
 extern "C" int b200mix_linear(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M,
                               int64_t N, int64_t K, const b200mix_epilogue* epi, void* stream) {

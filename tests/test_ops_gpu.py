@@ -37,15 +37,18 @@ GEMM_RTOL, GEMM_ATOL = 1.0e-2, 2e-2
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 640, 320), (8, 1280, 320), (1000, 328, 200), (4096, 1920, 640),
                                    (77, 64, 2048), (300, 40, 1176)])
 @pytest.mark.parametrize("bn", [0, 32, 64, 128, 160, 192, 224, 256])
-def test_linear_plain(ops, M, N, K, bn):
+@pytest.mark.parametrize("pair", [1, 0])  # 1: one 256-row MMA per CTA pair (default); 0: per-CTA MMA + multicast B
+def test_linear_plain(ops, M, N, K, bn, pair):
     from paddlemix_b200._lib import lib
     a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
     bias = rnd(N, seed=3, dtype=torch.float32)
     lib.b200mix_debug_force_bn(bn)
+    lib.b200mix_debug_gemm_pair(pair)
     try:
         out = ops.linear(a, w, bias)
     finally:
         lib.b200mix_debug_force_bn(0)
+        lib.b200mix_debug_gemm_pair(1)
     ref = a.float() @ w.float().t() + bias
     close(out, ref, GEMM_ATOL, GEMM_RTOL, f"linear {M}x{N}x{K} bn={bn}")
 
