@@ -98,6 +98,8 @@ def _load():
         getattr(lib, name).argtypes = []
     lib.b200mix_debug_force_bn.argtypes = [c_int]
     lib.b200mix_debug_force_bn.restype = None
+    lib.b200mix_debug_no_shortkv.argtypes = [c_int]
+    lib.b200mix_debug_no_shortkv.restype = None
     lib.b200mix_debug_gemm_pair.argtypes = [c_int]
     lib.b200mix_debug_gemm_pair.restype = None
     lib.b200mix_debug_ln_register_only.argtypes = [c_int]

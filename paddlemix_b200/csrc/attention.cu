@@ -353,6 +353,221 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Short-KV attention (cross-attention against <= 128 keys, e.g. the 77 text tokens of SD / SDXL): one K/V block, so a
+// query tile is a single QK^T -> softmax -> PV chain of ~2 us whose cost is all latency. Instead of one CTA per tile
+// (barrier / TMEM / K,V set-up paid 1280 times, Q load latency exposed every time) the grid is persistent: each CTA owns
+// a contiguous range of the flattened (batch, head, q-tile) space, keeps K / V of the current (batch, head) in shared
+// memory, prefetches the next Q tile through a 2-deep ring while the current one is in softmax, skips the key chunks
+// beyond kv_len, and writes O through the (idle) P buffer so global stores are full 128-byte lines.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SKV_SMEM = 2 * 16384 /*Q ring*/ + 16384 /*K*/ + 16384 /*V*/ + 32768 /*P, O staging*/ + 256;
+
+__global__ void __launch_bounds__(192, 2)
+    attn_shortkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p, int nq,
+                        int total_tiles) {
+  constexpr int D = 64;
+  constexpr int TILE_BYTES = 128 * D * 2;
+  constexpr uint32_t TM_S = 0, TM_O = 128;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;                   // 2 x 16 KB
+  uint8_t* sK = sQ + 2 * TILE_BYTES;
+  uint8_t* sV = sK + TILE_BYTES;
+  uint8_t* sP = sV + TILE_BYTES;        // 32 KB: P (bf16 128x128, two 64-column SW128 panels), then O staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 32768);
+  uint64_t* q_full = bars;        // 2
+  uint64_t* q_empty = bars + 2;   // 2
+  uint64_t* kv_full = bars + 4;
+  uint64_t* kv_empty = bars + 5;
+  uint64_t* s_full = bars + 6;
+  uint64_t* s_empty = bars + 7;   // 128
+  uint64_t* p_full = bars + 8;    // 128
+  uint64_t* pv_done = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full[0], 1), mbar_init(&q_full[1], 1);
+    mbar_init(&q_empty[0], 1), mbar_init(&q_empty[1], 1);
+    mbar_init(kv_full, 1), mbar_init(kv_empty, 1);
+    mbar_init(s_full, 1), mbar_init(s_empty, 128);
+    mbar_init(p_full, 128), mbar_init(pv_done, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  // my contiguous slice of the flattened (batch, head, q-tile) space
+  const int f0 = static_cast<int>(static_cast<long long>(blockIdx.x) * total_tiles / gridDim.x);
+  const int f1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * total_tiles / gridDim.x);
+  const int rep = p.Hq / p.Hkv;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int g_prev = -1, kvn = 0;
+      for (int f = f0, i = 0; f < f1; ++f, ++i) {
+        const int grp = f / nq, qt = f - grp * nq;
+        const int b = grp / p.Hq, h = grp - b * p.Hq;
+        if (grp != g_prev) {
+          if (kvn > 0) mbar_wait(kv_empty, (kvn - 1) & 1);  // every MMA on the previous K / V has completed
+          mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+          tma_load_rows(sK, &tmK, kv_full, p.k_pos, 0, 0, h / rep, b);  // rows >= Sk are zero-filled
+          tma_load_rows(sV, &tmV, kv_full, p.v_pos, 0, 0, h / rep, b);
+          ++kvn;
+          g_prev = grp;
+        }
+        const int s = i & 1;
+        mbar_wait(&q_empty[s], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[s], TILE_BYTES);
+        tma_load_rows(sQ + s * TILE_BYTES, &tmQ, &q_full[s], p.q_pos, 0, qt * 128, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);  // B (= V) is MN-major
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+      int g_prev = -1, kvn = 0;
+      for (int f = f0, i = 0; f < f1; ++f, ++i) {
+        const int grp = f / nq;
+        const int b = grp / p.Hq;
+        if (grp != g_prev) {
+          mbar_wait(kv_full, kvn & 1);
+          ++kvn;
+          g_prev = grp;
+        }
+        const int kv_len = p.kv_lens ? min(p.Sk, p.kv_lens[b]) : p.Sk;
+        const int s = i & 1;
+        mbar_wait(&q_full[s], (i >> 1) & 1);
+        if (i > 0) mbar_wait(s_empty, (i - 1) & 1);  // softmax(i-1) has copied S out of TMEM
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ + s * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          umma_bf16_ss(tmem_base + TM_S, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                       make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(&q_empty[s]);
+        umma_commit(s_full);
+        mbar_wait(p_full, i & 1);  // P(i) is in smem; the same threads finished reading O(i-1) before writing it
+        tc_fence_after();
+        const int ksteps = (kv_len + 15) >> 4;  // P columns beyond kv_len are never read
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ad = make_smem_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc_sw128(v_addr + k * 2048, 16384, 1024);
+          umma_bf16_ss(tmem_base + TM_O, ad, bd, idesc_pv, k != 0 ? 1u : 0u);
+        }
+        umma_commit(pv_done);
+        if (f + 1 == f1 || (f + 1) / nq != grp) umma_commit(kv_empty);  // last use of this K / V
+      }
+    }
+  } else {
+    // ===== softmax + output: one query row per thread =====
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+    uint8_t* p_row = sP + row * 128;
+    const int sw = row & 7;
+    uint8_t* o_stage = sP + qd * 4096;  // this warp's 32 rows x 128 B of O (P is dead once PV has completed)
+    for (int f = f0, i = 0; f < f1; ++f, ++i) {
+      const int grp = f / nq, qt = f - grp * nq;
+      const int b = grp / p.Hq, h = grp - b * p.Hq;
+      const int kv_len = p.kv_lens ? min(p.Sk, p.kv_lens[b]) : p.Sk;
+      const int nch = (kv_len + 31) >> 5;  // 32-column chunks of S that hold visible keys (1..4)
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      uint32_t sv[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < nch) tmem_ld_32x32b_x32(lane_base + TM_S + c * 32, sv[c]);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(s_empty);
+
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < nch) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float sc = (c * 32 + j < kv_len) ? __uint_as_float(sv[c][j]) : -INFINITY;
+            sv[c][j] = __float_as_uint(sc);
+            mx = fmaxf(mx, sc);
+          }
+        }
+      const float m_scaled = (mx == -INFINITY) ? 0.0f : mx * p.scale_log2;
+      float sum = 0.0f;
+#pragma unroll
+      for (int g8 = 0; g8 < 16; ++g8) {
+        if ((g8 >> 2) < nch) {
+          uint32_t w[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int col = g8 * 8 + t * 2;
+            const float e0 = fast_exp2(fmaf(__uint_as_float(sv[col >> 5][col & 31]), p.scale_log2, -m_scaled));
+            const float e1 = fast_exp2(fmaf(__uint_as_float(sv[col >> 5][(col & 31) + 1]), p.scale_log2, -m_scaled));
+            sum += e0 + e1;
+            w[t] = pack_bf16x2(e0, e1);
+          }
+          const int chunk = g8 >> 3, u = g8 & 7;
+          *reinterpret_cast<uint4*>(p_row + chunk * 16384 + ((u ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+
+      // ---- O / l -> (staging in the P buffer) -> global, 4 rows x 128 B per store instruction ----
+      mbar_wait(pv_done, i & 1);
+      tc_fence_after();
+      const float inv_l = (sum > 0.0f) ? 1.0f / sum : 0.0f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(lane_base + TM_O + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * u + 0]) * inv_l, __uint_as_float(o[8 * u + 1]) * inv_l);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * u + 2]) * inv_l, __uint_as_float(o[8 * u + 3]) * inv_l);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * u + 4]) * inv_l, __uint_as_float(o[8 * u + 5]) * inv_l);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * u + 6]) * inv_l, __uint_as_float(o[8 * u + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(o_stage + lane * 128 + (((c * 4 + u) ^ (lane & 7)) << 4)) = w;
+        }
+      }
+      __syncwarp();
+      __nv_bfloat16* dst0 = p.o + static_cast<long long>(b) * p.o_sb + static_cast<long long>(h) * p.o_sh;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), u = lane & 7;  // 8 lanes cover one row's 128 bytes
+        const uint4 w = *reinterpret_cast<const uint4*>(o_stage + r * 128 + ((u ^ (r & 7)) << 4));
+        const int q_abs = qt * 128 + qd * 32 + r;
+        if (q_abs < p.Sq) *(reinterpret_cast<uint4*>(dst0 + static_cast<long long>(q_abs) * p.o_ss) + u) = w;
+      }
+      __syncwarp();  // the staging rows are rewritten by next tile's P stores of other rows only after p_full ordering
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
 // Build a 4-D tensor map over (d, seq, head, batch) for a [.., D]-contiguous bf16 tensor with arbitrary (16-byte
 // aligned) strides; outer dims are ordered by increasing stride. pos[] returns the coordinate slot of (seq, head, batch).
 static int make_attn_tmap(CUtensorMap* tm, const void* ptr, int64_t D, int64_t S, int64_t H, int64_t B, int64_t ss,
@@ -393,9 +608,27 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   return 0;
 }
 
+static int g_no_shortkv = 0;  // test hook: 1 = always use the general kernel
+
+static int launch_attn_shortkv(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                               int B, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(attn_shortkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SKV_SMEM));
+    configured = true;
+  }
+  const int nq = (p.Sq + 127) / 128;
+  const long long total = static_cast<long long>(B) * p.Hq * nq;
+  const int grid = static_cast<int>(std::min<long long>(total, 2ll * num_sms()));
+  B200_CUDA(launch_pdl(attn_shortkv_kernel, dim3(grid), dim3(192), SKV_SMEM, stream, 1, tq, tk, tv, p, nq, (int)total));
+  return 0;
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" void b200mix_debug_no_shortkv(int on) { b200::g_no_shortkv = on; }
 
 extern "C" int b200mix_sdpa(const void* q, const void* k, const void* v, void* o, int64_t B, int64_t Hq, int64_t Hkv,
                             int64_t Sq, int64_t Sk, int64_t D, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t k_sb,
@@ -429,6 +662,9 @@ extern "C" int b200mix_sdpa(const void* q, const void* k, const void* v, void* o
   if (int rc = make_attn_tmap(&tq, q, D, Sq, Hq, B, q_ss, q_sh, q_sb, p.q_pos)) return rc;
   if (int rc = make_attn_tmap(&tk, k, D, Sk, Hkv, B, k_ss, k_sh, k_sb, p.k_pos)) return rc;
   if (int rc = make_attn_tmap(&tv, v, D, Sk, Hkv, B, v_ss, v_sh, v_sb, p.v_pos)) return rc;
+  cudaStream_t st0 = reinterpret_cast<cudaStream_t>(stream);
+  if (D == 64 && !causal && !cu_seqlens && Sk <= 128 && !g_no_shortkv && B * Hq * ((Sq + 127) / 128) < (1ll << 31))
+    return launch_attn_shortkv(tq, tk, tv, p, (int)B, st0);
   int64_t q_tiles = (Sq + 127) / 128 + (cu_seqlens ? nseq : 0);
   dim3 grid((unsigned)q_tiles, (unsigned)Hq, (unsigned)B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

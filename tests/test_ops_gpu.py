@@ -173,6 +173,30 @@ def test_sdpa(ops, B, Sq, Sk, Hq, Hkv, D, causal):
     close(out, ref, ATT_ATOL, ATT_RTOL, f"sdpa B{B} Sq{Sq} Sk{Sk} H{Hq}/{Hkv} D{D} causal={causal}")
 
 
+@pytest.mark.parametrize("B,Sq,Sk,Hq,Hkv", [(8, 1024, 77, 20, 20), (2, 4096, 77, 10, 10), (3, 1000, 1, 2, 2),
+                                            (1, 130, 17, 3, 3), (5, 384, 96, 6, 2), (2, 256, 128, 4, 4),
+                                            (1, 128, 33, 1, 1), (37, 200, 64, 9, 3)])
+def test_sdpa_short_kv_persistent(ops, B, Sq, Sk, Hq, Hkv):
+    """Sk <= 128, D = 64, non-causal takes the persistent short-KV kernel (K / V resident, Q ring, several
+    (batch, head) groups per CTA); it must agree with the general kernel and with the fp32 reference."""
+    from paddlemix_b200._lib import lib
+    D = 64
+    q, k, v = rnd(B, Sq, Hq, D, seed=90), rnd(B, Sk, Hkv, D, seed=91), rnd(B, Sk, Hkv, D, seed=92)
+    lens = torch.tensor([max(1, Sk - 3 * b) for b in range(B)], dtype=torch.int32, device="cuda")
+    for kv_lens in (None, lens):
+        out = ops.sdpa(q, k, v, kv_lens=kv_lens)
+        lib.b200mix_debug_no_shortkv(1)
+        try:
+            gen = ops.sdpa(q, k, v, kv_lens=kv_lens)
+        finally:
+            lib.b200mix_debug_no_shortkv(0)
+        close(out, gen.float(), ATT_ATOL, ATT_RTOL, f"short-kv vs general B{B} Sq{Sq} Sk{Sk}")
+        for b in ([0, B - 1] if kv_lens is not None else [0]):
+            n = int(lens[b]) if kv_lens is not None else Sk
+            ref = ref_sdpa(q[b:b + 1], k[b:b + 1, :n], v[b:b + 1, :n], D ** -0.5)
+            close(out[b:b + 1], ref, ATT_ATOL, ATT_RTOL, f"short-kv B{B} Sq{Sq} Sk{Sk} H{Hq}/{Hkv} b{b} n{n}")
+
+
 def test_sdpa_large_logits(ops):
     # large |q.k| exercises the lazy-rescale path (running max grows by more than 2^8 between tiles)
     B, S, H, D = 1, 512, 2, 64
