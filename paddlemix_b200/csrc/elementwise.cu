@@ -123,6 +123,68 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, void* _
   }
 }
 
+// conv_in with Cin == 4 (SD / SDXL latents): one thread = one output pixel. Its 3x3x4 input patch is read once into
+// registers (bf16-rounded, zero outside the image) and reused for every output channel; the filter bank sits in shared
+// memory as fp32 [36][Cout] and is read as warp-wide broadcasts (all lanes want the same 8 output channels), so the
+// kernel runs at the FP32 FMA rate: 8 x 128 x 128 x 320 in ~60 us instead of 1.4 ms for the generic kernel below.
+// Same accumulation order as the generic kernel (taps outside the image contribute fma(0, w, acc) == acc).
+__global__ void __launch_bounds__(256) conv3x3_cin4_kernel(const void* __restrict__ x, int x_fp32,
+                                                           const __nv_bfloat16* __restrict__ w,
+                                                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                           int B, int H, int W, int Cout) {
+  extern __shared__ float sw[];  // [36][Cout] then bias [Cout]
+  float* sb = sw + 36 * Cout;
+  for (int i = threadIdx.x; i < 36 * Cout; i += blockDim.x) {
+    const int co = i / 36, k = i - co * 36;  // w is [Cout][36]
+    sw[k * Cout + co] = __bfloat162float(w[i]);
+  }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.0f;
+  __syncthreads();
+  const long long npix = static_cast<long long>(B) * H * W;
+  for (long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; pix < npix;
+       pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ow = static_cast<int>(pix % W);
+    const int oh = static_cast<int>((pix / W) % H);
+    const long long b = pix / (static_cast<long long>(W) * H);
+    float xr[36];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int ih = oh + t / 3 - 1, iw = ow + t % 3 - 1;
+      float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+        const long long src = ((b * H + ih) * W + iw) * 4;
+        if (x_fp32) {
+          const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + src);
+          // rounded to bf16 first: the tensor-core path of every other conv sees bf16 activations
+          v = make_float4(__bfloat162float(__float2bfloat16(f.x)), __bfloat162float(__float2bfloat16(f.y)),
+                          __bfloat162float(__float2bfloat16(f.z)), __bfloat162float(__float2bfloat16(f.w)));
+        } else {
+          const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + src);
+          v = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+        }
+      }
+      xr[4 * t + 0] = v.x, xr[4 * t + 1] = v.y, xr[4 * t + 2] = v.z, xr[4 * t + 3] = v.w;
+    }
+    __nv_bfloat16* dst = y + pix * Cout;
+#pragma unroll 1
+    for (int g = 0; g < (Cout >> 3); ++g) {
+      const float4 b0 = *reinterpret_cast<const float4*>(sb + g * 8), b1 = *reinterpret_cast<const float4*>(sb + g * 8 + 4);
+      float acc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int k = 0; k < 36; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + k * Cout + g * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + k * Cout + g * 8 + 4);
+        acc[0] = fmaf(xr[k], w0.x, acc[0]), acc[1] = fmaf(xr[k], w0.y, acc[1]);
+        acc[2] = fmaf(xr[k], w0.z, acc[2]), acc[3] = fmaf(xr[k], w0.w, acc[3]);
+        acc[4] = fmaf(xr[k], w1.x, acc[4]), acc[5] = fmaf(xr[k], w1.y, acc[5]);
+        acc[6] = fmaf(xr[k], w1.z, acc[6]), acc[7] = fmaf(xr[k], w1.w, acc[7]);
+      }
+      *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                           pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+    }
+  }
+}
+
 // conv_in: Cin <= 8. Thread = (pixel, 8 output channels); weights staged in smem as fp32 [9*Cin][Cout].
 __global__ void conv3x3_small_cin_kernel(const void* __restrict__ x, int x_fp32, const __nv_bfloat16* __restrict__ w,
                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B, int H,
@@ -377,6 +439,21 @@ extern "C" int b200mix_conv3x3_small_cin(const void* x, int32_t x_fp32, const vo
   if (!configured) {
     B200_CUDA(cudaFuncSetAttribute(conv3x3_small_cin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
+  }
+  if (Cin == 4 && (9 * 4 + 1) * Cout * sizeof(float) <= 200 * 1024 && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
+    static bool configured4 = false;
+    if (!configured4) {
+      B200_CUDA(cudaFuncSetAttribute(conv3x3_cin4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured4 = true;
+    }
+    const size_t smem4 = (size_t)(36 + 1) * Cout * sizeof(float);
+    unsigned grid4 = ew_grid(B * H * W, 256);
+    if (grid4 > 4u * (unsigned)num_sms()) grid4 = 4u * (unsigned)num_sms();
+    conv3x3_cin4_kernel<<<grid4, 256, smem4, ST(stream)>>>(x, x_fp32, reinterpret_cast<const __nv_bfloat16*>(w), bias,
+                                                          reinterpret_cast<__nv_bfloat16*>(y), (int)B, (int)H, (int)W,
+                                                          (int)Cout);
+    B200_LAUNCH_CHECK();
+    return 0;
   }
   const long long total = B * H * W * (Cout / 8);
   // every block first stages the whole filter bank in shared memory: keep the grid at ~2 blocks per SM

@@ -125,14 +125,20 @@ def test_conv3x3_residual(ops):
     close(out, (ref + res.float()) * 0.5, GEMM_ATOL, GEMM_RTOL, "conv residual")
 
 
-def test_conv_small_cin(ops):
-    B, H, W, Cin, Cout = 2, 32, 32, 4, 320
+@pytest.mark.parametrize("B,H,W,Cin,Cout,fp32_in", [(2, 32, 32, 4, 320, True), (3, 17, 23, 4, 64, False),
+                                                    (1, 8, 8, 8, 32, True), (2, 9, 5, 3, 16, False), (1, 64, 64, 4, 1152, True)])
+def test_conv_small_cin(ops, B, H, W, Cin, Cout, fp32_in):
+    # Cin == 4 (16-byte aligned input) takes the pixel-per-thread kernel, everything else the generic one
     x = rnd(B, H, W, Cin, seed=27, dtype=torch.float32)
+    if not fp32_in:
+        x = x.to(bf16)
     w, bias = rnd(Cout, 3, 3, Cin, seed=28, scale=0.2), rnd(Cout, seed=29, dtype=torch.float32)
     out = ops.conv3x3_small_cin(x, w, bias)
     xr = x.to(bf16).float()
     ref = F.conv2d(xr.permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
-    close(out, ref, 1e-2, 1e-2, "conv_in")
+    close(out, ref, 1e-2, 1e-2, f"conv_in {B}x{H}x{W} {Cin}->{Cout}")
+    out_nb = ops.conv3x3_small_cin(x, w, None)
+    close(out_nb, ref - bias, 1e-2, 1e-2, "conv_in without bias")
 
 
 def ref_sdpa(q, k, v, scale, causal=False, cu=None):
