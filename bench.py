@@ -65,6 +65,16 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+def igemm_traffic_per_launch():
+    """DRAM bytes (read + write) per igemm launch, averaged over the launches of one SDXL forward, from the committed ncu
+    pass profiles/r01_igemm_dram_traffic.json (tools/gpu_ncu.sh); None if that file is absent. Not measured live."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_igemm_dram_traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -327,7 +337,7 @@ def run_b200(args):
             total_ms = sum(v["ms"] for v in prof.values())
             roof = {"kernel": "igemm_kernel (tcgen05 implicit GEMM: linear + conv3x3)", "bound": "tensor",
                     "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
-                    "traffic": None, "peak_source": how, "launches_per_step": ig["calls"],
+                    "traffic": igemm_traffic_per_launch(), "peak_source": how, "launches_per_step": ig["calls"],
                     "avg_launch_ms": round(ig["ms"] / ig["calls"], 4), "share_of_step": round(ig["ms"] / total_ms, 3),
                     "algorithmic_tflop_per_step": round(ig["work"] / 1e12, 2),
                     "by_kernel_ms": {k: round(v["ms"], 3) for k, v in prof.items()},

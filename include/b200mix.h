@@ -168,6 +168,12 @@ int b200mix_ddim_step(const void* eps_u, const void* eps_c, int32_t eps_fp32, fl
 int b200mix_euler_step(const void* v_u, const void* v_c, int32_t v_fp32, float guidance, const float* x, float* x_prev,
                        int64_t n, float sigma, float dt, void* stream);
 
+/* EulerDiscreteScheduler (scheduling_euler_discrete.py:135-503; SDXL's default sampler), deterministic path
+ * (s_churn = 0, epsilon prediction): its step IS b200mix_euler_step (pred = x - sigma*eps; derivative = (x - pred)/sigma;
+ * x_prev = x + derivative*dt). scale_model_input (:218-241) divides the fp32 sample by (sigma^2 + 1) ** 0.5; the
+ * host computes that denominator in fp32, this applies an IEEE fp32 division. */
+int b200mix_scale_model_input(const float* x, float* y, int64_t n, float denom, void* stream);
+
 /* SD3 / DiT patchify: x NCHW [B,C,H,W] (fp32|bf16) -> rows [B*(H/p)*(W/p), C*p*p] bf16 with the column order
  * (c, ph, pw) of a flattened Conv2D weight [D,C,p,p] (PatchEmbed.proj, embeddings.py:143-150), and its inverse for
  * the output head: rows [B*h*w, p*p*C] in (ph, pw, c) order -> NCHW [B,C,h*p,w*p] (transformer_sd3.py:350-356). */

@@ -194,3 +194,138 @@ class FlowMatchEulerDiscreteScheduler:
         prev_sample = sample + derivative * dt
         self._step_index += 1
         return prev_sample.to(model_output.dtype)
+
+
+class EulerDiscreteScheduler:
+    """ppdiffusers/schedulers/scheduling_euler_discrete.py:135-503 (SDXL's default sampler), s_churn = 0 (the
+    deterministic path: gamma = 0, the drawn noise is multiplied by zero). fp32 torch tensors stand in for paddle fp32
+    tensors; the numpy float64 pieces (np.interp, the Karras ramp, _sigma_to_t) are numpy float64 here as well.
+    Pinned by the RNG-free goldens of ppdiffusers/tests/schedulers/test_scheduler_euler.py:63-200
+    (tests/golden/euler_goldens.json)."""
+    order = 1
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                 prediction_type="epsilon", interpolation_type="linear", use_karras_sigmas=False, sigma_min=None,
+                 sigma_max=None, timestep_spacing="linspace", timestep_type="discrete", steps_offset=0):  # :135-203
+        if beta_schedule == "linear":
+            self.betas = linspace_f32(beta_start, beta_end, num_train_timesteps)
+        elif beta_schedule == "scaled_linear":
+            self.betas = linspace_f32(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps) ** 2
+        elif beta_schedule == "squaredcos_cap_v2":
+            self.betas = betas_for_alpha_bar(num_train_timesteps)
+        else:
+            raise NotImplementedError(f"{beta_schedule} does is not implemented for {self.__class__}")
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = cumprod_f32(self.alphas)
+        self.config = dict(num_train_timesteps=num_train_timesteps, prediction_type=prediction_type,
+                           interpolation_type=interpolation_type, sigma_min=sigma_min, sigma_max=sigma_max,
+                           timestep_spacing=timestep_spacing, timestep_type=timestep_type, steps_offset=steps_offset)
+        sigmas = self._train_sigmas()
+        timesteps = np.linspace(0, num_train_timesteps - 1, num_train_timesteps, dtype=float)[::-1].copy()
+        self.timesteps = torch.tensor(timesteps, dtype=torch.float32)
+        self.sigmas = torch.cat([torch.from_numpy(sigmas[::-1].copy()), torch.zeros(1)])
+        self.use_karras_sigmas = use_karras_sigmas
+        self.num_inference_steps = None
+        self._step_index = None
+
+    def _train_sigmas(self):  # np.array(((1 - alphas_cumprod) / alphas_cumprod) ** 0.5): fp32 tensor math -> float32 array
+        return pow_half((1 - self.alphas_cumprod) / self.alphas_cumprod).numpy()
+
+    @property
+    def init_noise_sigma(self):  # :205-211
+        if self.config["timestep_spacing"] in ("linspace", "trailing"):
+            return self.sigmas.max()
+        return pow_half(self.sigmas.max() ** 2 + 1)
+
+    def set_timesteps(self, num_inference_steps):  # :243-310
+        c = self.config
+        self.num_inference_steps = num_inference_steps
+        N = c["num_train_timesteps"]
+        if c["timestep_spacing"] == "linspace":
+            timesteps = np.linspace(0, N - 1, num_inference_steps, dtype=np.float32)[::-1].copy()
+        elif c["timestep_spacing"] == "leading":
+            step_ratio = N // num_inference_steps
+            timesteps = (np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(np.float32)
+            timesteps += c["steps_offset"]
+        elif c["timestep_spacing"] == "trailing":
+            step_ratio = N / num_inference_steps
+            timesteps = (np.arange(N, 0, -step_ratio)).round().copy().astype(np.float32)
+            timesteps -= 1
+        else:
+            raise ValueError(f"{c['timestep_spacing']} is not supported.")
+        sigmas = self._train_sigmas()
+        log_sigmas = np.log(sigmas)
+        if c["interpolation_type"] == "linear":
+            sigmas = np.interp(timesteps, np.arange(0, len(sigmas)), sigmas)
+        elif c["interpolation_type"] == "log_linear":
+            sigmas = np.exp(np.linspace(np.log(sigmas[-1]), np.log(sigmas[0]), num_inference_steps + 1, dtype=np.float32))
+        else:
+            raise ValueError(f"{c['interpolation_type']} is not implemented.")
+        if self.use_karras_sigmas:
+            sigmas = self._convert_to_karras(sigmas, num_inference_steps)
+            timesteps = np.array([self._sigma_to_t(sigma, log_sigmas) for sigma in sigmas])
+        sigmas = torch.from_numpy(np.asarray(sigmas)).to(torch.float32)
+        self.timesteps = torch.from_numpy(timesteps.astype(np.float32))
+        self.sigmas = torch.cat([sigmas, torch.zeros(1)])
+        self._step_index = None
+
+    @staticmethod
+    def _sigma_to_t(sigma, log_sigmas):  # :312-332
+        log_sigma = np.log(np.maximum(sigma, 1e-10))
+        dists = log_sigma - log_sigmas[:, np.newaxis]
+        low_idx = np.cumsum((dists >= 0), axis=0).argmax(axis=0).clip(max=log_sigmas.shape[0] - 2)
+        high_idx = low_idx + 1
+        low, high = log_sigmas[low_idx], log_sigmas[high_idx]
+        w = np.clip((low - log_sigma) / (low - high), 0, 1)
+        t = (1 - w) * low_idx + w * high_idx
+        return t.reshape(np.shape(sigma))
+
+    def _convert_to_karras(self, in_sigmas, num_inference_steps):  # :335-358
+        sigma_min = self.config["sigma_min"] if self.config["sigma_min"] is not None else in_sigmas[-1].item()
+        sigma_max = self.config["sigma_max"] if self.config["sigma_max"] is not None else in_sigmas[0].item()
+        rho = 7.0
+        ramp = np.linspace(0, 1, num_inference_steps)
+        min_inv_rho, max_inv_rho = sigma_min ** (1 / rho), sigma_max ** (1 / rho)
+        return (max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** rho
+
+    def _init_step_index(self, timestep):  # :360-373
+        cand = (self.timesteps == timestep).nonzero()
+        self._step_index = (cand[1] if len(cand) > 1 else cand[0]).item()
+
+    def scale_model_input(self, sample, timestep):  # :218-241
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        sigma = self.sigmas[self._step_index]
+        return sample / pow_half(sigma ** 2 + 1)
+
+    def step(self, model_output, timestep, sample):  # :375-470 with s_churn = 0 (gamma = 0, sigma_hat = sigma)
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        sigma = self.sigmas[self._step_index]
+        sigma_hat = sigma * (0.0 + 1)
+        pt = self.config["prediction_type"]
+        if pt in ("original_sample", "sample"):
+            pred_original_sample = model_output
+        elif pt == "epsilon":
+            pred_original_sample = sample - sigma_hat * model_output
+        elif pt == "v_prediction":
+            pred_original_sample = model_output * (-sigma / pow_half(sigma ** 2 + 1)) + (sample / (sigma ** 2 + 1))
+        else:
+            raise ValueError(f"prediction_type given as {pt} must be one of `epsilon`, or `v_prediction`")
+        derivative = (sample - pred_original_sample) / sigma_hat
+        dt = self.sigmas[self._step_index + 1] - sigma_hat
+        prev_sample = sample + derivative * dt
+        self._step_index += 1
+        return prev_sample
+
+    def step_scalars(self):
+        """(sigma, dt) of the NEXT step() call as python floats (what the product's host scheduler hands the kernel)."""
+        sigma = self.sigmas[self._step_index]
+        return float(sigma), float(self.sigmas[self._step_index + 1] - sigma)
+
+    def add_noise(self, original_samples, noise, timesteps):  # :472-497
+        idx = [(self.timesteps == t).nonzero().item() for t in timesteps]
+        sigma = self.sigmas[idx].flatten()
+        while sigma.ndim < original_samples.ndim:
+            sigma = sigma.unsqueeze(-1)
+        return original_samples + noise * sigma

@@ -69,6 +69,7 @@ SIGNATURES = {
                           c_float, c_float, c_void_p],
     "b200mix_euler_step": [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_int64, c_float, c_float,
                            c_void_p],
+    "b200mix_scale_model_input": [c_void_p, c_void_p, c_int64, c_float, c_void_p],
     "b200mix_gather_rows": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p],
     "b200mix_scatter_rows": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p],
     "b200mix_broadcast_add": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],

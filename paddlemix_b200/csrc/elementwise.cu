@@ -248,6 +248,13 @@ __global__ void ddim_step_kernel(const void* __restrict__ eps_u, const void* __r
   }
 }
 
+// EulerDiscreteScheduler.scale_model_input (scheduling_euler_discrete.py:218-241): sample / ((sigma^2 + 1) ** 0.5), the
+// denominator computed on the host in fp32; an IEEE division here, like the reference's tensor / 0-d tensor.
+__global__ void scale_model_input_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float denom) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __fdiv_rn(x[i], denom);
+}
+
 __global__ void euler_step_kernel(const void* __restrict__ v_u, const void* __restrict__ v_c, int v_fp32, float guidance,
                                   const float* __restrict__ x, float* __restrict__ x_prev, long long n, float sigma,
                                   float dt) {
@@ -482,6 +489,14 @@ extern "C" int b200mix_euler_step(const void* v_u, const void* v_c, int32_t v_fp
   if (int rc = ensure_device()) return rc;
   B200_CHECK_ARG(v_u && x && x_prev && n > 0, "euler_step: bad arguments");
   euler_step_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(v_u, v_c, v_fp32, guidance, x, x_prev, n, sigma, dt);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_scale_model_input(const float* x, float* y, int64_t n, float denom, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(x && y && n > 0 && denom > 0.0f, "scale_model_input: bad arguments");
+  scale_model_input_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(x, y, n, denom);
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -368,6 +368,17 @@ def euler_step(v_u, v_c, guidance, x, sigma, dt, out=None):
     return out
 
 
+def scale_model_input(x: torch.Tensor, denom: float, out=None) -> torch.Tensor:
+    """EulerDiscreteScheduler.scale_model_input: x / denom in fp32 (IEEE division)."""
+    _req(x, torch.float32, "x")
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.b200mix_scale_model_input(_p(x), _p(out), x.numel(), float(denom), _stream()), "b200mix_scale_model_input")
+    _count()
+    return out
+
+
 def cast(x: torch.Tensor, dtype):
     assert x.is_contiguous()
     out = torch.empty_like(x, dtype=dtype)

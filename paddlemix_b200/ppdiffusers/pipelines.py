@@ -120,6 +120,9 @@ class StableDiffusionPipeline:
                 raise ValueError("height/width (or latents) are required")
             g = generator or torch.Generator().manual_seed(0)
             latents = torch.randn(B, self.unet.config.in_channels, height // 8, width // 8, generator=g)
+        # timesteps first (pipeline_stable_diffusion.py:808-811), then prepare_latents scales the initial noise by the
+        # scheduler's init_noise_sigma (:813-824, :583): for EulerDiscrete that value depends on the chosen timesteps
+        self.scheduler.set_timesteps(num_inference_steps)
         latents = latents.to(device=dev, dtype=torch.float32).contiguous() * self.scheduler.init_noise_sigma
         ctx = prompt_embeds.to(device=dev, dtype=bf16)
         added = None
@@ -133,7 +136,6 @@ class StableDiffusionPipeline:
         ctx = ctx.contiguous()
         if added is not None:
             added = {k: (v.to(bf16) if k == "text_embeds" else v.to(torch.float32)).contiguous() for k, v in added.items()}
-        self.scheduler.set_timesteps(num_inference_steps)
         rows = 2 * B if do_cfg else B
         sample_shape = (rows,) + tuple(latents.shape[1:])
         den = self._denoiser(sample_shape, ctx.shape, added)
@@ -141,12 +143,14 @@ class StableDiffusionPipeline:
         nxt = torch.empty_like(latents)
         first = True
         for i, t in enumerate(self.scheduler.timesteps):
-            # latent_model_input = concat([latents] * 2) if CFG (:860); DDIM scale_model_input is the identity
+            # latent_model_input = scheduler.scale_model_input(concat([latents] * 2) if CFG) (:860-861): the identity for
+            # DDIM, x / sqrt(sigma^2 + 1) for EulerDiscrete
+            scaled = self.scheduler.scale_model_input(latents, t)
             if do_cfg:
-                model_in[:B].copy_(latents)
-                model_in[B:].copy_(latents)
+                model_in[:B].copy_(scaled)
+                model_in[B:].copy_(scaled)
             else:
-                model_in = latents
+                model_in = scaled
             if den is not None:
                 eps = den(model_in, float(t), ctx if first else None, added if first else None)
             else:

@@ -166,3 +166,139 @@ class FlowMatchEulerDiscreteScheduler:
         from .. import ops
         sigma, dt = self.step_scalars(timestep)
         return ops.euler_step(model_output, model_output_cond, guidance_scale, sample, sigma, dt, out=out)
+
+
+class EulerDiscreteScheduler:
+    """ppdiffusers.EulerDiscreteScheduler (scheduling_euler_discrete.py:135-503; SDXL's default sampler) restricted to
+    the deterministic path the pipelines use (s_churn = 0 => gamma = 0, sigma_hat = sigma; epsilon prediction). All
+    schedule arithmetic runs on the host in numpy with the reference's dtypes (fp32 tensors -> np.float32, its
+    np.interp / Karras ramp / _sigma_to_t pieces in float64); the per-step update is the same fp32 expression as the
+    reference's (`pred = x - sigma*eps; derivative = (x - pred)/sigma; x + derivative*dt`), which is exactly
+    `b200mix_euler_step`; `scale_model_input` is `b200mix_scale_model_input` (x / sqrt(sigma^2 + 1) with an IEEE fp32
+    division)."""
+
+    order = 1
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.0001, beta_end: float = 0.02,
+                 beta_schedule: str = "linear", prediction_type: str = "epsilon", interpolation_type: str = "linear",
+                 use_karras_sigmas: bool = False, sigma_min: Optional[float] = None, sigma_max: Optional[float] = None,
+                 timestep_spacing: str = "linspace", timestep_type: str = "discrete", steps_offset: int = 0):
+        if beta_schedule == "linear":
+            self.betas = _linspace_f32(beta_start, beta_end, num_train_timesteps)
+        elif beta_schedule == "scaled_linear":
+            self.betas = _linspace_f32(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps) ** 2
+        elif beta_schedule == "squaredcos_cap_v2":
+            self.betas = _betas_for_alpha_bar(num_train_timesteps)
+        else:
+            raise NotImplementedError(f"{beta_schedule} does is not implemented for {self.__class__}")
+        if prediction_type != "epsilon":
+            raise NotImplementedError("EulerDiscreteScheduler(b200): only prediction_type='epsilon' has a device step")
+        if timestep_type != "discrete":
+            raise NotImplementedError("EulerDiscreteScheduler(b200): only timestep_type='discrete'")
+        self.alphas = (f32(1.0) - self.betas).astype(f32)
+        self.alphas_cumprod = _cumprod_f32(self.alphas)
+        self.num_train_timesteps = num_train_timesteps
+        self.interpolation_type, self.use_karras_sigmas = interpolation_type, use_karras_sigmas
+        self.sigma_min, self.sigma_max = sigma_min, sigma_max
+        self.timestep_spacing, self.steps_offset = timestep_spacing, steps_offset
+        sig = self._train_sigmas()
+        self.timesteps = np.linspace(0, num_train_timesteps - 1, num_train_timesteps, dtype=float)[::-1].astype(f32)
+        self.sigmas = np.concatenate([sig[::-1], np.zeros(1, dtype=f32)]).astype(f32)
+        self.num_inference_steps: Optional[int] = None
+        self._step_index: Optional[int] = None
+
+    def _train_sigmas(self):
+        ac = self.alphas_cumprod
+        return np.sqrt(((f32(1.0) - ac) / ac).astype(f32), dtype=f32)
+
+    @property
+    def init_noise_sigma(self) -> float:
+        m = self.sigmas.max()
+        if self.timestep_spacing in ("linspace", "trailing"):
+            return float(m)
+        return float(np.sqrt(f32(f32(m * m) + f32(1.0)), dtype=f32))
+
+    def set_timesteps(self, num_inference_steps: int):
+        N = self.num_train_timesteps
+        self.num_inference_steps = num_inference_steps
+        if self.timestep_spacing == "linspace":
+            timesteps = np.linspace(0, N - 1, num_inference_steps, dtype=f32)[::-1].copy()
+        elif self.timestep_spacing == "leading":
+            step_ratio = N // num_inference_steps
+            timesteps = (np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(f32)
+            timesteps += self.steps_offset
+        elif self.timestep_spacing == "trailing":
+            step_ratio = N / num_inference_steps
+            timesteps = (np.arange(N, 0, -step_ratio)).round().copy().astype(f32)
+            timesteps -= 1
+        else:
+            raise ValueError(f"{self.timestep_spacing} is not supported. Please make sure to choose one of 'linspace', "
+                             "'leading' or 'trailing'.")
+        sigmas = self._train_sigmas()
+        log_sigmas = np.log(sigmas)
+        if self.interpolation_type == "linear":
+            sigmas = np.interp(timesteps, np.arange(0, len(sigmas)), sigmas)
+        elif self.interpolation_type == "log_linear":
+            sigmas = np.exp(np.linspace(np.log(sigmas[-1]), np.log(sigmas[0]), num_inference_steps + 1, dtype=f32))
+        else:
+            raise ValueError(f"{self.interpolation_type} is not implemented. Please specify interpolation_type to either"
+                             " 'linear' or 'log_linear'")
+        if self.use_karras_sigmas:
+            smin = self.sigma_min if self.sigma_min is not None else sigmas[-1].item()
+            smax = self.sigma_max if self.sigma_max is not None else sigmas[0].item()
+            rho = 7.0
+            ramp = np.linspace(0, 1, num_inference_steps)
+            sigmas = (smax ** (1 / rho) + ramp * (smin ** (1 / rho) - smax ** (1 / rho))) ** rho
+            timesteps = np.array([self._sigma_to_t(s, log_sigmas) for s in sigmas])
+        self.timesteps = np.asarray(timesteps).astype(f32)
+        self.sigmas = np.concatenate([np.asarray(sigmas).astype(f32), np.zeros(1, dtype=f32)])
+        self._step_index = None
+
+    @staticmethod
+    def _sigma_to_t(sigma, log_sigmas):
+        log_sigma = np.log(np.maximum(sigma, 1e-10))
+        dists = log_sigma - log_sigmas[:, np.newaxis]
+        low_idx = np.cumsum((dists >= 0), axis=0).argmax(axis=0).clip(max=log_sigmas.shape[0] - 2)
+        high_idx = low_idx + 1
+        low, high = log_sigmas[low_idx], log_sigmas[high_idx]
+        w = np.clip((low - log_sigma) / (low - high), 0, 1)
+        return ((1 - w) * low_idx + w * high_idx).reshape(np.shape(sigma))
+
+    def _init_step_index(self, timestep):
+        cand = np.nonzero(self.timesteps == f32(timestep))[0]
+        if len(cand) == 0:
+            raise ValueError(f"timestep {timestep} is not one of scheduler.timesteps")
+        self._step_index = int(cand[1] if len(cand) > 1 else cand[0])
+
+    def input_scale_denominator(self, timestep) -> float:
+        """(sigma^2 + 1) ** 0.5 in fp32: what scale_model_input divides the sample by."""
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        s = self.sigmas[self._step_index]
+        return float(np.sqrt(f32(f32(s * s) + f32(1.0)), dtype=f32))
+
+    def scale_model_input(self, sample, timestep, out=None):
+        from .. import ops
+        return ops.scale_model_input(sample, self.input_scale_denominator(timestep), out=out)
+
+    def step_scalars(self, timestep):
+        if isinstance(timestep, (int, np.integer)):
+            raise ValueError("Passing integer indices (e.g. from `enumerate(timesteps)`) as timesteps to "
+                             "`EulerDiscreteScheduler.step()` is not supported. Make sure to pass one of the "
+                             "`scheduler.timesteps` as a timestep.")
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        sigma = self.sigmas[self._step_index]
+        dt = f32(self.sigmas[self._step_index + 1] - sigma)
+        self._step_index += 1
+        return float(sigma), float(dt)
+
+    def step(self, model_output, timestep, sample, model_output_cond=None, guidance_scale=0.0, out=None):
+        from .. import ops
+        sigma, dt = self.step_scalars(timestep)
+        return ops.euler_step(model_output, model_output_cond, guidance_scale, sample, sigma, dt, out=out)
+
+    def add_noise_sigma(self, timestep) -> float:
+        """sigma of `timestep`: add_noise is original + noise * sigma (scheduling_euler_discrete.py:472-497)."""
+        idx = np.nonzero(self.timesteps == f32(timestep))[0]
+        return float(self.sigmas[int(idx[0])])

@@ -28,5 +28,17 @@ sinus = {
          "values": [-0.9801, -0.9464, -0.9349, -0.3952, 0.8887, -0.9709, 0.5299, -0.2853, -0.9927]},
     ],
 }
+euler = {  # ppdiffusers/tests/schedulers/test_scheduler_euler.py:25-33 (config), :63-200 (full loops, 10 steps)
+    "config": {"num_train_timesteps": 1100, "beta_start": 0.0001, "beta_end": 0.02, "beta_schedule": "linear"},
+    "num_inference_steps": 10,
+    "full_loop": [
+        {"config": {}, "sum": 10.0807, "mean": 0.0131},
+        {"config": {"prediction_type": "v_prediction"}, "sum": 0.0002, "mean": 2.2676e-06},
+        {"config": {"use_karras_sigmas": True}, "sum": 124.52299499511719, "mean": 0.16213932633399963},
+    ],
+    "full_loop_with_noise": {"t_start": 8, "sum": 57062.9023, "mean": 74.3007},
+    "sum_atol": 1e-2, "mean_atol": 1e-3,
+}
+json.dump(euler, open(os.path.join(HERE, "euler_goldens.json"), "w"), indent=1)
 json.dump(ddim, open(os.path.join(HERE, "ddim_goldens.json"), "w"), indent=1)
 json.dump(sinus, open(os.path.join(HERE, "sinusoid_goldens.json"), "w"), indent=1)

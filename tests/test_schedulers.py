@@ -57,3 +57,40 @@ def test_flow_match_bit_exact(shift):
         ref = o.step(v, torch.tensor(t), x)
         assert torch.equal(mine, ref)
         x = ref
+
+
+SDXL_EULER = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", timestep_spacing="leading", steps_offset=1)
+
+
+@pytest.mark.parametrize("kw", [dict(num_train_timesteps=1100), SDXL_EULER, dict(SDXL_EULER, use_karras_sigmas=True),
+                                dict(timestep_spacing="trailing"), dict(interpolation_type="log_linear"),
+                                dict(use_karras_sigmas=True, sigma_min=0.02, sigma_max=700.0)])
+@pytest.mark.parametrize("n", [10, 30])
+def test_euler_discrete_bit_exact(kw, n):
+    """Host EulerDiscreteScheduler (numpy) == oracle (torch fp32 restatement of scheduling_euler_discrete.py): sigmas,
+    timesteps, init_noise_sigma, the scale_model_input denominator and the (sigma, dt) handed to the step kernel."""
+    o, s = O.EulerDiscreteScheduler(**kw), S.EulerDiscreteScheduler(**kw)
+    assert np.array_equal(o.sigmas.numpy(), s.sigmas) and np.array_equal(o.timesteps.numpy(), s.timesteps)
+    o.set_timesteps(n), s.set_timesteps(n)
+    assert np.array_equal(o.sigmas.numpy(), s.sigmas) and np.array_equal(o.timesteps.numpy(), s.timesteps)
+    assert float(o.init_noise_sigma) == s.init_noise_sigma
+    g = torch.Generator().manual_seed(0)
+    x, e = torch.randn(2, 4, 8, 8, generator=g) * s.init_noise_sigma, torch.randn(2, 4, 8, 8, generator=g)
+    for t in s.timesteps[:5]:
+        den = torch.tensor(s.input_scale_denominator(t), dtype=torch.float32)
+        xs = o.scale_model_input(x, torch.tensor(t))
+        assert torch.equal(x / den, xs)
+        assert o.step_scalars() == tuple(np.float32(v) for v in s.step_scalars(t))
+        sigma, dt = (torch.tensor(v, dtype=torch.float32) for v in (s.sigmas[s._step_index - 1], s.sigmas[s._step_index] - s.sigmas[s._step_index - 1]))
+        mine = x + (x - (x - e * sigma)) / sigma * dt  # b200mix_euler_step's operation order
+        x = o.step(e, torch.tensor(t), x)
+        assert torch.equal(mine, x)
+
+
+def test_euler_rejects_what_has_no_device_path():
+    with pytest.raises(NotImplementedError):
+        S.EulerDiscreteScheduler(prediction_type="v_prediction")
+    s = S.EulerDiscreteScheduler()
+    s.set_timesteps(5)
+    with pytest.raises(ValueError):
+        s.step_scalars(3)

@@ -127,6 +127,49 @@ def test_graphed_pipeline_matches_eager_and_oracle_loop():
     compare(lat[True], cur, "4-step CFG DDIM loop")
 
 
+def test_euler_discrete_pipeline_matches_oracle_loop():
+    """SDXL's default sampler: EulerDiscreteScheduler (host numpy + b200mix_scale_model_input / b200mix_euler_step) driven
+    by the pipeline (graph and eager bit-identical) against the oracle's fp32 UNet + fp32 Euler loop; the device step
+    itself is bit-exact against the oracle on identical fp32 inputs."""
+    from oracle.schedulers import EulerDiscreteScheduler as OEuler
+    from paddlemix_b200 import ops
+    from paddlemix_b200.ppdiffusers.pipelines import StableDiffusionPipeline
+    from paddlemix_b200.ppdiffusers.schedulers import EulerDiscreteScheduler
+    XL = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", timestep_spacing="leading", steps_offset=1)
+    # (1) one step, bit-exact
+    o, s = OEuler(**XL), EulerDiscreteScheduler(**XL)
+    o.set_timesteps(8), s.set_timesteps(8)
+    g = torch.Generator().manual_seed(3)
+    xs, e = torch.randn(2, 4, 16, 16, generator=g) * s.init_noise_sigma, torch.randn(2, 4, 16, 16, generator=g)
+    for t in s.timesteps[:3]:
+        scaled = s.scale_model_input(xs.cuda(), t)
+        assert torch.equal(scaled.cpu(), o.scale_model_input(xs, torch.tensor(t)))
+        nxt = s.step(e.cuda(), t, xs.cuda())
+        xs = o.step(e, torch.tensor(t), xs)
+        assert torch.equal(nxt.cpu(), xs)
+    # (2) the pipeline loop
+    cfg, P, model = make("tiny_xl")
+    x, ctx, added = inputs(cfg, 2, 16, 20)
+    neg = torch.zeros_like(ctx)
+    steps, gs = 4, 5.0
+    lat = {}
+    for graph in (True, False):
+        pipe = StableDiffusionPipeline(model, EulerDiscreteScheduler(**XL), use_cuda_graph=graph)
+        lat[graph] = pipe(prompt_embeds=ctx, negative_prompt_embeds=neg, latents=x, num_inference_steps=steps,
+                          guidance_scale=gs, added_cond_kwargs=added).cpu()
+    assert torch.equal(lat[True], lat[False])
+    sch = OEuler(**XL)
+    sch.set_timesteps(steps)
+    cur = x.clone() * sch.init_noise_sigma
+    add2 = {k: torch.cat([v, v], 0) for k, v in added.items()}
+    for t in sch.timesteps:
+        xin = sch.scale_model_input(cur, t)
+        eps = O.unet_forward(cfg, P, torch.cat([xin, xin], 0), float(t), torch.cat([neg, ctx], 0), add2)
+        eu, ec = eps.chunk(2)
+        cur = sch.step(eu + gs * (ec - eu), t, cur)
+    compare(lat[True], cur, "4-step CFG Euler loop")
+
+
 @pytest.mark.slow
 def test_sd15_parity_config_c1():
     """BASELINE.json configs[0]: SD1.5 UNet, 1 x 512x512 (latent 64x64), one timestep, against the fp32 CPU oracle."""

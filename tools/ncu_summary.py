@@ -62,5 +62,23 @@ def full(path):
                 print(f"  {w:78s} {r[idx[w]][:24]:>24s} {units[idx[w]]}")
 
 
+def traffic(path):
+    """csv of `--metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:igemm` -> JSON for bench.py's roofline.traffic"""
+    import json
+    lines = [l for l in open(path) if not l.startswith("==")]
+    per = collections.defaultdict(float)
+    for row in csv.DictReader(lines):
+        if not row["Metric Name"].startswith("dram__bytes"):
+            continue
+        v = float(row["Metric Value"].replace(",", ""))
+        unit = row["Metric Unit"].lower()
+        mult = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
+        per[row["ID"]] += v * mult
+    n = len(per)
+    tot = sum(per.values())
+    print(json.dumps({"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:igemm, one eager SDXL forward "
+                                "(B=8, 1024^2)", "launches": n, "dram_bytes_total": tot, "dram_bytes_per_launch": round(tot / n)}))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
