@@ -99,6 +99,8 @@ def _load():
         getattr(lib, name).argtypes = []
     lib.b200mix_debug_force_bn.argtypes = [c_int]
     lib.b200mix_debug_force_bn.restype = None
+    lib.b200mix_debug_attn_bn64.argtypes = [c_int]
+    lib.b200mix_debug_attn_bn64.restype = None
     lib.b200mix_debug_no_shortkv.argtypes = [c_int]
     lib.b200mix_debug_no_shortkv.restype = None
     lib.b200mix_debug_gemm_pair.argtypes = [c_int]

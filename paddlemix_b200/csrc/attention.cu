@@ -50,26 +50,30 @@ __device__ __forceinline__ void tma_load_rows(void* dst, const CUtensorMap* m, u
 // tensor cores, so it runs TWO CTAs per SM (single S buffer, 2-deep K/V ring, 256 TMEM columns): while one CTA's
 // softmax warps exponentiate, the other CTA's MMAs use the tensor cores. D >= 128 keeps one CTA per SM with a
 // double-buffered S so QK^T(j+1) overlaps softmax(j) inside the CTA.
-template <int D>
+// BN = keys per K/V block. D = 64 with BN = 64 needs only 64 (S) + 64 (O) TMEM columns and 64 KB of shared memory, so
+// three CTAs could share an SM; measured slower than BN = 128 with two CTAs (see g_attn_bn64), so it is not the default.
+template <int D, int BN>
 struct AttnCfg {
   static constexpr int SB = (D == 64) ? 1 : 2;                      // S accumulator buffers in TMEM
   static constexpr int KS = (D == 192) ? 1 : 2;                     // K/V ring depth
-  static constexpr int TMEM_COLS = (D == 64) ? 256 : 512;           // SB*128 (S) + D (O), rounded to a power of 2
-  static constexpr int MIN_CTAS = (D == 64) ? 2 : 1;
-  // dynamic smem is declared __align__(1024) (128B-swizzle atoms), so no alignment slack: two D=64 CTAs fit one SM
-  static constexpr int SMEM = (1 + 2 * KS) * 128 * D * 2 + 128 * 128 * 2 + 256;
+  static constexpr int TMEM_COLS = (D == 64) ? (BN == 64 ? 128 : 256) : 512;  // SB*BN (S) + D (O), power of 2
+  static constexpr int MIN_CTAS = (D == 64) ? (BN == 64 ? 3 : 2) : 1;
+  // dynamic smem is declared __align__(1024) (128B-swizzle atoms), so no alignment slack
+  static constexpr int SMEM = 128 * D * 2 + 2 * KS * BN * D * 2 + 128 * BN * 2 + 256;
 };
 
-template <int D>
-__global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
+template <int D, int BN>
+__global__ void __launch_bounds__(192, AttnCfg<D, BN>::MIN_CTAS)
     attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
   constexpr int DC = D / 64;               // 64-wide head-dim chunks (one 128B swizzle atom each)
-  constexpr int TILE_BYTES = 128 * D * 2;  // one 128-row tile of Q / K / V
-  constexpr int KS = AttnCfg<D>::KS;
-  constexpr int SB = AttnCfg<D>::SB;
-  constexpr int P_BYTES = 128 * 128 * 2;
-  constexpr uint32_t TM_S = 0, TM_O = SB * 128;
+  constexpr int TILE_BYTES = 128 * D * 2;  // the 128-row Q tile
+  constexpr int KV_BYTES = BN * D * 2;     // one BN-row tile of K / V
+  constexpr int KV_PANEL = BN * 128;       // one 64-wide head-dim panel of it
+  constexpr int KS = AttnCfg<D, BN>::KS;
+  constexpr int SB = AttnCfg<D, BN>::SB;
+  constexpr int P_BYTES = 128 * BN * 2;
+  constexpr uint32_t TM_S = 0, TM_O = SB * BN;
 
   // cu_seqlens / kv_lens are read right away: if they are given, wait for the previous kernel first
   if (p.cu || p.kv_lens) pdl_wait();
@@ -107,14 +111,14 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
   const int kv_len = kv_end - kv_begin;
   int n_kv = kv_len;
   if (p.causal) n_kv = min(kv_len, q_rel0 + 128 + causal_off);
-  const int n_tiles = (n_kv + 127) >> 7;
+  const int n_tiles = (n_kv + BN - 1) / BN;
   const int hk = h / (p.Hq / p.Hkv);
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + TILE_BYTES;
-  uint8_t* sV = sK + KS * TILE_BYTES;
-  uint8_t* sP = sV + KS * TILE_BYTES;
+  uint8_t* sV = sK + KS * KV_BYTES;
+  uint8_t* sP = sV + KS * KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
   uint64_t* q_full = bars;            // 1
   uint64_t* k_full = bars + 1;        // KS
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
   }
-  if (warp == 1) tmem_alloc<AttnCfg<D>::TMEM_COLS>(tmem_slot);
+  if (warp == 1) tmem_alloc<AttnCfg<D, BN>::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -163,34 +167,35 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
       int st = 0;
       uint32_t ph = 0;
       for (int j = 0; j < n_tiles; ++j) {
-        const int row0 = kv_begin + j * 128;
+        const int row0 = kv_begin + j * BN;
         mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], TILE_BYTES);
+        mbar_expect_tx(&k_full[st], KV_BYTES);
 #pragma unroll
         for (int dc = 0; dc < DC; ++dc)
-          tma_load_rows(sK + st * TILE_BYTES + dc * 16384, &tmK, &k_full[st], p.k_pos, dc * 64, row0, hk, b);
+          tma_load_rows(sK + st * KV_BYTES + dc * KV_PANEL, &tmK, &k_full[st], p.k_pos, dc * 64, row0, hk, b);
         mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], TILE_BYTES);
+        mbar_expect_tx(&v_full[st], KV_BYTES);
 #pragma unroll
         for (int dc = 0; dc < DC; ++dc)
-          tma_load_rows(sV + st * TILE_BYTES + dc * 16384, &tmV, &v_full[st], p.v_pos, dc * 64, row0, hk, b);
+          tma_load_rows(sV + st * KV_BYTES + dc * KV_PANEL, &tmV, &v_full[st], p.v_pos, dc * 64, row0, hk, b);
         if (++st == KS) st = 0, ph ^= 1;
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);  // B (= V) is MN-major
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
       auto issue_qk = [&](int j, int st) {
-        const uint32_t k_addr = smem_u32(sK + st * TILE_BYTES);
-        const uint32_t d_tmem = tmem_base + TM_S + (j % SB) * 128;
+        const uint32_t k_addr = smem_u32(sK + st * KV_BYTES);
+        const uint32_t d_tmem = tmem_base + TM_S + (j % SB) * BN;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_bf16_ss(d_tmem, make_smem_desc_sw128(q_addr + off, 16, 1024),
-                       make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, k != 0 ? 1u : 0u);
+          const uint32_t q_off = (k >> 2) * 16384 + (k & 3) * 32;
+          const uint32_t k_off = (k >> 2) * KV_PANEL + (k & 3) * 32;
+          umma_bf16_ss(d_tmem, make_smem_desc_sw128(q_addr + q_off, 16, 1024),
+                       make_smem_desc_sw128(k_addr + k_off, 16, 1024), idesc_qk, k != 0 ? 1u : 0u);
         }
       };
       mbar_wait(q_full, 0);
@@ -217,11 +222,11 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
         mbar_wait(p_full, j & 1);
         mbar_wait(&v_full[vst], vph);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sV + vst * TILE_BYTES);
+        const uint32_t v_addr = smem_u32(sV + vst * KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < BN / 16; ++k) {
           const uint64_t ad = make_smem_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc_sw128(v_addr + k * 2048, 16384, 1024);
+          const uint64_t bd = make_smem_desc_sw128(v_addr + k * 2048, KV_PANEL, 1024);
           umma_bf16_ss(tmem_base + TM_O, ad, bd, idesc_pv, (j | k) != 0 ? 1u : 0u);
         }
         umma_commit(&v_empty[vst]);
@@ -242,25 +247,25 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[j % SB], (j / SB) & 1);
       tc_fence_after();
-      uint32_t sv[4][32];
+      uint32_t sv[BN / 32][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(lane_base + TM_S + (j % SB) * 128 + c * 32, sv[c]);
+      for (int c = 0; c < BN / 32; ++c) tmem_ld_32x32b_x32(lane_base + TM_S + (j % SB) * BN + c * 32, sv[c]);
       tmem_wait_ld();
       if (SB == 1) {
         tc_fence_before();
         mbar_arrive(s_empty);
       }
 
-      const int limit = min(kv_len, row_limit_base) - j * 128;  // columns [0, limit) of this tile are visible
+      const int limit = min(kv_len, row_limit_base) - j * BN;  // columns [0, limit) of this tile are visible
       float mx = -INFINITY;
-      if (limit >= 128) {
+      if (limit >= BN) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < BN / 32; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
       } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < BN / 32; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             float s = (c * 32 + i < limit) ? __uint_as_float(sv[c][i]) : -INFINITY;
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
       // expects (16-byte unit u of row r lives at u ^ (r & 7)); 8 columns at a time keeps the register footprint low
       float sum = 0.0f;
 #pragma unroll
-      for (int g8 = 0; g8 < 16; ++g8) {
+      for (int g8 = 0; g8 < BN / 8; ++g8) {
         uint32_t w[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -349,7 +354,7 @@ __global__ void __launch_bounds__(192, AttnCfg<D>::MIN_CTAS)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<AttnCfg<D>::TMEM_COLS>(tmem_base);
+    tmem_dealloc<AttnCfg<D, BN>::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -571,7 +576,7 @@ __global__ void __launch_bounds__(192, 2)
 // Build a 4-D tensor map over (d, seq, head, batch) for a [.., D]-contiguous bf16 tensor with arbitrary (16-byte
 // aligned) strides; outer dims are ordered by increasing stride. pos[] returns the coordinate slot of (seq, head, batch).
 static int make_attn_tmap(CUtensorMap* tm, const void* ptr, int64_t D, int64_t S, int64_t H, int64_t B, int64_t ss,
-                          int64_t sh, int64_t sb, int pos[3]) {
+                          int64_t sh, int64_t sb, int pos[3], uint32_t box_rows = 128) {
   struct Dim {
     int64_t size, stride;
     int which;
@@ -590,25 +595,32 @@ static int make_attn_tmap(CUtensorMap* tm, const void* ptr, int64_t D, int64_t S
     dims[i + 1] = (uint64_t)d[i].size;
     strides[i] = (uint64_t)d[i].stride * 2;
     pos[d[i].which] = i + 1;
-    if (d[i].which == 0) box[i + 1] = 128;
+    if (d[i].which == 0) box[i + 1] = box_rows;
   }
   return encode_tmap_bf16_sw128(tm, ptr, 4, dims, strides, box);
 }
 
-template <int D>
+template <int D, int BN>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        dim3 grid, cudaStream_t stream) {
-  constexpr int smem_bytes = AttnCfg<D>::SMEM;
+  constexpr int smem_bytes = AttnCfg<D, BN>::SMEM;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    B200_CUDA(cudaFuncSetAttribute(attn_kernel<D, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
-  B200_CUDA(launch_pdl(attn_kernel<D>, grid, dim3(192), smem_bytes, stream, 1, tq, tk, tv, p));
+  B200_CUDA(launch_pdl(attn_kernel<D, BN>, grid, dim3(192), smem_bytes, stream, 1, tq, tk, tv, p));
   return 0;
 }
 
 static int g_no_shortkv = 0;  // test hook: 1 = always use the general kernel
+#ifndef ATTN_BN64_DEFAULT
+#define ATTN_BN64_DEFAULT 0
+#endif
+// D = 64: 1 = 64-key blocks, 3 CTAs per SM; 0 (default) = 128-key blocks, 2 CTAs per SM. Measured (tools/attn_probe.py):
+// the third CTA does not pay for the halved block (twice the barrier round trips per key, 96 registers per thread):
+// 629 vs 680 TFLOP/s at S = 4096, 512 vs 517 at S = 1024. Kept selectable for A/B runs and tested.
+static int g_attn_bn64 = ATTN_BN64_DEFAULT;
 
 static int launch_attn_shortkv(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                                int B, cudaStream_t stream) {
@@ -629,6 +641,7 @@ static int launch_attn_shortkv(const CUtensorMap& tq, const CUtensorMap& tk, con
 using namespace b200;
 
 extern "C" void b200mix_debug_no_shortkv(int on) { b200::g_no_shortkv = on; }
+extern "C" void b200mix_debug_attn_bn64(int on) { b200::g_attn_bn64 = on; }
 
 extern "C" int b200mix_sdpa(const void* q, const void* k, const void* v, void* o, int64_t B, int64_t Hq, int64_t Hkv,
                             int64_t Sq, int64_t Sk, int64_t D, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t k_sb,
@@ -660,15 +673,18 @@ extern "C" int b200mix_sdpa(const void* q, const void* k, const void* v, void* o
   p.o_sb = o_sb, p.o_ss = o_ss, p.o_sh = o_sh;
   CUtensorMap tq, tk, tv;
   if (int rc = make_attn_tmap(&tq, q, D, Sq, Hq, B, q_ss, q_sh, q_sb, p.q_pos)) return rc;
-  if (int rc = make_attn_tmap(&tk, k, D, Sk, Hkv, B, k_ss, k_sh, k_sb, p.k_pos)) return rc;
-  if (int rc = make_attn_tmap(&tv, v, D, Sk, Hkv, B, v_ss, v_sh, v_sb, p.v_pos)) return rc;
+  // short-KV kernel: 128-key boxes; general kernel at D = 64: 128-key blocks unless the 64-key variant is switched on
+  const bool shortkv = D == 64 && !causal && !cu_seqlens && Sk <= 128 && !g_no_shortkv &&
+                       B * Hq * ((Sq + 127) / 128) < (1ll << 31);
+  const uint32_t kv_box = (D == 64 && !shortkv && g_attn_bn64) ? 64u : 128u;
+  if (int rc = make_attn_tmap(&tk, k, D, Sk, Hkv, B, k_ss, k_sh, k_sb, p.k_pos, kv_box)) return rc;
+  if (int rc = make_attn_tmap(&tv, v, D, Sk, Hkv, B, v_ss, v_sh, v_sb, p.v_pos, kv_box)) return rc;
   cudaStream_t st0 = reinterpret_cast<cudaStream_t>(stream);
-  if (D == 64 && !causal && !cu_seqlens && Sk <= 128 && !g_no_shortkv && B * Hq * ((Sq + 127) / 128) < (1ll << 31))
-    return launch_attn_shortkv(tq, tk, tv, p, (int)B, st0);
+  if (shortkv) return launch_attn_shortkv(tq, tk, tv, p, (int)B, st0);
   int64_t q_tiles = (Sq + 127) / 128 + (cu_seqlens ? nseq : 0);
   dim3 grid((unsigned)q_tiles, (unsigned)Hq, (unsigned)B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (D == 64) return launch_attn<64>(tq, tk, tv, p, grid, st);
-  if (D == 128) return launch_attn<128>(tq, tk, tv, p, grid, st);
-  return launch_attn<192>(tq, tk, tv, p, grid, st);
+  if (D == 64) return kv_box == 64 ? launch_attn<64, 64>(tq, tk, tv, p, grid, st) : launch_attn<64, 128>(tq, tk, tv, p, grid, st);
+  if (D == 128) return launch_attn<128, 128>(tq, tk, tv, p, grid, st);
+  return launch_attn<192, 128>(tq, tk, tv, p, grid, st);
 }

@@ -203,6 +203,19 @@ def test_sdpa_short_kv_persistent(ops, B, Sq, Sk, Hq, Hkv):
             close(out[b:b + 1], ref, ATT_ATOL, ATT_RTOL, f"short-kv B{B} Sq{Sq} Sk{Sk} H{Hq}/{Hkv} b{b} n{n}")
 
 
+@pytest.mark.parametrize("B,Sq,Sk,H,causal", [(2, 1024, 1024, 4, False), (1, 300, 450, 3, False), (1, 333, 333, 2, True)])
+def test_sdpa_d64_64_key_blocks(ops, B, Sq, Sk, H, causal):
+    """The D = 64 kernel with 64-key blocks (3 CTAs per SM; not the default, kept for A/B runs) against the fp32 reference."""
+    from paddlemix_b200._lib import lib
+    q, k, v = rnd(B, Sq, H, 64, seed=93), rnd(B, Sk, H, 64, seed=94), rnd(B, Sk, H, 64, seed=95)
+    lib.b200mix_debug_attn_bn64(1)
+    try:
+        out = ops.sdpa(q, k, v, causal=causal)
+    finally:
+        lib.b200mix_debug_attn_bn64(0)
+    close(out, ref_sdpa(q, k, v, 64 ** -0.5, causal), ATT_ATOL, ATT_RTOL, f"sdpa bn64 B{B} Sq{Sq} Sk{Sk} causal={causal}")
+
+
 def test_sdpa_large_logits(ops):
     # large |q.k| exercises the lazy-rescale path (running max grows by more than 2^8 between tiles)
     B, S, H, D = 1, 512, 2, 64
