@@ -52,14 +52,22 @@ __device__ __forceinline__ void tma_load_rows(void* dst, const CUtensorMap* m, u
 // double-buffered S so QK^T(j+1) overlaps softmax(j) inside the CTA.
 // BN = keys per K/V block. D = 64 with BN = 64 needs only 64 (S) + 64 (O) TMEM columns and 64 KB of shared memory, so
 // three CTAs could share an SM; measured slower than BN = 128 with two CTAs (see g_attn_bn64), so it is not the default.
+#ifndef ATTN_P_TMEM
+#define ATTN_P_TMEM 0  // measured (tools/attn_probe.py): 659 vs 680 TFLOP/s at S = 4096, 531 vs 524 at S = 1024 -> off
+#endif
 template <int D, int BN>
 struct AttnCfg {
   static constexpr int SB = (D == 64) ? 1 : 2;                      // S accumulator buffers in TMEM
   static constexpr int KS = (D == 192) ? 1 : 2;                     // K/V ring depth
-  static constexpr int TMEM_COLS = (D == 64) ? (BN == 64 ? 128 : 256) : 512;  // SB*BN (S) + D (O), power of 2
+  // Optional variant: P (bf16, two keys per 32-bit column) stays in TMEM and feeds the PV MMA as its A operand (no
+  // shared-memory round trip, half of exp(j) runs before PV(j-1) completes, 118 registers); S is then read from TMEM
+  // twice and released later, which costs more than it saves on long sequences. Parity-tested, not the default.
+  static constexpr bool P_TMEM = (BN == 128) && (ATTN_P_TMEM != 0);
+  // SB*BN (S) + BN/2 (P, if in TMEM) + D (O) <= 256 / 512 columns
+  static constexpr int TMEM_COLS = (D == 64) ? (BN == 64 ? 128 : 256) : 512;
   static constexpr int MIN_CTAS = (D == 64) ? (BN == 64 ? 3 : 2) : 1;
   // dynamic smem is declared __align__(1024) (128B-swizzle atoms), so no alignment slack
-  static constexpr int SMEM = 128 * D * 2 + 2 * KS * BN * D * 2 + 128 * BN * 2 + 256;
+  static constexpr int SMEM = 128 * D * 2 + 2 * KS * BN * D * 2 + (P_TMEM ? 0 : 128 * BN * 2) + 256;
 };
 
 template <int D, int BN>
@@ -72,8 +80,10 @@ __global__ void __launch_bounds__(192, AttnCfg<D, BN>::MIN_CTAS)
   constexpr int KV_PANEL = BN * 128;       // one 64-wide head-dim panel of it
   constexpr int KS = AttnCfg<D, BN>::KS;
   constexpr int SB = AttnCfg<D, BN>::SB;
-  constexpr int P_BYTES = 128 * BN * 2;
-  constexpr uint32_t TM_S = 0, TM_O = SB * BN;
+  constexpr bool PT = AttnCfg<D, BN>::P_TMEM;
+  constexpr int P_BYTES = PT ? 0 : 128 * BN * 2;
+  constexpr uint32_t TM_S = 0, TM_P = SB * BN, TM_O = TM_P + (PT ? BN / 2 : 0);
+  static_assert(TM_O + D <= AttnCfg<D, BN>::TMEM_COLS, "TMEM budget");
 
   // cu_seqlens / kv_lens are read right away: if they are given, wait for the previous kernel first
   if (p.cu || p.kv_lens) pdl_wait();
@@ -225,9 +235,13 @@ __global__ void __launch_bounds__(192, AttnCfg<D, BN>::MIN_CTAS)
         const uint32_t v_addr = smem_u32(sV + vst * KV_BYTES);
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k) {
-          const uint64_t ad = make_smem_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
           const uint64_t bd = make_smem_desc_sw128(v_addr + k * 2048, KV_PANEL, 1024);
-          umma_bf16_ss(tmem_base + TM_O, ad, bd, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          if (PT) {
+            umma_bf16_ts(tmem_base + TM_O, tmem_base + TM_P + k * 8, bd, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          } else {
+            const uint64_t ad = make_smem_desc_sw128(p_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+            umma_bf16_ss(tmem_base + TM_O, ad, bd, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&v_empty[vst]);
         umma_commit(pv_done);
@@ -244,6 +258,92 @@ __global__ void __launch_bounds__(192, AttnCfg<D, BN>::MIN_CTAS)
     uint8_t* p_row = sP + row * 128;
     const int sw = row & 7;
 
+    if constexpr (PT) {
+      // ---- P in TMEM: S is read from TMEM twice (row max, then exponentials) in 32-column chunks, the next chunk's
+      // load in flight while the current one is processed, so a thread holds 64 S values instead of 128 and the
+      // compiler has registers left to overlap the FFMA -> ex2 -> FADD chains. The packed P words go back to TMEM.
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&s_full[j % SB], (j / SB) & 1);
+        tc_fence_after();
+        const uint32_t s_addr = lane_base + TM_S + (j % SB) * BN;
+        const int limit = min(kv_len, row_limit_base) - j * BN;  // columns [0, limit) of this tile are visible
+        const bool full = limit >= BN;
+        uint32_t ch[2][32];
+        tmem_ld_32x32b_x32(s_addr, ch[0]);
+        tmem_wait_ld();
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          // next chunk (or chunk 0 again for the second pass) is fetched while this one is reduced
+          tmem_ld_32x32b_x32(s_addr + ((c + 1) & 3) * 32, ch[(c + 1) & 1]);
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(ch[c & 1][i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < limit) mx = fmaxf(mx, __uint_as_float(ch[c & 1][i]));
+          }
+          tmem_wait_ld();
+        }
+        const float m_cand = fmaxf(m, mx);
+        const bool grow = (m_cand - m) * p.scale_log2 > 8.0f;  // also true for the first finite tile (m = -inf)
+        float alpha = 1.0f;
+        if (grow) {
+          alpha = fast_exp2((m - m_cand) * p.scale_log2);
+          m = m_cand;
+          l *= alpha;
+        }
+        const float m_scaled = (m == -INFINITY) ? 0.0f : m * p.scale_log2;
+        float sum = 0.0f;
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < 3) tmem_ld_32x32b_x32(s_addr + (c + 1) * 32, ch[(c + 1) & 1]);
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            float s0 = __uint_as_float(ch[c & 1][2 * t]), s1 = __uint_as_float(ch[c & 1][2 * t + 1]);
+            if (!full) {
+              s0 = (c * 32 + 2 * t < limit) ? s0 : -INFINITY;
+              s1 = (c * 32 + 2 * t + 1 < limit) ? s1 : -INFINITY;
+            }
+            const float e0 = fast_exp2(fmaf(s0, p.scale_log2, -m_scaled));
+            const float e1 = fast_exp2(fmaf(s1, p.scale_log2, -m_scaled));
+            sum += e0 + e1;
+            pk[16 * (c & 1) + t] = pack_bf16x2(e0, e1);
+          }
+          if (c < 3) tmem_wait_ld();
+          if (c == 2 && SB == 1) {  // the last S chunk is in registers: QK^T of the next block may overwrite S
+            tc_fence_before();
+            mbar_arrive(s_empty);
+          }
+          if (c == 1 || c == 3) {
+            if (c == 1 && j > 0) {
+              // O and the P columns are free once PV_{j-1} has completed; the lazy rescale of O happens here too, i.e.
+              // AFTER half of this block's exponentials: they overlap the previous block's second MMA
+              mbar_wait(pv_done, (j - 1) & 1);
+              tc_fence_after();
+              if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+                for (int oc = 0; oc < D / 32; ++oc) {
+                  uint32_t o[32];
+                  tmem_ld_32x32b_x32(lane_base + TM_O + oc * 32, o);
+                  tmem_wait_ld();
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                  tmem_st_32x32b_x32(lane_base + TM_O + oc * 32, o);
+                }
+              }
+            }
+            tmem_st_32x32b_x32(lane_base + TM_P + (c >> 1) * 32, pk);
+          }
+        }
+        l += sum;
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(p_full);
+      }
+    } else {
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[j % SB], (j / SB) & 1);
       tc_fence_after();
@@ -300,9 +400,9 @@ __global__ void __launch_bounds__(192, AttnCfg<D, BN>::MIN_CTAS)
           tmem_wait_st();
         }
       }
+      float sum = 0.0f;
       // exponentiate (row sum in fp32), pack P to bf16 and stream it into the K-major SW128 layout the second MMA
       // expects (16-byte unit u of row r lives at u ^ (r & 7)); 8 columns at a time keeps the register footprint low
-      float sum = 0.0f;
 #pragma unroll
       for (int g8 = 0; g8 < BN / 8; ++g8) {
         uint32_t w[4];
@@ -321,6 +421,7 @@ __global__ void __launch_bounds__(192, AttnCfg<D, BN>::MIN_CTAS)
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
+    }
     }
 
     // ---- epilogue: O / l -> global ----
