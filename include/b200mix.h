@@ -174,6 +174,18 @@ int b200mix_euler_step(const void* v_u, const void* v_c, int32_t v_fp32, float g
  * host computes that denominator in fp32, this applies an IEEE fp32 division. */
 int b200mix_scale_model_input(const float* x, float* y, int64_t n, float denom, void* stream);
 
+/* DPMSolverMultistepScheduler.step for "dpmsolver++" / midpoint / epsilon prediction ("DPM-Solver++ 2M",
+ * scheduling_dpmsolver_multistep.py:801-873), fused with the CFG combine, fp32 state:
+ *   x0 = (x - sigma_cur*eps) / alpha_cur                                   (convert_model_output, :446-453)
+ *   m_prev == NULL: x_next = A*x - C*x0                                     (first order, :548-553)
+ *   else          : x_next = A*x - C*x0 - halfC*(inv_r0*(x0 - m_prev))      (second order midpoint, :633-640)
+ * m_out receives x0 (next step's m_prev). The scalars A = sigma_t/sigma_s0, C = alpha_t*(exp(-h) - 1), halfC = 0.5*C,
+ * inv_r0 = 1/r0 are computed on the host in fp32 like the reference's 0-d tensors; every operation is rounded
+ * individually in the reference's order. */
+int b200mix_dpmpp_2m_step(const void* eps_u, const void* eps_c, int32_t eps_fp32, float guidance, const float* x,
+                          const float* m_prev, float* x_next, float* m_out, int64_t n, float sigma_cur, float alpha_cur,
+                          float A, float C, float halfC, float inv_r0, void* stream);
+
 /* SD3 / DiT patchify: x NCHW [B,C,H,W] (fp32|bf16) -> rows [B*(H/p)*(W/p), C*p*p] bf16 with the column order
  * (c, ph, pw) of a flattened Conv2D weight [D,C,p,p] (PatchEmbed.proj, embeddings.py:143-150), and its inverse for
  * the output head: rows [B*h*w, p*p*C] in (ph, pw, c) order -> NCHW [B,C,h*p,w*p] (transformer_sd3.py:350-356). */

@@ -329,3 +329,199 @@ class EulerDiscreteScheduler:
         while sigma.ndim < original_samples.ndim:
             sigma = sigma.unsqueeze(-1)
         return original_samples + noise * sigma
+
+
+def log_f32(t):
+    """fp32 natural log, evaluated with numpy's float32 kernel so that the oracle and the product's host scheduler (numpy)
+    share one definition (a libm / SIMD kernel may differ from another in the last bit)."""
+    a = np.log(np.asarray(t.detach().numpy(), dtype=np.float32), dtype=np.float32)
+    return torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).reshape(t.shape)
+
+
+def exp_f32(t):
+    a = np.exp(np.asarray(t.detach().numpy(), dtype=np.float32), dtype=np.float32)
+    return torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).reshape(t.shape)
+
+
+class DPMSolverMultistepScheduler:
+    """ppdiffusers/schedulers/scheduling_dpmsolver_multistep.py:36-919, the deterministic solvers ("dpmsolver++" and
+    "dpmsolver", orders 1-2, midpoint / heun, epsilon / sample / v_prediction, Karras sigmas, Lu lambdas); the SDE variants
+    (they draw noise), order 3 and dynamic thresholding (a quantile) are not restated. fp32 torch tensors stand in for
+    paddle fp32 tensors. Pinned by the RNG-free goldens of tests/schedulers/test_scheduler_dpm_multi.py:229-284
+    (tests/golden/dpm_multistep_goldens.json)."""
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", solver_order=2,
+                 prediction_type="epsilon", thresholding=False, sample_max_value=1.0, algorithm_type="dpmsolver++",
+                 solver_type="midpoint", lower_order_final=True, euler_at_final=False, use_karras_sigmas=False,
+                 use_lu_lambdas=False, lambda_min_clipped=-float("inf"), variance_type=None, timestep_spacing="linspace",
+                 steps_offset=0):  # :147-218
+        if beta_schedule == "linear":
+            self.betas = linspace_f32(beta_start, beta_end, num_train_timesteps)
+        elif beta_schedule == "scaled_linear":
+            self.betas = linspace_f32(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps) ** 2
+        elif beta_schedule == "squaredcos_cap_v2":
+            self.betas = betas_for_alpha_bar(num_train_timesteps)
+        else:
+            raise NotImplementedError(f"{beta_schedule} does is not implemented for {self.__class__}")
+        if thresholding or algorithm_type not in ("dpmsolver++", "dpmsolver") or solver_order not in (1, 2) or variance_type:
+            raise NotImplementedError("oracle: deterministic dpmsolver(++) of order 1-2 without thresholding only")
+        if solver_type not in ("midpoint", "heun"):
+            raise NotImplementedError(f"{solver_type} does is not implemented for {self.__class__}")
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = cumprod_f32(self.alphas)
+        self.config = dict(num_train_timesteps=num_train_timesteps, solver_order=solver_order, prediction_type=prediction_type,
+                           algorithm_type=algorithm_type, solver_type=solver_type, lower_order_final=lower_order_final,
+                           euler_at_final=euler_at_final, use_karras_sigmas=use_karras_sigmas, use_lu_lambdas=use_lu_lambdas,
+                           lambda_min_clipped=lambda_min_clipped, timestep_spacing=timestep_spacing, steps_offset=steps_offset)
+        self.num_inference_steps = None
+        self.timesteps = torch.from_numpy(np.linspace(0, num_train_timesteps - 1, num_train_timesteps, dtype=np.float32)[::-1].copy())
+        self.model_outputs = [None] * solver_order
+        self.lower_order_nums = 0
+        self._step_index = None
+
+    def _lambda_t(self):  # :188-192
+        alpha_t, sigma_t = pow_half(self.alphas_cumprod), pow_half(1 - self.alphas_cumprod)
+        return log_f32(alpha_t) - log_f32(sigma_t)
+
+    def set_timesteps(self, num_inference_steps):  # :226-296
+        c = self.config
+        N = c["num_train_timesteps"]
+        if np.isinf(c["lambda_min_clipped"]):
+            clipped_idx = 0
+        else:
+            clipped_idx = int(np.searchsorted(np.flip(self._lambda_t().numpy()), np.float32(c["lambda_min_clipped"])))
+        last_timestep = N - clipped_idx
+        if c["timestep_spacing"] == "linspace":
+            timesteps = np.linspace(0, last_timestep - 1, num_inference_steps + 1).round()[::-1][:-1].copy().astype(np.int64)
+        elif c["timestep_spacing"] == "leading":
+            step_ratio = last_timestep // (num_inference_steps + 1)
+            timesteps = (np.arange(0, num_inference_steps + 1) * step_ratio).round()[::-1][:-1].copy().astype(np.int64)
+            timesteps += c["steps_offset"]
+        elif c["timestep_spacing"] == "trailing":
+            step_ratio = N / num_inference_steps
+            timesteps = np.arange(last_timestep, 0, -step_ratio).round().copy().astype(np.int64)
+            timesteps -= 1
+        else:
+            raise ValueError(f"{c['timestep_spacing']} is not supported.")
+        sigmas = pow_half((1 - self.alphas_cumprod) / self.alphas_cumprod).numpy()
+        log_sigmas = np.log(sigmas)
+        if c["use_karras_sigmas"]:
+            sigmas = np.flip(sigmas).copy()
+            smin, smax, rho = sigmas[-1].item(), sigmas[0].item(), 7.0
+            ramp = np.linspace(0, 1, num_inference_steps)
+            sigmas = (smax ** (1 / rho) + ramp * (smin ** (1 / rho) - smax ** (1 / rho))) ** rho
+            timesteps = np.array([EulerDiscreteScheduler._sigma_to_t(s, log_sigmas) for s in sigmas]).round()
+            sigmas = np.concatenate([sigmas, sigmas[-1:]]).astype(np.float32)
+        elif c["use_lu_lambdas"]:
+            lambdas = np.flip(log_sigmas.copy())
+            lmin, lmax = lambdas[-1].item(), lambdas[0].item()
+            ramp = np.linspace(0, 1, num_inference_steps)
+            lambdas = lmax + ramp * (lmin - lmax)  # rho = 1
+            sigmas = np.exp(lambdas)
+            timesteps = np.array([EulerDiscreteScheduler._sigma_to_t(s, log_sigmas) for s in sigmas]).round()
+            sigmas = np.concatenate([sigmas, sigmas[-1:]]).astype(np.float32)
+        else:
+            sigmas = np.interp(timesteps, np.arange(0, len(sigmas)), sigmas)
+            sigma_last = pow_half((1 - self.alphas_cumprod[0]) / self.alphas_cumprod[0]).item()
+            sigmas = np.concatenate([sigmas, [sigma_last]]).astype(np.float32)
+        self.sigmas = torch.from_numpy(sigmas)
+        self.timesteps = torch.from_numpy(np.asarray(timesteps).astype(np.int64))
+        self.num_inference_steps = len(timesteps)
+        self.model_outputs = [None] * c["solver_order"]
+        self.lower_order_nums = 0
+        self._step_index = None
+
+    @staticmethod
+    def _sigma_to_alpha_sigma_t(sigma):  # :362-366
+        alpha_t = 1 / pow_half(sigma ** 2 + 1)
+        return alpha_t, sigma * alpha_t
+
+    def scale_model_input(self, sample, *a, **k):
+        return sample
+
+    def _init_step_index(self, timestep):  # :785-799
+        cand = (self.timesteps == timestep).nonzero()
+        if len(cand) == 0:
+            self._step_index = len(self.timesteps) - 1
+        else:
+            self._step_index = (cand[1] if len(cand) > 1 else cand[0]).item()
+
+    def convert_model_output(self, model_output, sample):  # :408-505
+        c = self.config
+        sigma = self.sigmas[self._step_index]
+        alpha_t, sigma_t = self._sigma_to_alpha_sigma_t(sigma)
+        if c["algorithm_type"] == "dpmsolver++":
+            if c["prediction_type"] == "epsilon":
+                return (sample - sigma_t * model_output) / alpha_t
+            if c["prediction_type"] == "sample":
+                return model_output
+            if c["prediction_type"] == "v_prediction":
+                return alpha_t * sample - sigma_t * model_output
+        else:
+            if c["prediction_type"] == "epsilon":
+                return model_output
+            if c["prediction_type"] == "sample":
+                return (sample - alpha_t * model_output) / sigma_t
+            if c["prediction_type"] == "v_prediction":
+                return alpha_t * model_output + sigma_t * sample
+        raise ValueError(f"prediction_type given as {c['prediction_type']} must be one of `epsilon`, `sample`, or `v_prediction`")
+
+    def _lambdas(self, *idx):
+        out = []
+        for i in idx:
+            a, s = self._sigma_to_alpha_sigma_t(self.sigmas[i])
+            out.append((a, s, log_f32(a) - log_f32(s)))
+        return out
+
+    def first_order_update(self, m0, sample):  # :507-580
+        (alpha_t, sigma_t, lam_t), (alpha_s, sigma_s, lam_s) = self._lambdas(self._step_index + 1, self._step_index)
+        h = lam_t - lam_s
+        if self.config["algorithm_type"] == "dpmsolver++":
+            return (sigma_t / sigma_s) * sample - (alpha_t * (exp_f32(-h) - 1.0)) * m0
+        return (alpha_t / alpha_s) * sample - (sigma_t * (exp_f32(h) - 1.0)) * m0
+
+    def second_order_update(self, outs, sample):  # :582-700
+        (alpha_t, sigma_t, lam_t), (alpha_s0, sigma_s0, lam_s0), (_, _, lam_s1) = self._lambdas(
+            self._step_index + 1, self._step_index, self._step_index - 1)
+        m0, m1 = outs[-1], outs[-2]
+        h, h_0 = lam_t - lam_s0, lam_s0 - lam_s1
+        r0 = h_0 / h
+        D0, D1 = m0, (1.0 / r0) * (m0 - m1)
+        pp, mid = self.config["algorithm_type"] == "dpmsolver++", self.config["solver_type"] == "midpoint"
+        if pp and mid:
+            return (sigma_t / sigma_s0) * sample - (alpha_t * (exp_f32(-h) - 1.0)) * D0 - 0.5 * (alpha_t * (exp_f32(-h) - 1.0)) * D1
+        if pp:
+            return (sigma_t / sigma_s0) * sample - (alpha_t * (exp_f32(-h) - 1.0)) * D0 + (alpha_t * ((exp_f32(-h) - 1.0) / h + 1.0)) * D1
+        if mid:
+            return (alpha_t / alpha_s0) * sample - (sigma_t * (exp_f32(h) - 1.0)) * D0 - 0.5 * (sigma_t * (exp_f32(h) - 1.0)) * D1
+        return (alpha_t / alpha_s0) * sample - (sigma_t * (exp_f32(h) - 1.0)) * D0 - (sigma_t * ((exp_f32(h) - 1.0) / h - 1.0)) * D1
+
+    def step(self, model_output, timestep, sample):  # :801-873
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        c, n = self.config, len(self.timesteps)
+        lower_order_final = (self._step_index == n - 1) and (c["euler_at_final"] or (c["lower_order_final"] and n < 15))
+        m = self.convert_model_output(model_output, sample)
+        for i in range(c["solver_order"] - 1):
+            self.model_outputs[i] = self.model_outputs[i + 1]
+        self.model_outputs[-1] = m
+        if c["solver_order"] == 1 or self.lower_order_nums < 1 or lower_order_final:
+            prev = self.first_order_update(m, sample)
+        else:
+            prev = self.second_order_update(self.model_outputs, sample)
+        if self.lower_order_nums < c["solver_order"]:
+            self.lower_order_nums += 1
+        self._step_index += 1
+        return prev
+
+    def add_noise(self, original_samples, noise, timesteps):  # :893-916
+        idx = [(self.timesteps == t).nonzero().item() for t in timesteps]
+        sigma = self.sigmas[idx].flatten()
+        while sigma.ndim < original_samples.ndim:
+            sigma = sigma.unsqueeze(-1)
+        alpha_t, sigma_t = self._sigma_to_alpha_sigma_t(sigma)
+        return alpha_t * original_samples + sigma_t * noise

@@ -70,6 +70,8 @@ SIGNATURES = {
     "b200mix_euler_step": [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_int64, c_float, c_float,
                            c_void_p],
     "b200mix_scale_model_input": [c_void_p, c_void_p, c_int64, c_float, c_void_p],
+    "b200mix_dpmpp_2m_step": [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float,
+                              c_float, c_float, c_float, c_float, c_float, c_void_p],
     "b200mix_gather_rows": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p],
     "b200mix_scatter_rows": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p],
     "b200mix_broadcast_add": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],
@@ -99,6 +101,8 @@ def _load():
         getattr(lib, name).argtypes = []
     lib.b200mix_debug_force_bn.argtypes = [c_int]
     lib.b200mix_debug_force_bn.restype = None
+    lib.b200mix_debug_attn_ptmem.argtypes = [c_int]
+    lib.b200mix_debug_attn_ptmem.restype = None
     lib.b200mix_debug_attn_bn64.argtypes = [c_int]
     lib.b200mix_debug_attn_bn64.restype = None
     lib.b200mix_debug_no_shortkv.argtypes = [c_int]

@@ -52,17 +52,15 @@ __device__ __forceinline__ void tma_load_rows(void* dst, const CUtensorMap* m, u
 // double-buffered S so QK^T(j+1) overlaps softmax(j) inside the CTA.
 // BN = keys per K/V block. D = 64 with BN = 64 needs only 64 (S) + 64 (O) TMEM columns and 64 KB of shared memory, so
 // three CTAs could share an SM; measured slower than BN = 128 with two CTAs (see g_attn_bn64), so it is not the default.
-#ifndef ATTN_P_TMEM
-#define ATTN_P_TMEM 0  // measured (tools/attn_probe.py): 659 vs 680 TFLOP/s at S = 4096, 531 vs 524 at S = 1024 -> off
-#endif
-template <int D, int BN>
+template <int D, int BN, bool PTM = false>
 struct AttnCfg {
   static constexpr int SB = (D == 64) ? 1 : 2;                      // S accumulator buffers in TMEM
   static constexpr int KS = (D == 192) ? 1 : 2;                     // K/V ring depth
   // Optional variant: P (bf16, two keys per 32-bit column) stays in TMEM and feeds the PV MMA as its A operand (no
   // shared-memory round trip, half of exp(j) runs before PV(j-1) completes, 118 registers); S is then read from TMEM
   // twice and released later, which costs more than it saves on long sequences. Parity-tested, not the default.
-  static constexpr bool P_TMEM = (BN == 128) && (ATTN_P_TMEM != 0);
+  // (b200mix_debug_attn_ptmem; measured with tools/attn_probe.py: 659 vs 680 TFLOP/s at S = 4096, 531 vs 524 at S = 1024)
+  static constexpr bool P_TMEM = PTM && (BN == 128);
   // SB*BN (S) + BN/2 (P, if in TMEM) + D (O) <= 256 / 512 columns
   static constexpr int TMEM_COLS = (D == 64) ? (BN == 64 ? 128 : 256) : 512;
   static constexpr int MIN_CTAS = (D == 64) ? (BN == 64 ? 3 : 2) : 1;
@@ -70,20 +68,20 @@ struct AttnCfg {
   static constexpr int SMEM = 128 * D * 2 + 2 * KS * BN * D * 2 + (P_TMEM ? 0 : 128 * BN * 2) + 256;
 };
 
-template <int D, int BN>
-__global__ void __launch_bounds__(192, AttnCfg<D, BN>::MIN_CTAS)
+template <int D, int BN, bool PTM>
+__global__ void __launch_bounds__(192, AttnCfg<D, BN, PTM>::MIN_CTAS)
     attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
   constexpr int DC = D / 64;               // 64-wide head-dim chunks (one 128B swizzle atom each)
   constexpr int TILE_BYTES = 128 * D * 2;  // the 128-row Q tile
   constexpr int KV_BYTES = BN * D * 2;     // one BN-row tile of K / V
   constexpr int KV_PANEL = BN * 128;       // one 64-wide head-dim panel of it
-  constexpr int KS = AttnCfg<D, BN>::KS;
-  constexpr int SB = AttnCfg<D, BN>::SB;
-  constexpr bool PT = AttnCfg<D, BN>::P_TMEM;
+  constexpr int KS = AttnCfg<D, BN, PTM>::KS;
+  constexpr int SB = AttnCfg<D, BN, PTM>::SB;
+  constexpr bool PT = AttnCfg<D, BN, PTM>::P_TMEM;
   constexpr int P_BYTES = PT ? 0 : 128 * BN * 2;
   constexpr uint32_t TM_S = 0, TM_P = SB * BN, TM_O = TM_P + (PT ? BN / 2 : 0);
-  static_assert(TM_O + D <= AttnCfg<D, BN>::TMEM_COLS, "TMEM budget");
+  static_assert(TM_O + D <= AttnCfg<D, BN, PTM>::TMEM_COLS, "TMEM budget");
 
   // cu_seqlens / kv_lens are read right away: if they are given, wait for the previous kernel first
   if (p.cu || p.kv_lens) pdl_wait();
@@ -160,7 +158,7 @@ __global__ void __launch_bounds__(192, AttnCfg<D, BN>::MIN_CTAS)
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
   }
-  if (warp == 1) tmem_alloc<AttnCfg<D, BN>::TMEM_COLS>(tmem_slot);
+  if (warp == 1) tmem_alloc<AttnCfg<D, BN, PTM>::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -455,7 +453,7 @@ __global__ void __launch_bounds__(192, AttnCfg<D, BN>::MIN_CTAS)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<AttnCfg<D, BN>::TMEM_COLS>(tmem_base);
+    tmem_dealloc<AttnCfg<D, BN, PTM>::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -701,16 +699,16 @@ static int make_attn_tmap(CUtensorMap* tm, const void* ptr, int64_t D, int64_t S
   return encode_tmap_bf16_sw128(tm, ptr, 4, dims, strides, box);
 }
 
-template <int D, int BN>
+template <int D, int BN, bool PTM = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        dim3 grid, cudaStream_t stream) {
-  constexpr int smem_bytes = AttnCfg<D, BN>::SMEM;
+  constexpr int smem_bytes = AttnCfg<D, BN, PTM>::SMEM;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(attn_kernel<D, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    B200_CUDA(cudaFuncSetAttribute(attn_kernel<D, BN, PTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
-  B200_CUDA(launch_pdl(attn_kernel<D, BN>, grid, dim3(192), smem_bytes, stream, 1, tq, tk, tv, p));
+  B200_CUDA(launch_pdl(attn_kernel<D, BN, PTM>, grid, dim3(192), smem_bytes, stream, 1, tq, tk, tv, p));
   return 0;
 }
 
@@ -722,6 +720,7 @@ static int g_no_shortkv = 0;  // test hook: 1 = always use the general kernel
 // the third CTA does not pay for the halved block (twice the barrier round trips per key, 96 registers per thread):
 // 629 vs 680 TFLOP/s at S = 4096, 512 vs 517 at S = 1024. Kept selectable for A/B runs and tested.
 static int g_attn_bn64 = ATTN_BN64_DEFAULT;
+static int g_attn_ptmem = 0;  // D = 64: 1 = keep P in TMEM (A operand of the PV MMA); measured slower on long sequences
 
 static int launch_attn_shortkv(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                                int B, cudaStream_t stream) {
@@ -743,6 +742,7 @@ using namespace b200;
 
 extern "C" void b200mix_debug_no_shortkv(int on) { b200::g_no_shortkv = on; }
 extern "C" void b200mix_debug_attn_bn64(int on) { b200::g_attn_bn64 = on; }
+extern "C" void b200mix_debug_attn_ptmem(int on) { b200::g_attn_ptmem = on; }
 
 extern "C" int b200mix_sdpa(const void* q, const void* k, const void* v, void* o, int64_t B, int64_t Hq, int64_t Hkv,
                             int64_t Sq, int64_t Sk, int64_t D, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t k_sb,
@@ -785,7 +785,10 @@ extern "C" int b200mix_sdpa(const void* q, const void* k, const void* v, void* o
   int64_t q_tiles = (Sq + 127) / 128 + (cu_seqlens ? nseq : 0);
   dim3 grid((unsigned)q_tiles, (unsigned)Hq, (unsigned)B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (D == 64) return kv_box == 64 ? launch_attn<64, 64>(tq, tk, tv, p, grid, st) : launch_attn<64, 128>(tq, tk, tv, p, grid, st);
+  if (D == 64) {
+    if (kv_box == 64) return launch_attn<64, 64>(tq, tk, tv, p, grid, st);
+    return g_attn_ptmem ? launch_attn<64, 128, true>(tq, tk, tv, p, grid, st) : launch_attn<64, 128>(tq, tk, tv, p, grid, st);
+  }
   if (D == 128) return launch_attn<128, 128>(tq, tk, tv, p, grid, st);
   return launch_attn<192, 128>(tq, tk, tv, p, grid, st);
 }

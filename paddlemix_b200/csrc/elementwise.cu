@@ -493,6 +493,41 @@ extern "C" int b200mix_euler_step(const void* v_u, const void* v_c, int32_t v_fp
   return 0;
 }
 
+// DPM-Solver++ (2M) step, scheduling_dpmsolver_multistep.py:446-453 (x0 from epsilon), :548-553 (first order) and
+// :633-640 (second order, midpoint), every operation individually rounded in the reference's order.
+__global__ void dpmpp_2m_step_kernel(const void* __restrict__ eps_u, const void* __restrict__ eps_c, int eps_fp32,
+                                     float guidance, const float* __restrict__ x, const float* __restrict__ m_prev,
+                                     float* __restrict__ x_next, float* __restrict__ m_out, long long n, float sigma_cur,
+                                     float alpha_cur, float A, float C, float halfC, float inv_r0) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float e = load_any(eps_u, i, eps_fp32);
+    if (eps_c) {
+      const float ec = load_any(eps_c, i, eps_fp32);
+      e = __fadd_rn(e, __fmul_rn(guidance, __fsub_rn(ec, e)));
+    }
+    const float xv = x[i];
+    const float m0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(sigma_cur, e)), alpha_cur);
+    float r = __fsub_rn(__fmul_rn(A, xv), __fmul_rn(C, m0));
+    if (m_prev) {
+      const float d1 = __fmul_rn(inv_r0, __fsub_rn(m0, m_prev[i]));
+      r = __fsub_rn(r, __fmul_rn(halfC, d1));
+    }
+    m_out[i] = m0;
+    x_next[i] = r;
+  }
+}
+
+extern "C" int b200mix_dpmpp_2m_step(const void* eps_u, const void* eps_c, int32_t eps_fp32, float guidance, const float* x,
+                                     const float* m_prev, float* x_next, float* m_out, int64_t n, float sigma_cur,
+                                     float alpha_cur, float A, float C, float halfC, float inv_r0, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(eps_u && x && x_next && m_out && n > 0 && alpha_cur != 0.0f, "dpmpp_2m_step: bad arguments");
+  dpmpp_2m_step_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(eps_u, eps_c, eps_fp32, guidance, x, m_prev, x_next, m_out, n,
+                                                               sigma_cur, alpha_cur, A, C, halfC, inv_r0);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int b200mix_scale_model_input(const float* x, float* y, int64_t n, float denom, void* stream) {
   if (int rc = ensure_device()) return rc;
   B200_CHECK_ARG(x && y && n > 0 && denom > 0.0f, "scale_model_input: bad arguments");

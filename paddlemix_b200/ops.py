@@ -368,6 +368,18 @@ def euler_step(v_u, v_c, guidance, x, sigma, dt, out=None):
     return out
 
 
+def dpmpp_2m_step(eps_u, eps_c, guidance, x, m_prev, m_out, sigma_cur, alpha_cur, A, C, halfC, inv_r0, out=None):
+    """DPM-Solver++ 2M update (see include/b200mix.h); m_prev None = first-order step; m_out receives x0."""
+    _req(x, torch.float32, "x"), _req(m_out, torch.float32, "m_out")
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.b200mix_dpmpp_2m_step(_p(eps_u), _p(eps_c), 1 if eps_u.dtype == torch.float32 else 0, float(guidance), _p(x),
+                                    _p(m_prev), _p(out), _p(m_out), x.numel(), float(sigma_cur), float(alpha_cur), float(A),
+                                    float(C), float(halfC), float(inv_r0), _stream()), "b200mix_dpmpp_2m_step")
+    _count()
+    return out
+
+
 def scale_model_input(x: torch.Tensor, denom: float, out=None) -> torch.Tensor:
     """EulerDiscreteScheduler.scale_model_input: x / denom in fp32 (IEEE division)."""
     _req(x, torch.float32, "x")

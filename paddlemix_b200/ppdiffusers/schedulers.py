@@ -302,3 +302,147 @@ class EulerDiscreteScheduler:
         """sigma of `timestep`: add_noise is original + noise * sigma (scheduling_euler_discrete.py:472-497)."""
         idx = np.nonzero(self.timesteps == f32(timestep))[0]
         return float(self.sigmas[int(idx[0])])
+
+
+class DPMSolverMultistepScheduler:
+    """ppdiffusers.DPMSolverMultistepScheduler (scheduling_dpmsolver_multistep.py:36-919) restricted to what has a device
+    step: algorithm "dpmsolver++", solver_type "midpoint", order 1 or 2, epsilon prediction (the "DPM-Solver++ 2M"
+    sampler of SD / SDXL), incl. Karras sigmas / Lu lambdas, lower_order_final, euler_at_final. The schedule and the
+    per-step scalars are computed on the host in numpy with the reference's dtypes; `step` runs ONE fused kernel
+    (`b200mix_dpmpp_2m_step`): CFG combine, x0 = (x - sigma_t*eps)/alpha_t, the first / second order update in the
+    reference's operation order, and the x0 history for the next step (kept on the device)."""
+
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.0001, beta_end: float = 0.02,
+                 beta_schedule: str = "linear", solver_order: int = 2, prediction_type: str = "epsilon",
+                 thresholding: bool = False, sample_max_value: float = 1.0, algorithm_type: str = "dpmsolver++",
+                 solver_type: str = "midpoint", lower_order_final: bool = True, euler_at_final: bool = False,
+                 use_karras_sigmas: bool = False, use_lu_lambdas: bool = False, lambda_min_clipped: float = -float("inf"),
+                 variance_type: Optional[str] = None, timestep_spacing: str = "linspace", steps_offset: int = 0):
+        if beta_schedule == "linear":
+            self.betas = _linspace_f32(beta_start, beta_end, num_train_timesteps)
+        elif beta_schedule == "scaled_linear":
+            self.betas = _linspace_f32(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps) ** 2
+        elif beta_schedule == "squaredcos_cap_v2":
+            self.betas = _betas_for_alpha_bar(num_train_timesteps)
+        else:
+            raise NotImplementedError(f"{beta_schedule} does is not implemented for {self.__class__}")
+        if (algorithm_type != "dpmsolver++" or solver_type != "midpoint" or solver_order not in (1, 2) or thresholding or
+                prediction_type != "epsilon" or variance_type):
+            raise NotImplementedError("DPMSolverMultistepScheduler(b200): the device step covers dpmsolver++ / midpoint / "
+                                      "order 1-2 / epsilon prediction without thresholding")
+        self.alphas = (f32(1.0) - self.betas).astype(f32)
+        self.alphas_cumprod = _cumprod_f32(self.alphas)
+        self.num_train_timesteps, self.solver_order = num_train_timesteps, solver_order
+        self.lower_order_final, self.euler_at_final = lower_order_final, euler_at_final
+        self.use_karras_sigmas, self.use_lu_lambdas = use_karras_sigmas, use_lu_lambdas
+        self.lambda_min_clipped = lambda_min_clipped
+        self.timestep_spacing, self.steps_offset = timestep_spacing, steps_offset
+        self.num_inference_steps: Optional[int] = None
+        self.timesteps = np.linspace(0, num_train_timesteps - 1, num_train_timesteps, dtype=f32)[::-1].copy()
+        self.lower_order_nums = 0
+        self._step_index: Optional[int] = None
+        self._m_prev = None  # x0 prediction of the previous step (device fp32)
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def set_timesteps(self, num_inference_steps: int):
+        N = self.num_train_timesteps
+        ac = self.alphas_cumprod
+        if np.isinf(self.lambda_min_clipped):
+            clipped_idx = 0
+        else:
+            lam = np.log(np.sqrt(ac, dtype=f32), dtype=f32) - np.log(np.sqrt((f32(1.0) - ac).astype(f32), dtype=f32), dtype=f32)
+            clipped_idx = int(np.searchsorted(np.flip(lam), f32(self.lambda_min_clipped)))
+        last_timestep = N - clipped_idx
+        if self.timestep_spacing == "linspace":
+            timesteps = np.linspace(0, last_timestep - 1, num_inference_steps + 1).round()[::-1][:-1].copy().astype(np.int64)
+        elif self.timestep_spacing == "leading":
+            step_ratio = last_timestep // (num_inference_steps + 1)
+            timesteps = (np.arange(0, num_inference_steps + 1) * step_ratio).round()[::-1][:-1].copy().astype(np.int64)
+            timesteps += self.steps_offset
+        elif self.timestep_spacing == "trailing":
+            step_ratio = N / num_inference_steps
+            timesteps = np.arange(last_timestep, 0, -step_ratio).round().copy().astype(np.int64)
+            timesteps -= 1
+        else:
+            raise ValueError(f"{self.timestep_spacing} is not supported. Please make sure to choose one of 'linspace', "
+                             "'leading' or 'trailing'.")
+        sigmas = np.sqrt(((f32(1.0) - ac) / ac).astype(f32), dtype=f32)
+        log_sigmas = np.log(sigmas)
+        if self.use_karras_sigmas:
+            sigmas = np.flip(sigmas).copy()
+            smin, smax, rho = sigmas[-1].item(), sigmas[0].item(), 7.0
+            ramp = np.linspace(0, 1, num_inference_steps)
+            sigmas = (smax ** (1 / rho) + ramp * (smin ** (1 / rho) - smax ** (1 / rho))) ** rho
+            timesteps = np.array([EulerDiscreteScheduler._sigma_to_t(s, log_sigmas) for s in sigmas]).round()
+            sigmas = np.concatenate([sigmas, sigmas[-1:]]).astype(f32)
+        elif self.use_lu_lambdas:
+            lambdas = np.flip(log_sigmas.copy())
+            lmin, lmax = lambdas[-1].item(), lambdas[0].item()
+            ramp = np.linspace(0, 1, num_inference_steps)
+            sigmas = np.exp(lmax + ramp * (lmin - lmax))
+            timesteps = np.array([EulerDiscreteScheduler._sigma_to_t(s, log_sigmas) for s in sigmas]).round()
+            sigmas = np.concatenate([sigmas, sigmas[-1:]]).astype(f32)
+        else:
+            sigmas = np.interp(timesteps, np.arange(0, len(sigmas)), sigmas)
+            sigma_last = np.sqrt(f32((f32(1.0) - ac[0]) / ac[0]), dtype=f32)
+            sigmas = np.concatenate([sigmas, [sigma_last]]).astype(f32)
+        self.sigmas = sigmas
+        self.timesteps = np.asarray(timesteps).astype(np.int64)
+        self.num_inference_steps = len(timesteps)
+        self.lower_order_nums = 0
+        self._step_index = None
+        self._m_prev = None
+
+    @staticmethod
+    def _alpha_sigma_lambda(sigma):
+        """_sigma_to_alpha_sigma_t (:362-366) + lambda = log(alpha) - log(sigma), all fp32."""
+        sigma = f32(sigma)
+        alpha_t = f32(f32(1.0) / np.sqrt(f32(f32(sigma * sigma) + f32(1.0)), dtype=f32))
+        sigma_t = f32(sigma * alpha_t)
+        return alpha_t, sigma_t, f32(np.log(alpha_t, dtype=f32) - np.log(sigma_t, dtype=f32))
+
+    def step_scalars(self, timestep):
+        """(order, sigma_cur, alpha_cur, A, C, halfC, inv_r0): x0 = (x - sigma_cur*eps)/alpha_cur;
+        order 1: x' = A*x - C*x0; order 2: x' = A*x - C*x0 - halfC*(inv_r0*(x0 - x0_prev))."""
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
+        if self._step_index is None:
+            cand = np.nonzero(self.timesteps == int(timestep))[0]
+            self._step_index = len(self.timesteps) - 1 if len(cand) == 0 else int(cand[1] if len(cand) > 1 else cand[0])
+        i, n = self._step_index, len(self.timesteps)
+        lower_order_final = (i == n - 1) and (self.euler_at_final or (self.lower_order_final and n < 15))
+        alpha_s0, sigma_s0, lam_s0 = self._alpha_sigma_lambda(self.sigmas[i])
+        alpha_t, sigma_t, lam_t = self._alpha_sigma_lambda(self.sigmas[i + 1])
+        h = f32(lam_t - lam_s0)
+        A = f32(sigma_t / sigma_s0)
+        C = f32(alpha_t * f32(np.exp(f32(-h), dtype=f32) - f32(1.0)))
+        first = self.solver_order == 1 or self.lower_order_nums < 1 or lower_order_final
+        inv_r0 = f32(0.0)
+        if not first:
+            _, _, lam_s1 = self._alpha_sigma_lambda(self.sigmas[i - 1])
+            # Karras / Lu schedules repeat the last sigma: h == 0 there, r0 = inf, 1/r0 = 0 and C = 0 (x' = x), exactly
+            # like the reference's 0-d tensor arithmetic
+            with np.errstate(divide="ignore", invalid="ignore"):
+                r0 = f32(f32(lam_s0 - lam_s1) / h)
+                inv_r0 = f32(f32(1.0) / r0)
+        if self.lower_order_nums < self.solver_order:
+            self.lower_order_nums += 1
+        self._step_index += 1
+        return (1 if first else 2, float(sigma_s0), float(alpha_s0), float(A), float(C), float(f32(f32(0.5) * C)), float(inv_r0))
+
+    def step(self, model_output, timestep, sample, model_output_cond=None, guidance_scale=0.0, out=None):
+        from .. import ops
+        order, sigma_cur, alpha_cur, A, C, halfC, inv_r0 = self.step_scalars(timestep)
+        if self._m_prev is None:
+            import torch
+            self._m_prev = [torch.empty_like(sample), torch.empty_like(sample)]
+            self._m_slot = 0
+        m_out, m_prev = self._m_prev[self._m_slot], self._m_prev[self._m_slot ^ 1]
+        self._m_slot ^= 1
+        return ops.dpmpp_2m_step(model_output, model_output_cond, guidance_scale, sample, m_prev if order == 2 else None,
+                                 m_out, sigma_cur, alpha_cur, A, C, halfC, inv_r0, out=out)

@@ -39,6 +39,21 @@ euler = {  # ppdiffusers/tests/schedulers/test_scheduler_euler.py:25-33 (config)
     "full_loop_with_noise": {"t_start": 8, "sum": 57062.9023, "mean": 74.3007},
     "sum_atol": 1e-2, "mean_atol": 1e-3,
 }
+dpm = {  # ppdiffusers/tests/schedulers/test_scheduler_dpm_multi.py:33-52 (config), :116-131 (full_loop), :229-284
+    "config": {"num_train_timesteps": 1000, "beta_start": 0.0001, "beta_end": 0.02, "beta_schedule": "linear", "solver_order": 2,
+               "prediction_type": "epsilon", "algorithm_type": "dpmsolver++", "solver_type": "midpoint",
+               "lower_order_final": False, "euler_at_final": False},
+    "num_inference_steps": 10,
+    "full_loop": [
+        {"config": {}, "mean": 0.3301},
+        {"config": {"prediction_type": "v_prediction"}, "mean": 0.2251},
+        {"config": {"prediction_type": "v_prediction", "use_karras_sigmas": True}, "mean": 0.2096},
+        {"config": {"prediction_type": "v_prediction", "use_lu_lambdas": True}, "mean": 0.1554},
+    ],
+    "full_loop_with_noise": {"t_start": 5, "sum": 318.4111, "mean": 0.4146},
+    "sum_atol": 1e-2, "mean_atol": 1e-3,
+}
+json.dump(dpm, open(os.path.join(HERE, "dpm_multistep_goldens.json"), "w"), indent=1)
 json.dump(euler, open(os.path.join(HERE, "euler_goldens.json"), "w"), indent=1)
 json.dump(ddim, open(os.path.join(HERE, "ddim_goldens.json"), "w"), indent=1)
 json.dump(sinus, open(os.path.join(HERE, "sinusoid_goldens.json"), "w"), indent=1)

@@ -216,6 +216,21 @@ def test_sdpa_d64_64_key_blocks(ops, B, Sq, Sk, H, causal):
     close(out, ref_sdpa(q, k, v, 64 ** -0.5, causal), ATT_ATOL, ATT_RTOL, f"sdpa bn64 B{B} Sq{Sq} Sk{Sk} causal={causal}")
 
 
+@pytest.mark.parametrize("B,Sq,Sk,H,causal,scale", [(2, 1024, 1024, 4, False, 1.0), (1, 300, 450, 3, False, 1.0),
+                                                      (1, 333, 333, 2, True, 1.0), (1, 512, 512, 2, False, 4.0)])
+def test_sdpa_d64_p_in_tmem(ops, B, Sq, Sk, H, causal, scale):
+    """The D = 64 kernel variant that keeps P in TMEM (tcgen05.mma with the A operand in TMEM; not the default, kept
+    for A/B runs) against the fp32 reference, incl. masked tiles and the lazy-rescale path (large logits)."""
+    from paddlemix_b200._lib import lib
+    q, k, v = rnd(B, Sq, H, 64, seed=96, scale=scale), rnd(B, Sk, H, 64, seed=97, scale=scale), rnd(B, Sk, H, 64, seed=98)
+    lib.b200mix_debug_attn_ptmem(1)
+    try:
+        out = ops.sdpa(q, k, v, causal=causal)
+    finally:
+        lib.b200mix_debug_attn_ptmem(0)
+    close(out, ref_sdpa(q, k, v, 64 ** -0.5, causal), ATT_ATOL, ATT_RTOL, f"sdpa P-in-TMEM B{B} Sq{Sq} Sk{Sk} causal={causal}")
+
+
 def test_sdpa_large_logits(ops):
     # large |q.k| exercises the lazy-rescale path (running max grows by more than 2^8 between tiles)
     B, S, H, D = 1, 512, 2, 64

@@ -7,13 +7,14 @@ import os
 import numpy as np
 import torch
 
-from oracle.schedulers import DDIMScheduler, EulerDiscreteScheduler
+from oracle.schedulers import DDIMScheduler, DPMSolverMultistepScheduler, EulerDiscreteScheduler
 from oracle.unet import get_timestep_embedding
 
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 DDIM_GOLD = json.load(open(os.path.join(GOLD, "ddim_goldens.json")))
 SIN_GOLD = json.load(open(os.path.join(GOLD, "sinusoid_goldens.json")))
+DPM_GOLD = json.load(open(os.path.join(GOLD, "dpm_multistep_goldens.json")))
 EULER_GOLD = json.load(open(os.path.join(GOLD, "euler_goldens.json")))
 
 
@@ -107,6 +108,25 @@ def test_euler_full_loop_with_noise_golden():  # :163-195
     sample = euler_loop(sch, sample, timesteps)
     assert abs(sample.abs().mean().item() - g["mean"]) < EULER_GOLD["mean_atol"]
     assert abs(sample.abs().sum().item() - g["sum"]) < 2e-6 * g["sum"]
+
+
+def test_dpm_multistep_goldens():  # test_scheduler_dpm_multi.py:116-131, 229-284 (DPM-Solver++ 2M; v-pred; Karras; Lu)
+    for case in DPM_GOLD["full_loop"]:
+        sch = DPMSolverMultistepScheduler(**{**DPM_GOLD["config"], **case["config"]})
+        sch.set_timesteps(DPM_GOLD["num_inference_steps"])
+        x = dummy_sample_deter()
+        for t in sch.timesteps:
+            x = sch.step(dummy_model(x, t), t, x)
+        assert abs(x.abs().mean().item() - case["mean"]) < DPM_GOLD["mean_atol"], (case, x.abs().mean().item())
+    g = DPM_GOLD["full_loop_with_noise"]  # :235-260
+    sch = DPMSolverMultistepScheduler(**DPM_GOLD["config"])
+    sch.set_timesteps(DPM_GOLD["num_inference_steps"])
+    timesteps = sch.timesteps[g["t_start"]:]
+    x = sch.add_noise(dummy_sample_deter(), dummy_noise_deter(), timesteps[:1])
+    for t in timesteps:
+        x = sch.step(dummy_model(x, t), t, x)
+    assert abs(x.abs().sum().item() - g["sum"]) < DPM_GOLD["sum_atol"]
+    assert abs(x.abs().mean().item() - g["mean"]) < DPM_GOLD["mean_atol"]
 
 
 def test_timestep_embedding_structure():  # test_layers_utils.py:32-52

@@ -94,3 +94,49 @@ def test_euler_rejects_what_has_no_device_path():
     s.set_timesteps(5)
     with pytest.raises(ValueError):
         s.step_scalars(3)
+
+
+SD_DPM = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", timestep_spacing="leading", steps_offset=1)
+
+
+@pytest.mark.parametrize("kw", [dict(), SD_DPM, dict(SD_DPM, use_karras_sigmas=True), dict(use_lu_lambdas=True),
+                                dict(solver_order=1), dict(lower_order_final=False), dict(euler_at_final=True),
+                                dict(timestep_spacing="trailing"), dict(beta_schedule="squaredcos_cap_v2", lambda_min_clipped=-5.1)])
+@pytest.mark.parametrize("n", [10, 25])
+def test_dpm_solver_pp_2m_bit_exact(kw, n):
+    """Host DPMSolverMultistepScheduler (numpy) == oracle: sigmas, timesteps, and the per-step scalars applied in the
+    kernel's operation order reproduce the oracle's step() bit for bit through a whole trajectory (orders 1 and 2,
+    lower_order_final / euler_at_final switching)."""
+    o, s = O.DPMSolverMultistepScheduler(**kw), S.DPMSolverMultistepScheduler(**kw)
+    o.set_timesteps(n), s.set_timesteps(n)
+    assert np.array_equal(o.sigmas.numpy(), s.sigmas) and o.timesteps.tolist() == s.timesteps.tolist()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 4, 8, 8, generator=g)
+    m_prev = None
+    orders = []
+    for t in s.timesteps:
+        e = torch.randn(2, 4, 8, 8, generator=g)
+        order, sigma_cur, alpha_cur, A, C, halfC, inv_r0 = (torch.tensor(v, dtype=torch.float32) if i else v
+                                                            for i, v in enumerate(s.step_scalars(int(t))))
+        orders.append(order)
+        m0 = (x - sigma_cur * e) / alpha_cur
+        mine = A * x - C * m0
+        if order == 2:
+            mine = mine - halfC * (inv_r0 * (m0 - m_prev))
+        x = o.step(e, torch.tensor(int(t)), x)
+        assert torch.equal(mine, x), (kw, int(t), order)
+        m_prev = m0
+    assert orders[0] == 1
+    if kw.get("solver_order", 2) == 2:
+        assert 2 in orders
+        if kw.get("euler_at_final") or (kw.get("lower_order_final", True) and n < 15):
+            assert orders[-1] == 1
+        else:
+            assert orders[-1] == 2
+
+
+def test_dpm_solver_rejects_what_has_no_device_path():
+    for bad in (dict(algorithm_type="dpmsolver"), dict(solver_type="heun"), dict(solver_order=3), dict(prediction_type="v_prediction"),
+                dict(thresholding=True)):
+        with pytest.raises(NotImplementedError):
+            S.DPMSolverMultistepScheduler(**bad)

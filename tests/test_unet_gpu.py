@@ -208,3 +208,43 @@ def test_load_pretrained_from_safetensors_and_pdparams(tmp_path):
     assert torch.equal(m3(x.cuda(), 481, ctx.cuda(), **kw)[0], base)
     with pytest.raises(W.CheckpointError):
         W.load_pretrained(m3, st, device=0, layout="paddle", prefix="unet.")  # wrong layout is caught by the shape check
+
+
+def test_dpm_solver_pp_2m_device_step_and_pipeline():
+    """DPM-Solver++ 2M: the fused device step (b200mix_dpmpp_2m_step, x0 history kept on the device) is bit-exact against
+    the oracle's fp32 step over a whole trajectory, with and without the fused CFG combine; the pipeline loop (graph and
+    eager bit-identical) tracks the oracle's fp32 UNet + fp32 solver."""
+    from oracle.schedulers import DPMSolverMultistepScheduler as ODPM
+    from paddlemix_b200.ppdiffusers.pipelines import StableDiffusionPipeline
+    from paddlemix_b200.ppdiffusers.schedulers import DPMSolverMultistepScheduler
+    SD = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", timestep_spacing="leading", steps_offset=1)
+    for kw, n in ((SD, 12), (dict(SD, use_karras_sigmas=True), 20)):
+        o, s = ODPM(**kw), DPMSolverMultistepScheduler(**kw)
+        o.set_timesteps(n), s.set_timesteps(n)
+        g = torch.Generator().manual_seed(11)
+        x = torch.randn(2, 4, 16, 16, generator=g)
+        xd = x.cuda()
+        for t in s.timesteps:
+            eu, ec = torch.randn(2, 4, 16, 16, generator=g), torch.randn(2, 4, 16, 16, generator=g)
+            xd = s.step(eu.cuda(), int(t), xd, model_output_cond=ec.cuda(), guidance_scale=7.5)
+            x = o.step(eu + 7.5 * (ec - eu), torch.tensor(int(t)), x)
+            assert torch.equal(xd.cpu(), x), f"DPM-Solver++ step at t={int(t)} is not bit-exact"
+    cfg, P, model = make("tiny_xl")
+    x, ctx, added = inputs(cfg, 2, 16, 20)
+    neg = torch.zeros_like(ctx)
+    steps, gs = 5, 5.0
+    lat = {}
+    for graph in (True, False):
+        pipe = StableDiffusionPipeline(model, DPMSolverMultistepScheduler(**SD), use_cuda_graph=graph)
+        lat[graph] = pipe(prompt_embeds=ctx, negative_prompt_embeds=neg, latents=x, num_inference_steps=steps,
+                          guidance_scale=gs, added_cond_kwargs=added).cpu()
+    assert torch.equal(lat[True], lat[False])
+    sch = ODPM(**SD)
+    sch.set_timesteps(steps)
+    cur = x.clone()
+    add2 = {k: torch.cat([v, v], 0) for k, v in added.items()}
+    for t in sch.timesteps:
+        eps = O.unet_forward(cfg, P, torch.cat([cur, cur], 0), int(t), torch.cat([neg, ctx], 0), add2)
+        eu, ec = eps.chunk(2)
+        cur = sch.step(eu + gs * (ec - eu), t, cur)
+    compare(lat[True], cur, "5-step CFG DPM-Solver++ loop")
