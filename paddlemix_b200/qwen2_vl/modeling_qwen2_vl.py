@@ -51,6 +51,20 @@ class Qwen2VLCausalLMOutputWithPast:
     rope_deltas: Optional[torch.Tensor] = None
 
 
+class KVCache:
+    """past_key_values of the LLM (modeling_qwen2_vl.py:591-596 appends along the sequence axis): one preallocated
+    [B, max_len, kv_heads, head_dim] bf16 buffer per layer for K (after RoPE) and V, plus the number of valid positions
+    (all sequences of a batch have the same length: padded batches are outside this path)."""
+
+    def __init__(self, n_layers, B, max_len, n_kv, head_dim, device):
+        self.k = [torch.empty(B, max_len, n_kv, head_dim, device=device, dtype=bf16) for _ in range(n_layers)]
+        self.v = [torch.empty(B, max_len, n_kv, head_dim, device=device, dtype=bf16) for _ in range(n_layers)]
+        self.length, self.max_len, self.batch = 0, max_len, B
+
+    def get_seq_length(self):
+        return self.length
+
+
 def _pad_rows(w, heads, d, dp):  # [heads*d, in] -> [heads*dp, in]
     if d == dp:
         return w
@@ -307,33 +321,53 @@ class Qwen2VLForConditionalGeneration:
                 labels=None, use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None,
                 pixel_values=None, pixel_values_videos=None, image_grid_thw=None, video_grid_thw=None,
                 rope_deltas=None):
-        """Same signature as the reference (:1382-1399). Prefill only: no KV cache in / out, attention_mask all ones."""
+        """Same signature as the reference (:1382-1399). Prefill (optionally filling a KV cache: use_cache=True) and
+        single-token decode (past_key_values = the KVCache a previous call returned; position = past length +
+        rope_deltas, :1413-1441). attention_mask must be all ones."""
         if self.device is None:
             raise RuntimeError("load_state_dict() must be called before forward()")
-        for name, val in (("past_key_values", past_key_values), ("labels", labels), ("pixel_values_videos", pixel_values_videos),
+        for name, val in (("labels", labels), ("pixel_values_videos", pixel_values_videos),
                           ("video_grid_thw", video_grid_thw), ("inputs_embeds", inputs_embeds)):
             if val is not None:
-                raise NotImplementedError(f"Qwen2VL(b200).forward: `{name}` is outside the prefill hot path")
-        if use_cache or output_attentions or output_hidden_states:
-            raise NotImplementedError("use_cache / output_attentions / output_hidden_states are outside the prefill hot path")
+                raise NotImplementedError(f"Qwen2VL(b200).forward: `{name}` is outside the inference hot path")
+        if output_attentions or output_hidden_states:
+            raise NotImplementedError("output_attentions / output_hidden_states are outside the inference hot path")
         if attention_mask is not None and not bool((attention_mask == 1).all()):
-            raise NotImplementedError("padded batches are outside the prefill hot path (attention_mask must be all ones)")
+            raise NotImplementedError("padded batches are outside the hot path (attention_mask must be all ones)")
         c, dev = self.config, self.device
         ids_host = input_ids.cpu()
         B, S = ids_host.shape
         ids_dev = ids_host.to(dev).reshape(-1).contiguous()
+        if past_key_values is not None and past_key_values.length > 0:
+            # ---- decode: one new token per sequence against the cache ----
+            if S != 1 or pixel_values is not None:
+                raise NotImplementedError("decode takes exactly one new token per sequence and no new images")
+            if position_ids is None:
+                if rope_deltas is None:
+                    raise ValueError("decode needs the rope_deltas returned by the prefill call (or explicit position_ids)")
+                pos = past_key_values.length + rope_deltas.reshape(B, 1).cpu().long()  # arange(1) + cache_position + delta
+                position_ids = pos.unsqueeze(0).expand(3, -1, -1)
+            cos, sin = self._mrope_tables(position_ids.cpu())
+            logits = self.decode_device(ids_dev, B, cos, sin, past_key_values).reshape(B, 1, c.vocab_size)
+            if return_dict is False:
+                return (logits, past_key_values)
+            return Qwen2VLCausalLMOutputWithPast(logits=logits, past_key_values=past_key_values, rope_deltas=rope_deltas)
         image_idx = None
         if pixel_values is not None:
             image_idx = (ids_host.reshape(-1) == c.image_token_id).nonzero().reshape(-1).to(dev)
         if position_ids is None:
             position_ids, rope_deltas = self.get_rope_index(ids_host, image_grid_thw, None, attention_mask)
         cos, sin = self._mrope_tables(position_ids.cpu())
-        logits = self.prefill_device(ids_dev, B, S, cos, sin, pixel_values, image_grid_thw, image_idx)
+        cache = None
+        if use_cache:
+            cache = past_key_values if past_key_values is not None else KVCache(
+                c.num_hidden_layers, B, S + int(getattr(self, "cache_headroom", 256)), c.num_key_value_heads, self.head_dim, dev)
+        logits = self.prefill_device(ids_dev, B, S, cos, sin, pixel_values, image_grid_thw, image_idx, cache=cache)
         if return_dict is False:
-            return (logits,)
-        return Qwen2VLCausalLMOutputWithPast(logits=logits, rope_deltas=rope_deltas)
+            return (logits,) if cache is None else (logits, cache)
+        return Qwen2VLCausalLMOutputWithPast(logits=logits, past_key_values=cache, rope_deltas=rope_deltas)
 
-    def prefill_device(self, ids_dev, B, S, cos, sin, pixel_values=None, image_grid_thw=None, image_idx=None):
+    def prefill_device(self, ids_dev, B, S, cos, sin, pixel_values=None, image_grid_thw=None, image_idx=None, cache=None):
         """The device part of forward(): everything below is kernel launches on the current stream (no host sync).
         ids_dev int64 [B*S]; cos/sin fp32 [B*S, head_dim] (M-RoPE tables); image_idx int64 [n_image_tokens]."""
         from .. import ops
@@ -348,7 +382,11 @@ class Qwen2VLForConditionalGeneration:
                                  f"features {image_embeds.shape[0]}")
             ops.scatter_rows(image_embeds, image_idx, x)  # inputs_embeds[image_mask] = image_embeds (:1449-1452)
         qd, kvd = nh * hd, nkv * hd
-        for L in self.layers:
+        if cache is not None:
+            if cache.batch != B or cache.max_len < S:
+                raise ValueError(f"KV cache [{cache.batch}, {cache.max_len}] cannot hold a [{B}, {S}] prefill")
+            cache.length = S
+        for li, L in enumerate(self.layers):
             h1 = ops.layernorm(x, L["ln1"], None, eps=c.rms_norm_eps, rms=True)
             qkv = ops.linear(h1, *L["qkv"])  # [B*S, qd + 2*kvd]
             q = qkv[:, :qd].unflatten(-1, (nh, hd))
@@ -356,6 +394,9 @@ class Qwen2VLForConditionalGeneration:
             vv = qkv[:, qd + kvd:].unflatten(-1, (nkv, hd))
             ops.rope_inplace(q, cos, sin)
             ops.rope_inplace(k, cos, sin)
+            if cache is not None:  # key_states / value_states after RoPE are what the reference caches (:591-596)
+                cache.k[li][:, :S].copy_(k.unflatten(0, (B, S)))
+                cache.v[li][:, :S].copy_(vv.unflatten(0, (B, S)))
             a = ops.sdpa(q.unflatten(0, (B, S)), k.unflatten(0, (B, S)), vv.unflatten(0, (B, S)), scale=hd ** -0.5, causal=True)
             x = ops.linear(a.reshape(B * S, qd), L["o"], residual=x)
             h2 = ops.layernorm(x, L["ln2"], None, eps=c.rms_norm_eps, rms=True)
@@ -363,5 +404,58 @@ class Qwen2VLForConditionalGeneration:
             x = ops.linear(g, L["down"], residual=x)
         hN = ops.layernorm(x, self.norm_w, None, eps=c.rms_norm_eps, rms=True)
         return ops.linear(hN, self.lm_head, out_fp32=True).reshape(B, S, c.vocab_size)  # fp32 logits (:1474-1475)
+
+    def decode_device(self, ids_dev, B, cos, sin, cache: KVCache):
+        """One decode step (Qwen2VLDecoderLayer.forward :829-889 with a cache): ids_dev int64 [B] = the newest token of each
+        sequence, cos / sin fp32 [B, head_dim] for its position. Appends K / V at cache.length, attends over the
+        cache.length + 1 cached positions (GQA, no mask needed: everything cached is in the past), returns fp32 logits
+        [B, vocab] and advances the cache. Kernel launches only."""
+        from .. import ops
+        from .._lib import GLU_SWIGLU
+        c, hd = self.config, self.head_dim
+        nh, nkv = c.num_attention_heads, c.num_key_value_heads
+        P = cache.length
+        if P + 1 > cache.max_len:
+            raise ValueError(f"KV cache is full ({cache.max_len} positions)")
+        x = ops.gather_rows(self.embed, ids_dev)  # [B, H]
+        qd, kvd = nh * hd, nkv * hd
+        for li, L in enumerate(self.layers):
+            h1 = ops.layernorm(x, L["ln1"], None, eps=c.rms_norm_eps, rms=True)
+            qkv = ops.linear(h1, *L["qkv"])  # [B, qd + 2*kvd]
+            q = qkv[:, :qd].unflatten(-1, (nh, hd))
+            k = qkv[:, qd:qd + kvd].unflatten(-1, (nkv, hd))
+            vv = qkv[:, qd + kvd:].unflatten(-1, (nkv, hd))
+            ops.rope_inplace(q, cos, sin)
+            ops.rope_inplace(k, cos, sin)
+            cache.k[li][:, P].copy_(k)
+            cache.v[li][:, P].copy_(vv)
+            a = ops.sdpa(q.unsqueeze(1), cache.k[li][:, :P + 1], cache.v[li][:, :P + 1], scale=hd ** -0.5)  # [B,1,nh,hd]
+            x = ops.linear(a.reshape(B, qd), L["o"], residual=x)
+            h2 = ops.layernorm(x, L["ln2"], None, eps=c.rms_norm_eps, rms=True)
+            g = ops.linear(h2, L["gu"], glu=GLU_SWIGLU)
+            x = ops.linear(g, L["down"], residual=x)
+        cache.length = P + 1
+        hN = ops.layernorm(x, self.norm_w, None, eps=c.rms_norm_eps, rms=True)
+        return ops.linear(hN, self.lm_head, out_fp32=True)
+
+    @torch.no_grad()
+    def generate(self, input_ids, pixel_values=None, image_grid_thw=None, max_new_tokens: int = 16, eos_token_id=None):
+        """Greedy decoding (generation_utils' default `do_sample=False`): prefill with use_cache, then one decode step per
+        token; returns [B, S + n_new] token ids (generation stops early when every sequence has produced EOS)."""
+        B, S = input_ids.shape
+        self.cache_headroom = max_new_tokens
+        out = self.forward(input_ids=input_ids, pixel_values=pixel_values, image_grid_thw=image_grid_thw, use_cache=True)
+        cache, deltas = out.past_key_values, out.rope_deltas
+        nxt = out.logits[:, -1].argmax(-1)
+        seq = [input_ids.cpu(), nxt.cpu().unsqueeze(1)]
+        done = torch.zeros(B, dtype=torch.bool)
+        for _ in range(max_new_tokens - 1):
+            if eos_token_id is not None:
+                done |= seq[-1].squeeze(1) == eos_token_id
+                if bool(done.all()):
+                    break
+            out = self.forward(input_ids=seq[-1], past_key_values=cache, rope_deltas=deltas, use_cache=True)
+            seq.append(out.logits[:, -1].argmax(-1).cpu().unsqueeze(1))
+        return torch.cat(seq, 1)
 
     __call__ = forward

@@ -46,3 +46,41 @@ def test_qwen2vl_tiny_prefill_parity(grid, n_text):
     ref2 = O.qwen2vl_prefill(cfg, P, ids2, None, None, position_ids=torch.arange(16).reshape(1, 1, -1).expand(3, ids2.shape[0], -1))
     out2 = model(input_ids=ids2).logits.cpu()
     assert torch.nn.functional.cosine_similarity(out2.flatten(), ref2.flatten(), dim=0).item() >= 0.999
+
+
+def test_qwen2vl_kv_cache_decode_matches_full_recompute():
+    """Decode phase: prefill with use_cache, then single-token steps against the KV cache
+    (M-RoPE position = past length + rope_delta, modeling_qwen2_vl.py:1413-1441). A cached step is algebraically the
+    last row of a full causal forward over the extended sequence, so each step's logits are compared with the fp32
+    oracle's prefill of the extended ids; greedy generate() must reproduce the argmax chain."""
+    from paddlemix_b200.qwen2_vl import Qwen2VLForConditionalGeneration
+    cfg = O.QWEN2VL_CONFIGS["tiny"]
+    P = O.init_qwen2vl_params(cfg, seed=2)
+    model = Qwen2VLForConditionalGeneration(cfg).load_state_dict(P, device=0)
+    grid = [[1, 8, 8], [1, 8, 8]]
+    input_ids, pv = _inputs(cfg, grid, [14, 14], seed=3)
+    B, S = input_ids.shape
+    out = model(input_ids=input_ids, pixel_values=pv.cuda(), image_grid_thw=torch.tensor(grid), use_cache=True)
+    cache, deltas = out.past_key_values, out.rope_deltas
+    assert cache.get_seq_length() == S
+    ref = O.qwen2vl_prefill(cfg, P, input_ids, pv, grid)
+    assert torch.nn.functional.cosine_similarity(out.logits.cpu().flatten(), ref.flatten(), dim=0).item() >= 0.999
+    g = torch.Generator().manual_seed(5)
+    ids = input_ids
+    for step in range(4):
+        new = torch.randint(0, 1000, (B, 1), generator=g)  # teacher-forced continuation
+        ids = torch.cat([ids, new], 1)
+        step_out = model(input_ids=new, past_key_values=cache, rope_deltas=deltas, use_cache=True)
+        assert step_out.logits.shape == (B, 1, cfg["vocab_size"]) and cache.get_seq_length() == S + step + 1
+        ref = O.qwen2vl_prefill(cfg, P, ids, pv, grid)[:, -1]
+        o = step_out.logits[:, 0].cpu()
+        cos = torch.nn.functional.cosine_similarity(o.flatten(), ref.flatten(), dim=0).item()
+        err = (o - ref).abs().max().item() / ref.abs().max().item()
+        assert cos >= 0.999 and err <= 0.04, (step, cos, err)
+    # greedy generate: the first new token is the prefill argmax, the next ones follow the model's own decode steps
+    gen = model.generate(input_ids, pixel_values=pv.cuda(), image_grid_thw=torch.tensor(grid), max_new_tokens=3)
+    assert gen.shape == (B, S + 3) and torch.equal(gen[:, :S], input_ids)
+    first = model(input_ids=input_ids, pixel_values=pv.cuda(), image_grid_thw=torch.tensor(grid)).logits[:, -1].argmax(-1).cpu()
+    assert torch.equal(gen[:, S], first)
+    with pytest.raises(NotImplementedError):
+        model(input_ids=input_ids[:, :2], past_key_values=cache, rope_deltas=deltas)  # decode takes one token per sequence
