@@ -505,6 +505,9 @@ __global__ void __launch_bounds__(320, 1)
         c_off = gm * p.ldc;
         r_off = (p.res_row_mod > 0 ? gm % p.res_row_mod : gm) * p.ldr;
       }
+      // rows outside the problem (phantom m-tile of an odd pair, rows past M) still run the warp-collective epilogue:
+      // give them group 0 so their row_add / row_gate reads stay inside the [groups, N] tables (nothing is stored)
+      if (!valid) g = 0;
       const int n0 = nt * BN;
       RowMap rm;  // offsets are multiples of 8 elements whenever staged_ok (vec_ok: 16-byte aligned rows)
       rm.valid = 0;
