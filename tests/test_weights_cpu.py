@@ -136,3 +136,25 @@ def test_embedding_tables_are_not_transposed():
     lin = W.linear_weight_keys(model)
     assert "model.embed_tokens.weight" not in lin and "lm_head.weight" in lin
     assert "visual.patch_embed.proj.weight" not in lin and "model.layers.0.self_attn.q_proj.weight" in lin
+
+
+def test_safetensors_interop_with_the_reference_library(tmp_path):
+    """Cross-check with the `safetensors` wheel when it is installed (it is in this image; the product does not depend
+    on it): archives written by either side are read identically by the other, incl. bf16, metadata and 0-d tensors."""
+    st = pytest.importorskip("safetensors.torch")
+    g = torch.Generator().manual_seed(1)
+    t = {"lin.weight": torch.randn(6, 10, generator=g), "lin.bias": torch.randn(10, generator=g).to(torch.bfloat16),
+         "conv.weight": torch.randn(4, 3, 3, 3, generator=g).to(torch.float16), "step": torch.tensor(7), "mask": torch.tensor([True, False, True])}
+    theirs, ours = str(tmp_path / "theirs.safetensors"), str(tmp_path / "ours.safetensors")
+    st.save_file(t, theirs, metadata={"format": "pt"})
+    sd, meta = W.read_safetensors(theirs)
+    assert meta == {"format": "pt"} and set(sd) == set(t)
+    for k in t:
+        assert sd[k].dtype == t[k].dtype and torch.equal(sd[k], t[k]), k
+    W.write_safetensors(ours, t, {"format": "pd"})
+    back = st.load_file(ours)
+    for k in t:
+        assert back[k].dtype == t[k].dtype and torch.equal(back[k], t[k]), k
+    from safetensors import safe_open
+    with safe_open(ours, framework="pt") as f:
+        assert f.metadata() == {"format": "pd"}
