@@ -96,18 +96,25 @@ int b200mix_conv3x3_small_cin(const void* x, int32_t x_fp32, const void* w, cons
                               int64_t H, int64_t W, int64_t Cin, int64_t Cout, void* stream);
 
 /* Scaled dot-product attention, flash-style on tcgen05 (S=QK^T and O+=PV in TMEM, online softmax in registers).
- * Semantics = the `math` branch of scaled_dot_product_attention_ (ppdiffusers/patches/paddle_patch.py:445-461):
- * softmax(q k^T * scale [+ causal mask]) v. q/k/v/o are bf16 with head_dim contiguous; strides in elements for
- * (batch, seq, head). D in {64, 128, 192}; heads with other sizes are zero-padded by the shim at weight-load time.
- * Hq % Hkv == 0 (GQA, modeling_qwen2_vl.py:497-506). cu_seqlens (int32 device [nseq+1], may be NULL) switches on the
- * varlen block-diagonal mode of the Qwen2-VL ViT (modeling_qwen2_vl.py:354-381): then B must be 1 and both q and k
- * are packed along seq. kv_lens (int32 device [B], may be NULL) gives the number of valid keys per batch element
- * (the block-diagonal text mask of STDiT2's MultiHeadCrossAttention, Open-Sora layers/blocks.py:275-331). */
+ * Full signature of scaled_dot_product_attention_(query, key, value, attn_mask, dropout_p=0, is_causal, scale)
+ * (ppdiffusers/patches/paddle_patch.py:414-424), semantics of its `math` branch (:445-461):
+ *   softmax(q k^T * scale [+ attn_mask | causal mask]) v.
+ * q/k/v/o are bf16 with head_dim contiguous; strides in elements for (batch, seq, head). D in {64, 128, 192}; heads
+ * with other sizes are zero-padded by the shim at weight-load time. Hq % Hkv == 0 (GQA, modeling_qwen2_vl.py:497-506).
+ * cu_seqlens (int32 device [nseq+1], may be NULL) switches on the varlen block-diagonal mode of the Qwen2-VL ViT
+ * (modeling_qwen2_vl.py:354-381): then B must be 1 and both q and k are packed along seq. kv_lens (int32 device [B],
+ * may be NULL) gives the number of valid keys per batch element (the block-diagonal text mask of STDiT2's
+ * MultiHeadCrossAttention, Open-Sora layers/blocks.py:275-331); a batch element with 0 valid keys gets zeros.
+ * attn_mask (may be NULL): additive bias on the scaled scores, bf16 or fp32 (mask_fp32), element (b, h, q, k) at
+ * attn_mask + b*m_sb + h*m_sh + q*m_sq + k (key stride 1; a stride of 0 broadcasts that dimension, so the
+ * [B,1,1,Sk] key-padding bias (1 - m) * -10000 of unet_2d_condition.py:916-927 and the full [B,H,Sq,Sk] mask of
+ * attention_processor.py:588-630 are both expressible). Like the reference, attn_mask is not combined with is_causal.
+ * causal uses the bottom-right alignment (query i sees keys <= i + Sk - Sq) and requires Sq <= Sk. */
 int b200mix_sdpa(const void* q, const void* k, const void* v, void* o, int64_t B, int64_t Hq, int64_t Hkv, int64_t Sq,
                  int64_t Sk, int64_t D, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t k_sb, int64_t k_ss,
                  int64_t k_sh, int64_t v_sb, int64_t v_ss, int64_t v_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh,
                  float scale, int32_t causal, const int32_t* cu_seqlens, int32_t nseq, const int32_t* kv_lens,
-                 void* stream);
+                 const void* attn_mask, int32_t mask_fp32, int64_t m_sb, int64_t m_sh, int64_t m_sq, void* stream);
 
 /* ---- HBM-bound normalisation / modulation kernels (coalesced 16-byte accesses, fp32 statistics) -------------- */
 
@@ -152,6 +159,13 @@ int b200mix_nchw_to_nhwc(const void* x, int32_t x_fp32, void* y, int64_t B, int6
                          void* stream);
 int b200mix_nhwc_to_nchw(const void* x, void* y, int32_t y_fp32, int64_t B, int64_t C, int64_t H, int64_t W,
                          void* stream);
+
+/* y = a + r for an NHWC bf16 activation a [B,H,W,C]; r is NHWC bf16 (r_nchw = 0) or the caller's NCHW fp32|bf16 tensor
+ * (r_nchw = 1). The ControlNet / T2I-Adapter residual adds of UNet2DConditionModel.forward:
+ * down_block_additional_residuals, mid_block_additional_residual, down_intrablock_additional_residuals
+ * (unet_2d_condition.py:1109-1155; unet_2d_blocks.py:1211-1213). y may alias a. */
+int b200mix_add_residual_nhwc(const void* a, const void* r, int32_t r_fp32, int32_t r_nchw, void* y, int64_t B, int64_t C,
+                              int64_t H, int64_t W, void* stream);
 
 /* Fused classifier-free-guidance combine + DDIM step (eta = 0, epsilon prediction), fp32 state:
  *   eps = eps_u + g*(eps_c - eps_u)  (pipeline_stable_diffusion.py:882-884; eps_c NULL => eps = eps_u)

@@ -271,15 +271,20 @@ def feed_forward_geglu(x, P, p):
     return linear(hidden * F.gelu(gate), P, p + ".net.2")
 
 
-def basic_transformer_block(x, ctx, P, p, heads, processor=None):
-    """BasicTransformerBlock.forward, attention.py:376-489 (layer_norm branch, eps 1e-5)."""
-    x = attention(layer_norm(x, P, p + ".norm1"), None, P, p + ".attn1", heads, processor=processor) + x
-    x = attention(layer_norm(x, P, p + ".norm2"), ctx, P, p + ".attn2", heads, processor=processor) + x
+def basic_transformer_block(x, ctx, P, p, heads, processor=None, attention_mask=None, encoder_attention_mask=None):
+    """BasicTransformerBlock.forward, attention.py:376-489 (layer_norm branch, eps 1e-5): attn1 takes attention_mask,
+    attn2 takes encoder_attention_mask (:411-441); both are additive biases [B, 1, keys] here and are broadcast over
+    heads like prepare_attention_mask (attention_processor.py:588-630) does by repeat_interleave."""
+    am = None if attention_mask is None else attention_mask[:, None]
+    eam = None if encoder_attention_mask is None else encoder_attention_mask[:, None]
+    x = attention(layer_norm(x, P, p + ".norm1"), None, P, p + ".attn1", heads, am, processor=processor) + x
+    x = attention(layer_norm(x, P, p + ".norm2"), ctx, P, p + ".attn2", heads, eam, processor=processor) + x
     x = feed_forward_geglu(layer_norm(x, P, p + ".norm3"), P, p + ".ff") + x
     return x
 
 
-def transformer_2d(x, ctx, P, p, heads, layers, groups, use_linear, processor=None):
+def transformer_2d(x, ctx, P, p, heads, layers, groups, use_linear, processor=None, attention_mask=None,
+                   encoder_attention_mask=None):
     """Transformer2DModel.forward, transformer_2d.py:272-509 (continuous branch); its GroupNorm eps is hard-coded
     1e-6 (:161-163)."""
     B, C, H, W = x.shape
@@ -292,7 +297,8 @@ def transformer_2d(x, ctx, P, p, heads, layers, groups, use_linear, processor=No
         h = conv2d(h, P, p + ".proj_in", padding=0)
         h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
     for j in range(layers):
-        h = basic_transformer_block(h, ctx, P, f"{p}.transformer_blocks.{j}", heads, processor)
+        h = basic_transformer_block(h, ctx, P, f"{p}.transformer_blocks.{j}", heads, processor, attention_mask,
+                                    encoder_attention_mask)
     if use_linear:
         h = linear(h, P, p + ".proj_out")
         h = h.reshape(B, H, W, C).permute(0, 3, 1, 2)
@@ -306,10 +312,23 @@ def transformer_2d(x, ctx, P, p, heads, layers, groups, use_linear, processor=No
 # the model
 # ----------------------------------------------------------------------------------------------------------------
 def unet_forward(cfg, P: Params, sample, timestep, encoder_hidden_states, added_cond_kwargs: Optional[dict] = None,
-                 processor=None):
+                 processor=None, attention_mask=None, encoder_attention_mask=None, down_block_additional_residuals=None,
+                 mid_block_additional_residual=None, down_intrablock_additional_residuals=None):
     """UNet2DConditionModel.forward, unet_2d_condition.py:809-1207. sample [B,C,H,W]; timestep number / 0-d / 1-d;
-    encoder_hidden_states [B,L,Dctx]; SDXL: added_cond_kwargs = {text_embeds [B,1280], time_ids [B,6]}."""
+    encoder_hidden_states [B,L,Dctx]; SDXL: added_cond_kwargs = {text_embeds [B,1280], time_ids [B,6]}.
+    attention_mask / encoder_attention_mask: [B, keys] keep-masks (1 = keep) -> biases (:916-927).
+    ControlNet / T2I-Adapter residuals as in :1078-1155."""
     L = unet_layout(cfg)
+    am = eam = None
+    if attention_mask is not None:  # :916-922
+        am = ((1 - attention_mask.to(sample.dtype)) * -10000.0).unsqueeze(1)
+    if encoder_attention_mask is not None:  # :925-927
+        eam = ((1 - encoder_attention_mask.to(sample.dtype)) * -10000.0).unsqueeze(1)
+    is_controlnet = mid_block_additional_residual is not None and down_block_additional_residuals is not None
+    is_adapter = down_intrablock_additional_residuals is not None
+    if not is_adapter and mid_block_additional_residual is None and down_block_additional_residuals is not None:
+        down_intrablock_additional_residuals, is_adapter = down_block_additional_residuals, True  # :1085-1095
+    intra = list(down_intrablock_additional_residuals) if is_adapter else []
     groups, eps, osf = cfg["norm_num_groups"], cfg["norm_eps"], cfg["resnet_out_scale_factor"]
     B = sample.shape[0]
     # 1. time (:934-953): broadcast to batch, fp32 sinusoid, cast to sample dtype, MLP
@@ -332,21 +351,35 @@ def unet_forward(cfg, P: Params, sample, timestep, encoder_hidden_states, added_
     # 3. down (:1096-1119)
     skips = [h]
     for i, d in enumerate(L["down"]):
+        cross = d["type"] == "CrossAttnDownBlock2D"
+        extra = intra.pop(0) if (cross and intra) else None  # :1099-1102
         for j in range(d["layers"]):
             h = resnet_block(h, emb, P, f"down_blocks.{i}.resnets.{j}", groups, eps, osf)
-            if d["type"] == "CrossAttnDownBlock2D":
+            if cross:
                 h = transformer_2d(h, ctx, P, f"down_blocks.{i}.attentions.{j}", d["heads"], d["tlayers"], groups,
-                                   cfg["use_linear_projection"], processor)
+                                   cfg["use_linear_projection"], processor, am, eam)
+                if extra is not None and j == d["layers"] - 1:  # unet_2d_blocks.py:1211-1213
+                    h = h + extra
             skips.append(h)
         if d["downsample"]:  # Downsample2D: conv3x3 stride 2 padding 1 (resnet.py:271-294)
             h = conv2d(h, P, f"down_blocks.{i}.downsamplers.0.conv", stride=2, padding=1)
             skips.append(h)
+        if not cross and intra:  # :1115-1119: in-place add that also lands in the block's last res sample
+            h = h + intra.pop(0)
+            skips[-1] = h
+    if is_controlnet:  # :1121-1131
+        assert len(skips) == len(down_block_additional_residuals)
+        skips = [s_ + r_ for s_, r_ in zip(skips, down_block_additional_residuals)]
     # 4. mid (:1133-1144, unet_2d_blocks.py:750-800)
     m = L["mid"]
     h = resnet_block(h, emb, P, "mid_block.resnets.0", groups, eps, osf)
     h = transformer_2d(h, ctx, P, "mid_block.attentions.0", m["heads"], m["tlayers"], groups,
-                       cfg["use_linear_projection"], processor)
+                       cfg["use_linear_projection"], processor, am, eam)
     h = resnet_block(h, emb, P, "mid_block.resnets.1", groups, eps, osf)
+    if intra and h.shape == intra[0].shape:  # T2I-Adapter-XL, :1145-1151
+        h = h + intra.pop(0)
+    if is_controlnet:  # :1153-1154
+        h = h + mid_block_additional_residual
     # 5. up (:1158-1190): pop len(resnets) skips from the end, concat [hidden, skip] on channels
     for i, u in enumerate(L["up"]):
         for j in range(u["layers"]):
@@ -354,7 +387,7 @@ def unet_forward(cfg, P: Params, sample, timestep, encoder_hidden_states, added_
             h = resnet_block(h, emb, P, f"up_blocks.{i}.resnets.{j}", groups, eps, osf)
             if u["type"] == "CrossAttnUpBlock2D":
                 h = transformer_2d(h, ctx, P, f"up_blocks.{i}.attentions.{j}", u["heads"], u["tlayers"], groups,
-                                   cfg["use_linear_projection"], processor)
+                                   cfg["use_linear_projection"], processor, am, eam)
         if u["upsample"]:  # Upsample2D: nearest x2 then conv3x3 (resnet.py:169-218)
             h = F.interpolate(h, scale_factor=2.0, mode="nearest")
             h = conv2d(h, P, f"up_blocks.{i}.upsamplers.0.conv")

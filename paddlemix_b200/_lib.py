@@ -53,7 +53,7 @@ SIGNATURES = {
     "b200mix_conv3x3_small_cin": [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                                   c_int64, c_void_p],
     "b200mix_sdpa": [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 6 + [c_int64] * 12 +
-                    [c_float, c_int32, c_void_p, c_int32, c_void_p, c_void_p],
+                    [c_float, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p],
     "b200mix_groupnorm_nhwc": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                c_int64, c_int64, c_int32, c_float, c_int32, c_void_p],
     "b200mix_layernorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -65,6 +65,8 @@ SIGNATURES = {
     "b200mix_concat_channels": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p],
     "b200mix_nchw_to_nhwc": [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p],
     "b200mix_nhwc_to_nchw": [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_void_p],
+    "b200mix_add_residual_nhwc": [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                  c_void_p],
     "b200mix_ddim_step": [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_int64, c_float, c_float,
                           c_float, c_float, c_void_p],
     "b200mix_euler_step": [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_int64, c_float, c_float,
@@ -107,6 +109,8 @@ def _load():
     lib.b200mix_debug_attn_bn64.restype = None
     lib.b200mix_debug_no_shortkv.argtypes = [c_int]
     lib.b200mix_debug_no_shortkv.restype = None
+    lib.b200mix_debug_attn_pingpong.argtypes = [c_int]
+    lib.b200mix_debug_attn_pingpong.restype = None
     lib.b200mix_debug_gemm_pair.argtypes = [c_int]
     lib.b200mix_debug_gemm_pair.restype = None
     lib.b200mix_debug_ln_register_only.argtypes = [c_int]

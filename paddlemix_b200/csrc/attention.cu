@@ -28,7 +28,30 @@ struct AttnParams {
   int q_pos[3], k_pos[3], v_pos[3];  // tensor-map coordinate slot (1..3) of (seq, head, batch)
   __nv_bfloat16* o;
   long long o_sb, o_ss, o_sh;
+  // optional additive mask / bias on the scaled scores (attn_mask of scaled_dot_product_attention_,
+  // paddle_patch.py:418,454-455): element (b, h, q, k) at mask + b*m_sb + h*m_sh + q*m_sq + k; a stride of 0 broadcasts
+  const void* mask;
+  int mask_fp32;
+  long long m_sb, m_sh, m_sq;
+  float inv_scale;  // 1 / scale: the bias is folded into the raw score as s + mask * inv_scale
 };
+
+// Adds the mask bias of keys [k0, k0 + 32) of one query row to a 32-column chunk of raw scores (columns at or beyond
+// `sk` are left alone: the caller masks them through its visible-column limit).
+__device__ __forceinline__ void add_mask_chunk(uint32_t (&sv)[32], const AttnParams& p, long long row_off, int k0) {
+  if (p.mask_fp32) {
+    const float* mrow = reinterpret_cast<const float*>(p.mask) + row_off + k0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (k0 + i < p.Sk) sv[i] = __float_as_uint(fmaf(__ldg(mrow + i), p.inv_scale, __uint_as_float(sv[i])));
+  } else {
+    const __nv_bfloat16* mrow = reinterpret_cast<const __nv_bfloat16*>(p.mask) + row_off + k0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (k0 + i < p.Sk)
+        sv[i] = __float_as_uint(fmaf(__bfloat162float(mrow[i]), p.inv_scale, __uint_as_float(sv[i])));
+  }
+}
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -211,12 +234,14 @@ __global__ void __launch_bounds__(192, AttnCfg<D, BN, PTM>::MIN_CTAS)
       uint32_t kph = 0;  // K ring position of the NEXT QK^T to issue
       int vst = 0;
       uint32_t vph = 0;  // V ring position of the next PV
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      umma_commit(&k_empty[0]);
-      umma_commit(&s_full[0]);
-      if (++kst == KS) kst = 0, kph ^= 1;
+      if (n_tiles > 0) {  // no visible key (kv_lens[b] == 0): the producer loads no K, nothing to multiply
+        mbar_wait(&k_full[0], 0);
+        tc_fence_after();
+        issue_qk(0, 0);
+        umma_commit(&k_empty[0]);
+        umma_commit(&s_full[0]);
+        if (++kst == KS) kst = 0, kph ^= 1;
+      }
       for (int j = 0; j < n_tiles; ++j) {
         if (j + 1 < n_tiles) {
           mbar_wait(&k_full[kst], kph);
@@ -255,6 +280,9 @@ __global__ void __launch_bounds__(192, AttnCfg<D, BN, PTM>::MIN_CTAS)
     float m = -INFINITY, l = 0.0f;
     uint8_t* p_row = sP + row * 128;
     const int sw = row & 7;
+    // additive mask row of this query (rows past the end of the sequence read row Sq - 1: in bounds, never stored)
+    const long long mask_row = static_cast<long long>(b) * p.m_sb + static_cast<long long>(h) * p.m_sh +
+                               static_cast<long long>(min(q_begin + row, p.Sq - 1)) * p.m_sq;
 
     if constexpr (PT) {
       // ---- P in TMEM: S is read from TMEM twice (row max, then exponentials) in 32-column chunks, the next chunk's
@@ -353,6 +381,10 @@ __global__ void __launch_bounds__(192, AttnCfg<D, BN, PTM>::MIN_CTAS)
         tc_fence_before();
         mbar_arrive(s_empty);
       }
+      if (p.mask) {
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) add_mask_chunk(sv[c], p, mask_row, kv_begin + j * BN + c * 32);
+      }
 
       const int limit = min(kv_len, row_limit_base) - j * BN;  // columns [0, limit) of this tile are visible
       float mx = -INFINITY;
@@ -422,9 +454,11 @@ __global__ void __launch_bounds__(192, AttnCfg<D, BN, PTM>::MIN_CTAS)
     }
     }
 
-    // ---- epilogue: O / l -> global ----
-    mbar_wait(pv_done, (n_tiles - 1) & 1);
-    tc_fence_after();
+    // ---- epilogue: O / l -> global (a row without any visible key gets zeros: O was never written) ----
+    if (n_tiles > 0) {
+      mbar_wait(pv_done, (n_tiles - 1) & 1);
+      tc_fence_after();
+    }
     const float inv_l = (l > 0.0f) ? 1.0f / l : 0.0f;
     const int q_abs = q_begin + row;
     const bool valid = q_abs < q_end;
@@ -433,8 +467,13 @@ __global__ void __launch_bounds__(192, AttnCfg<D, BN, PTM>::MIN_CTAS)
 #pragma unroll 1
     for (int c = 0; c < D / 32; ++c) {
       uint32_t o[32];
-      tmem_ld_32x32b_x32(lane_base + TM_O + c * 32, o);
-      tmem_wait_ld();
+      if (n_tiles > 0) {
+        tmem_ld_32x32b_x32(lane_base + TM_O + c * 32, o);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0u;
+      }
       if (valid) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -598,6 +637,13 @@ __global__ void __launch_bounds__(192, 2)
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(s_empty);
+      if (p.mask) {
+        const long long mask_row = static_cast<long long>(b) * p.m_sb + static_cast<long long>(h) * p.m_sh +
+                                   static_cast<long long>(min(qt * 128 + row, p.Sq - 1)) * p.m_sq;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < nch) add_mask_chunk(sv[c], p, mask_row, c * 32);
+      }
 
       float mx = -INFINITY;
 #pragma unroll
@@ -641,6 +687,10 @@ __global__ void __launch_bounds__(192, 2)
         uint32_t o[32];
         tmem_ld_32x32b_x32(lane_base + TM_O + c * 32, o);
         tmem_wait_ld();
+        if (!(sum > 0.0f)) {  // no visible key (kv_len == 0, or everything masked to -inf): O was never written
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = 0u;
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           uint4 w;
@@ -669,6 +719,337 @@ __global__ void __launch_bounds__(192, 2)
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<256>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Persistent ping-pong attention, D = 64, non-causal, fixed-length batches: the self-attention of SD / SDXL / SD3
+// (Sq, Sk in the thousands, 8..32 key blocks per query tile). One CTA per SM, 384 threads, looping over a contiguous range
+// of work items; a work item = TWO consecutive 128-row query tiles of one (batch, head):
+//   warp 0      TMA producer: Q of the next item (2-slot ring), K / V blocks through KS-deep rings. Each K / V block is
+//               loaded ONCE for both query tiles.   (warps 0-3 form the producer warpgroup; warps 2, 3 idle)
+//   warp 1      MMA issuer. Per key block s, in this fixed order:  S0(s+1) = Q0 K^T,  O0 += P0(s) V,
+//               S1(s+1) = Q1 K^T,  O1 += P1(s) V.  The block sequence runs across item boundaries (the first QK^T of
+//               the next item is issued while the current item's last blocks are still in softmax), so there is no
+//               per-tile prologue / epilogue bubble: a CTA pays barrier init, TMEM allocation and pipeline fill once.
+//   warps 4-7   softmax warpgroup of query tile 0, warps 8-11 of query tile 1: one query row per thread. While one
+//               warpgroup exponentiates (MUFU), the other drains S / takes its row max / writes its output, and the
+//               tensor cores run the other tile's MMAs.
+// P never touches shared memory: the bf16 probabilities are stored to TMEM (two keys per 32-bit column) and feed the
+// PV MMA as its A operand (tcgen05.mma with A in TMEM), which removes 64 KB of shared-memory writes + 64 KB of reads
+// per key block: with P in shared memory the two MMAs plus the P round trip need ~2000 clk of the 128 B/clk shared-memory
+// port per block pair, the same as the 2048 clk MUFU bound of the exponentials.
+// TMEM (512 columns): tile t owns [256 t, 256 t + 256): S fp32 (128) | P bf16x2 (64) | O fp32 (64).
+// Softmax inner loop uses the Blackwell packed-fp32 instructions (FFMA2 / FADD2) and the 3-input max (FMNMX3).
+// Rows past the end of the sequence (odd number of query tiles) are computed on zero-filled Q rows and not stored.
+// ------------------------------------------------------------------------------------------------------------
+template <int KS>
+struct AttnPPCfg {
+  static constexpr int TILE = 128 * 64 * 2;  // a 128-row x 64 bf16 tile: Q, K or V
+  static constexpr int SMEM = 4 * TILE /*Q: 2 slots x 2 tiles*/ + 2 * KS * TILE /*K and V rings*/ +
+                              2 * TILE /*O staging*/ + 512 /*barriers*/;
+};
+
+template <int KS>
+__global__ void __launch_bounds__(384, 1)
+    attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p, int npairs,
+                   int total_items) {
+  constexpr int D = 64;
+  constexpr int TILE = AttnPPCfg<KS>::TILE;
+  constexpr uint32_t TM_TILE = 256, TM_S = 0, TM_P = 128, TM_O = 192;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;                  // [slot][tile]
+  uint8_t* sK = sQ + 4 * TILE;         // [KS]
+  uint8_t* sV = sK + KS * TILE;        // [KS]
+  uint8_t* sO = sV + KS * TILE;        // [tile]: output staging for coalesced stores
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * TILE);
+  uint64_t* q_full = bars;             // 2
+  uint64_t* q_empty = bars + 2;        // 2
+  uint64_t* s_full = bars + 4;         // 2 (per tile)
+  uint64_t* s_empty = bars + 6;        // 2, 128 arrivals
+  uint64_t* p_full = bars + 8;         // 2, 128 arrivals
+  uint64_t* pv_done = bars + 10;       // 2
+  uint64_t* k_full = bars + 12;        // KS
+  uint64_t* k_empty = k_full + KS;
+  uint64_t* v_full = k_empty + KS;
+  uint64_t* v_empty = v_full + KS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + KS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1), mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1), mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 128), mbar_init(&pv_done[i], 1);
+    }
+    for (int i = 0; i < KS; ++i) {
+      mbar_init(&k_full[i], 1), mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1), mbar_init(&v_empty[i], 1);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  // my contiguous slice of the flattened (batch, head, query-tile pair) space
+  const int f0 = static_cast<int>(static_cast<long long>(blockIdx.x) * total_items / gridDim.x);
+  const int f1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * total_items / gridDim.x);
+  const int rep = p.Hq / p.Hkv;
+  // key blocks of batch element b (at least one: a batch element without visible keys runs one fully masked block)
+  auto blocks_of = [&](int b) -> int {
+    const int kv_len = p.kv_lens ? min(p.Sk, __ldg(p.kv_lens + b)) : p.Sk;
+    return max(1, (kv_len + 127) >> 7);
+  };
+
+  // register re-allocation between the warpgroups: the producer warpgroup keeps 72 registers per thread, each softmax
+  // thread gets 216 (its 128 scores + 32 packed probabilities + addresses stay in registers, no spills)
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int kst = 0, vst = 0;
+      uint32_t kph = 0, vph = 0;
+      for (int f = f0, n = 0; f < f1; ++f, ++n) {
+        const int grp = f / npairs, pr = f - grp * npairs;
+        const int b = grp / p.Hq, h = grp - b * p.Hq;
+        const int slot = n & 1;
+        mbar_wait(&q_empty[slot], ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[slot], 2 * TILE);
+        tma_load_rows(sQ + (slot * 2 + 0) * TILE, &tmQ, &q_full[slot], p.q_pos, 0, pr * 256, h, b);
+        tma_load_rows(sQ + (slot * 2 + 1) * TILE, &tmQ, &q_full[slot], p.q_pos, 0, pr * 256 + 128, h, b);
+        const int nb = blocks_of(b), hk = h / rep;
+        for (int j = 0; j < nb; ++j) {
+          mbar_wait(&k_empty[kst], kph ^ 1);
+          mbar_expect_tx(&k_full[kst], TILE);
+          tma_load_rows(sK + kst * TILE, &tmK, &k_full[kst], p.k_pos, 0, j * 128, hk, b);
+          if (++kst == KS) kst = 0, kph ^= 1;
+          mbar_wait(&v_empty[vst], vph ^ 1);
+          mbar_expect_tx(&v_full[vst], TILE);
+          tma_load_rows(sV + vst * TILE, &tmV, &v_full[vst], p.v_pos, 0, j * 128, hk, b);
+          if (++vst == KS) vst = 0, vph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && f0 < f1) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);  // B (= V) is MN-major
+      auto issue_qk = [&](int t, int slot, int st) {
+        const uint32_t q_addr = smem_u32(sQ + (slot * 2 + t) * TILE), k_addr = smem_u32(sK + st * TILE);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          umma_bf16_ss(tmem_base + t * TM_TILE + TM_S, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                       make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_qk, k != 0 ? 1u : 0u);
+      };
+      auto issue_pv = [&](int t, int st, bool acc) {
+        const uint32_t v_addr = smem_u32(sV + st * TILE);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16_ts(tmem_base + t * TM_TILE + TM_O, tmem_base + t * TM_TILE + TM_P + k * 8,
+                       make_smem_desc_sw128(v_addr + k * 2048, 16384, 1024), idesc_pv, (acc || k != 0) ? 1u : 0u);
+      };
+      int kst = 0, vst = 0;
+      uint32_t kph = 0, vph = 0;
+      uint32_t sidx = 0;  // key blocks issued so far (per tile): parity source of s_empty / p_full
+      const int nitems = f1 - f0;
+      int nb = blocks_of((f0 / npairs) / p.Hq);
+      // pipeline fill: both QK^T of the very first block
+      mbar_wait(&q_full[0], 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0, 0);
+      umma_commit(&s_full[0]);
+      issue_qk(1, 0, 0);
+      umma_commit(&s_full[1]);
+      umma_commit(&k_empty[0]);
+      if (nb == 1) umma_commit(&q_empty[0]);
+      if (++kst == KS) kst = 0, kph ^= 1;
+      for (int n = 0; n < nitems; ++n) {
+        const int nb_next = (n + 1 < nitems) ? blocks_of(((f0 + n + 1) / npairs) / p.Hq) : 0;
+        for (int j = 0; j < nb; ++j, ++sidx) {
+          const bool same = j + 1 < nb;
+          const bool has_next = same || (n + 1 < nitems);
+          const int n2 = same ? n : n + 1;
+          const bool last_qk_of_item = same ? (j + 2 == nb) : (nb_next == 1);
+          if (has_next) {
+            if (!same) mbar_wait(&q_full[n2 & 1], (n2 >> 1) & 1);
+            mbar_wait(&k_full[kst], kph);
+          }
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (has_next) {
+              mbar_wait(&s_empty[t], sidx & 1);  // softmax warpgroup t has S_t(s) in registers
+              tc_fence_after();
+              issue_qk(t, n2 & 1, kst);
+              umma_commit(&s_full[t]);
+              if (t == 1) {
+                umma_commit(&k_empty[kst]);
+                if (last_qk_of_item) umma_commit(&q_empty[n2 & 1]);
+                if (++kst == KS) kst = 0, kph ^= 1;
+              }
+            }
+            mbar_wait(&p_full[t], sidx & 1);  // P_t(s) is in TMEM (and the warpgroup is done with O_t)
+            if (t == 0) mbar_wait(&v_full[vst], vph);
+            tc_fence_after();
+            issue_pv(t, vst, j != 0);
+            umma_commit(&pv_done[t]);
+            if (t == 1) {
+              umma_commit(&v_empty[vst]);
+              if (++vst == KS) vst = 0, vph ^= 1;
+            }
+          }
+        }
+        nb = nb_next;
+      }
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    // ===== softmax warpgroups: one query row per thread =====
+    const int t = (warp - 4) >> 2;
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + t * TM_TILE;
+    uint8_t* o_stage = sO + t * TILE + qd * 4096;  // this warp's 32 rows x 128 B
+    const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
+    uint32_t sidx = 0;
+    for (int f = f0; f < f1; ++f) {
+      const int grp = f / npairs, pr = f - grp * npairs;
+      const int b = grp / p.Hq, h = grp - b * p.Hq;
+      const int kv_len = p.kv_lens ? min(p.Sk, __ldg(p.kv_lens + b)) : p.Sk;
+      const int nb = max(1, (kv_len + 127) >> 7);
+      const int q0 = pr * 256 + t * 128;
+      const long long mask_row = static_cast<long long>(b) * p.m_sb + static_cast<long long>(h) * p.m_sh +
+                                 static_cast<long long>(min(q0 + row, p.Sq - 1)) * p.m_sq;
+      float m = -INFINITY, l = 0.0f;
+      for (int j = 0; j < nb; ++j, ++sidx) {
+        mbar_wait(&s_full[t], sidx & 1);
+        tc_fence_after();
+        uint32_t sv[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(lane_base + TM_S + c * 32, sv[c]);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&s_empty[t]);  // QK^T of the next block may overwrite S_t
+        if (p.mask) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) add_mask_chunk(sv[c], p, mask_row, j * 128 + c * 32);
+        }
+        const int limit = kv_len - j * 128;  // columns [0, limit) of this block are visible
+        if (limit < 128) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= limit) sv[c][i] = 0xff800000u;  // -inf
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent FMNMX3 chains
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            mx4[i & 3] = fmax3(mx4[i & 3], __uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1]));
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        const float m_cand = fmaxf(m, mx);
+        const bool grow = (m_cand - m) * p.scale_log2 > 8.0f;  // also true for the first finite block (m = -inf)
+        float alpha = 1.0f;
+        if (grow) {
+          alpha = fast_exp2((m - m_cand) * p.scale_log2);
+          m = m_cand;
+          l *= alpha;
+        }
+        const float m_scaled = (m == -INFINITY) ? 0.0f : m * p.scale_log2;
+        if (j > 0) {
+          // P_t and O_t are free once PV_t of the previous block has completed
+          mbar_wait(&pv_done[t], (sidx - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, grow)) {  // lazy rescale: only when the running max grew by more than 2^8
+#pragma unroll 1
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t o[32];
+              tmem_ld_32x32b_x32(lane_base + TM_O + c * 32, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x32b_x32(lane_base + TM_O + c * 32, o);
+            }
+          }
+        }
+        // exponentials: (s * scale_log2 - m_scaled) two at a time (FFMA2), ex2 on the MUFU pipe, packed row sum
+        // (FADD2), bf16 pairs straight back to TMEM as the A operand of the PV MMA
+        const uint64_t nm2 = pack_f32x2(-m_scaled, -m_scaled);
+        uint64_t sum2[2] = {0ull, 0ull};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t* pk = sv[c & 2];  // chunks 0 / 2 are dead by the time their packed words overwrite them
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t s2 = pack_f32x2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1]));
+            float t0, t1;
+            unpack_f32x2(ffma2(s2, sc2, nm2), t0, t1);
+            const float e0 = fast_exp2(t0), e1 = fast_exp2(t1);
+            sum2[i & 1] = fadd2(sum2[i & 1], pack_f32x2(e0, e1));
+            pk[(c & 1) * 16 + i] = pack_bf16x2(e0, e1);
+          }
+          if (c & 1) tmem_st_32x32b_x32(lane_base + TM_P + (c >> 1) * 32, sv[c & 2]);
+        }
+        float a0, a1, b0, b1;
+        unpack_f32x2(sum2[0], a0, a1);
+        unpack_f32x2(sum2[1], b0, b1);
+        l += (a0 + a1) + (b0 + b1);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+      }
+
+      // ---- item epilogue: O / l -> staging (swizzled) -> global, 4 rows x 128 B per store instruction ----
+      mbar_wait(&pv_done[t], (sidx - 1) & 1);
+      tc_fence_after();
+      const float inv_l = (l > 0.0f) ? 1.0f / l : 0.0f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(lane_base + TM_O + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * u + 0]) * inv_l, __uint_as_float(o[8 * u + 1]) * inv_l);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * u + 2]) * inv_l, __uint_as_float(o[8 * u + 3]) * inv_l);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * u + 4]) * inv_l, __uint_as_float(o[8 * u + 5]) * inv_l);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * u + 6]) * inv_l, __uint_as_float(o[8 * u + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(o_stage + lane * 128 + (((c * 4 + u) ^ (lane & 7)) << 4)) = w;
+        }
+      }
+      __syncwarp();
+      __nv_bfloat16* dst0 = p.o + static_cast<long long>(b) * p.o_sb + static_cast<long long>(h) * p.o_sh;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), u = lane & 7;  // 8 lanes cover one row's 128 bytes
+        const uint4 w = *reinterpret_cast<const uint4*>(o_stage + r * 128 + ((u ^ (r & 7)) << 4));
+        const int q_abs = q0 + qd * 32 + r;
+        if (q_abs < p.Sq) *(reinterpret_cast<uint4*>(dst0 + static_cast<long long>(q_abs) * p.o_ss) + u) = w;
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -736,6 +1117,29 @@ static int launch_attn_shortkv(const CUtensorMap& tq, const CUtensorMap& tk, con
   return 0;
 }
 
+#ifndef ATTN_PP_STAGES
+#define ATTN_PP_STAGES 3
+#endif
+static int g_attn_pp = 1;  // test / measurement hook: 0 = D = 64 self-attention goes through attn_kernel<64> again
+
+static int launch_attn_pp(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
+                          cudaStream_t stream) {
+  constexpr int smem_bytes = AttnPPCfg<ATTN_PP_STAGES>::SMEM;
+  static_assert(smem_bytes <= 227 * 1024, "ring depth does not fit shared memory");
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(attn_pp_kernel<ATTN_PP_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   smem_bytes));
+    configured = true;
+  }
+  const int npairs = (p.Sq + 255) / 256;
+  const long long total = static_cast<long long>(B) * p.Hq * npairs;
+  const int grid = static_cast<int>(std::min<long long>(total, num_sms()));
+  B200_CUDA(launch_pdl(attn_pp_kernel<ATTN_PP_STAGES>, dim3(grid), dim3(384), smem_bytes, stream, 1, tq, tk, tv, p,
+                       npairs, (int)total));
+  return 0;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -743,12 +1147,14 @@ using namespace b200;
 extern "C" void b200mix_debug_no_shortkv(int on) { b200::g_no_shortkv = on; }
 extern "C" void b200mix_debug_attn_bn64(int on) { b200::g_attn_bn64 = on; }
 extern "C" void b200mix_debug_attn_ptmem(int on) { b200::g_attn_ptmem = on; }
+extern "C" void b200mix_debug_attn_pingpong(int on) { b200::g_attn_pp = on; }
 
 extern "C" int b200mix_sdpa(const void* q, const void* k, const void* v, void* o, int64_t B, int64_t Hq, int64_t Hkv,
                             int64_t Sq, int64_t Sk, int64_t D, int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t k_sb,
                             int64_t k_ss, int64_t k_sh, int64_t v_sb, int64_t v_ss, int64_t v_sh, int64_t o_sb,
                             int64_t o_ss, int64_t o_sh, float scale, int32_t causal, const int32_t* cu_seqlens,
-                            int32_t nseq, const int32_t* kv_lens, void* stream) {
+                            int32_t nseq, const int32_t* kv_lens, const void* attn_mask, int32_t mask_fp32,
+                            int64_t m_sb, int64_t m_sh, int64_t m_sq, void* stream) {
   if (int rc = ensure_device()) return rc;
   B200_CHECK_ARG(q && k && v && o, "sdpa: null pointer");
   B200_CHECK_ARG(D == 64 || D == 128 || D == 192,
@@ -757,6 +1163,12 @@ extern "C" int b200mix_sdpa(const void* q, const void* k, const void* v, void* o
   B200_CHECK_ARG(B > 0 && Hq > 0 && Hkv > 0 && Sq > 0 && Sk > 0, "sdpa: bad shape");
   B200_CHECK_ARG(Hq % Hkv == 0, "sdpa: Hq %% Hkv != 0");
   B200_CHECK_ARG(!cu_seqlens || (B == 1 && nseq > 0 && Sq == Sk), "sdpa: varlen mode needs B == 1, Sq == Sk");
+  // bottom-right aligned causal mask (query i sees keys <= i + Sk - Sq): with Sq > Sk the first rows see nothing
+  B200_CHECK_ARG(!(causal && Sq > Sk), "sdpa: causal attention needs Sq <= Sk (got Sq=%lld, Sk=%lld)", (long long)Sq,
+                 (long long)Sk);
+  // the reference drops attn_mask when is_causal is set (paddle_patch.py:451-455,502,513); refuse the combination
+  B200_CHECK_ARG(!(attn_mask && (causal || cu_seqlens)), "sdpa: attn_mask cannot be combined with causal / varlen");
+  B200_CHECK_ARG(!attn_mask || scale != 0.0f, "sdpa: attn_mask needs a non-zero scale");
   const int64_t all_strides[12] = {q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb, o_ss, o_sh};
   for (int i = 0; i < 12; ++i)
     B200_CHECK_ARG(all_strides[i] % 8 == 0, "sdpa: stride %d (= %lld) must be a multiple of 8 elements", i,
@@ -772,22 +1184,30 @@ extern "C" int b200mix_sdpa(const void* q, const void* k, const void* v, void* o
   p.kv_lens = kv_lens;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.o_sb = o_sb, p.o_ss = o_ss, p.o_sh = o_sh;
+  p.mask = attn_mask;
+  p.mask_fp32 = mask_fp32;
+  p.m_sb = m_sb, p.m_sh = m_sh, p.m_sq = m_sq;
+  p.inv_scale = attn_mask ? 1.0f / scale : 0.0f;
   CUtensorMap tq, tk, tv;
   if (int rc = make_attn_tmap(&tq, q, D, Sq, Hq, B, q_ss, q_sh, q_sb, p.q_pos)) return rc;
   // short-KV kernel: 128-key boxes; general kernel at D = 64: 128-key blocks unless the 64-key variant is switched on
   const bool shortkv = D == 64 && !causal && !cu_seqlens && Sk <= 128 && !g_no_shortkv &&
                        B * Hq * ((Sq + 127) / 128) < (1ll << 31);
-  const uint32_t kv_box = (D == 64 && !shortkv && g_attn_bn64) ? 64u : 128u;
+  const bool pingpong = D == 64 && !causal && !cu_seqlens && !shortkv && g_attn_pp && !g_attn_bn64 && !g_attn_ptmem &&
+                        Sk > 128 && B * Hq * ((Sq + 255) / 256) < (1ll << 31);
+  const uint32_t kv_box = (D == 64 && !shortkv && !pingpong && g_attn_bn64) ? 64u : 128u;
   if (int rc = make_attn_tmap(&tk, k, D, Sk, Hkv, B, k_ss, k_sh, k_sb, p.k_pos, kv_box)) return rc;
   if (int rc = make_attn_tmap(&tv, v, D, Sk, Hkv, B, v_ss, v_sh, v_sb, p.v_pos, kv_box)) return rc;
   cudaStream_t st0 = reinterpret_cast<cudaStream_t>(stream);
   if (shortkv) return launch_attn_shortkv(tq, tk, tv, p, (int)B, st0);
+  if (pingpong) return launch_attn_pp(tq, tk, tv, p, (int)B, st0);
   int64_t q_tiles = (Sq + 127) / 128 + (cu_seqlens ? nseq : 0);
   dim3 grid((unsigned)q_tiles, (unsigned)Hq, (unsigned)B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (D == 64) {
     if (kv_box == 64) return launch_attn<64, 64>(tq, tk, tv, p, grid, st);
-    return g_attn_ptmem ? launch_attn<64, 128, true>(tq, tk, tv, p, grid, st) : launch_attn<64, 128>(tq, tk, tv, p, grid, st);
+    return (g_attn_ptmem && !attn_mask) ? launch_attn<64, 128, true>(tq, tk, tv, p, grid, st)
+                                        : launch_attn<64, 128>(tq, tk, tv, p, grid, st);
   }
   if (D == 128) return launch_attn<128, 128>(tq, tk, tv, p, grid, st);
   return launch_attn<192, 128>(tq, tk, tv, p, grid, st);

@@ -123,6 +123,29 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, void* _
   }
 }
 
+// y = a + r on an NHWC bf16 activation, r either NHWC (bf16) or NCHW (fp32 | bf16): the ControlNet / T2I-Adapter
+// residuals of UNet2DConditionModel.forward (unet_2d_condition.py:1109-1155) arrive in the caller's NCHW layout.
+__global__ void add_residual_nhwc_kernel(const __nv_bfloat16* __restrict__ a, const void* __restrict__ r, int r_fp32,
+                                         int r_nchw, __nv_bfloat16* __restrict__ y, int B, int C, int H, int W) {
+  const long long total = (long long)B * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long src = i;
+    if (r_nchw) {
+      const int c = (int)(i % C);
+      long long q = i / C;
+      const int w = (int)(q % W);
+      q /= W;
+      const int h = (int)(q % H);
+      const long long b = q / H;
+      src = ((b * C + c) * H + h) * W + w;
+    }
+    const float rv = r_fp32 ? reinterpret_cast<const float*>(r)[src]
+                            : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(r)[src]);
+    y[i] = __float2bfloat16(__bfloat162float(a[i]) + rv);
+  }
+}
+
 // conv_in with Cin == 4 (SD / SDXL latents): one thread = one output pixel. Its 3x3x4 input patch is read once into
 // registers (bf16-rounded, zero outside the image) and reused for every output channel; the filter bank sits in shared
 // memory as fp32 [36][Cout] and is read as warp-wide broadcasts (all lanes want the same 8 output channels), so the
@@ -421,6 +444,17 @@ extern "C" int b200mix_nchw_to_nhwc(const void* x, int32_t x_fp32, void* y, int6
   nchw_to_nhwc_kernel<<<ew_grid(B * C * H * W, 256), 256, 0, ST(stream)>>>(x, x_fp32,
                                                                            reinterpret_cast<__nv_bfloat16*>(y), (int)B,
                                                                            (int)C, (int)H, (int)W);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_add_residual_nhwc(const void* a, const void* r, int32_t r_fp32, int32_t r_nchw, void* y, int64_t B,
+                                         int64_t C, int64_t H, int64_t W, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(a && r && y && B > 0 && C > 0 && H > 0 && W > 0, "add_residual_nhwc: bad arguments");
+  add_residual_nhwc_kernel<<<ew_grid(B * C * H * W, 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a), r, r_fp32, r_nchw, reinterpret_cast<__nv_bfloat16*>(y), (int)B, (int)C,
+      (int)H, (int)W);
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -60,11 +60,16 @@ __device__ __forceinline__ float x_sigmoid_neg_log2(float x, float neg_q_log2e) 
 }
 __device__ __forceinline__ float act_silu(float x) { return x_sigmoid_neg_log2(x, -1.4426950408889634f * x); }
 // Exact-erf GELU  x * Phi(x)  with  Phi(x) = sigmoid(2 x (c0 + c1 x^2 + c2 x^4)),  coefficients fitted (minimax over
-// [-7,7]) so that |gelu_fast - gelu_erf| <= 3.1e-5 absolute: 250x below the bf16 rounding of the output.
+// [-7,7]) so that |gelu_fast - gelu_erf| <= 3.1e-5 absolute: 250x below the bf16 rounding of the output. The quartic
+// coefficient is negative, so the polynomial is only evaluated for x^2 <= 49 (ACT_X2_MAX): beyond |x| = 7 the exponent
+// continues linearly (slope 2 * 1.788), where both Phi and the sigmoid differ from 0 / 1 by < 1e-12, and it
+// saturates to exactly x (x -> +inf) and exactly 0 (x -> -inf: 2^(+big) = inf, x / inf = 0) like erf-GELU does
+// (the reference asserts gelu(-100) == 0 and gelu(20) == 20, ppdiffusers/tests/models/test_activations.py:55-63).
+constexpr float ACT_X2_MAX = 49.0f;
 __device__ __forceinline__ float act_gelu_erf(float x) {
   const float k = -2.0f * 1.4426950408889634f;
   const float c0 = 7.97627599e-01f * k, c1 = 3.69255429e-02f * k, c2 = -3.41174308e-04f * k;
-  const float x2 = x * x;
+  const float x2 = fminf(x * x, ACT_X2_MAX);
   return x_sigmoid_neg_log2(x, x * fmaf(fmaf(c2, x2, c1), x2, c0));
 }
 // tanh-GELU: 0.5 x (1 + tanh(u)) == x * sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3)   (identity, not an approximation)
@@ -104,7 +109,9 @@ __device__ __forceinline__ ActCoef act_coef(int act, int glu) {
   return a;
 }
 __device__ __forceinline__ float act_eval(float x, const ActCoef& a) {
-  const float x2 = x * x;
+  // x^2 is clamped to the range the erf-GELU polynomial was fitted on (see act_gelu_erf); SiLU / quick-GELU have
+  // c1 = c2 = 0 and tanh-GELU is saturated to 1 ulp long before |x| = 7, so the clamp changes none of them
+  const float x2 = fminf(x * x, ACT_X2_MAX);
   return x_sigmoid_neg_log2(x, x * fmaf(fmaf(a.c2, x2, a.c1), x2, a.c0));
 }
 
@@ -698,6 +705,9 @@ static int fill_epilogue(IGemmParams& p, const b200mix_epilogue* e, void* C, lon
   bool vec = (reinterpret_cast<uintptr_t>(C) % 16 == 0) && ((ldc * out_elem) % 16 == 0);
   if (p.residual) vec = vec && (reinterpret_cast<uintptr_t>(p.residual) % 16 == 0) && ((p.ldr * 2) % 16 == 0);
   if (p.bias) vec = vec && (reinterpret_cast<uintptr_t>(p.bias) % 16 == 0);
+  // the coalesced epilogue reads the per-group vectors as float4 at (group * ld_row + 32-column chunk)
+  if (p.row_add) vec = vec && (reinterpret_cast<uintptr_t>(p.row_add) % 16 == 0) && (p.ld_row % 4 == 0);
+  if (p.row_gate) vec = vec && (reinterpret_cast<uintptr_t>(p.row_gate) % 16 == 0) && (p.ld_row % 4 == 0);
   p.vec_ok = vec ? 1 : 0;
   return 0;
 }

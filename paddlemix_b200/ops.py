@@ -215,9 +215,10 @@ def conv3x3_small_cin(x: torch.Tensor, w: torch.Tensor, bias=None) -> torch.Tens
 
 def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[float] = None, causal=False,
          cu_seqlens: Optional[torch.Tensor] = None, kv_lens: Optional[torch.Tensor] = None,
-         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         attn_mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q: [B,Sq,Hq,D], k/v: [B,Sk,Hkv,D] bf16 views (head_dim contiguous; other strides arbitrary multiples of 8).
-    Returns [B,Sq,Hq,D] (the reference layout of scaled_dot_product_attention_)."""
+    attn_mask: additive bias (bf16 / fp32) broadcastable to [B,Hq,Sq,Sk] with a contiguous key axis (the reference's
+    `attn_mask` argument, paddle_patch.py:418). Returns [B,Sq,Hq,D] (the layout of scaled_dot_product_attention_)."""
     _req(q, bf16, "q"), _req(k, bf16, "k"), _req(v, bf16, "v")
     B, Sq, Hq, D = q.shape
     _, Sk, Hkv, _ = k.shape
@@ -227,12 +228,26 @@ def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: Optional[f
     if scale is None:
         scale = D ** -0.5
     nseq = 0 if cu_seqlens is None else cu_seqlens.numel() - 1
+    m_fp32, msb, msh, msq = 0, 0, 0, 0
+    if attn_mask is not None:
+        if attn_mask.dtype not in (torch.float32, bf16):
+            raise TypeError(f"attn_mask must be an additive float32 / bfloat16 bias, got {attn_mask.dtype}")
+        while attn_mask.dim() < 4:
+            attn_mask = attn_mask.unsqueeze(0)
+        if attn_mask.shape[-1] != Sk or any(a not in (1, n) for a, n in zip(attn_mask.shape[:3], (B, Hq, Sq))):
+            raise ValueError(f"attn_mask shape {tuple(attn_mask.shape)} does not broadcast to {(B, Hq, Sq, Sk)}")
+        if attn_mask.stride(-1) != 1 and Sk > 1:
+            attn_mask = attn_mask.contiguous()
+        attn_mask = _req(attn_mask, attn_mask.dtype, "attn_mask")
+        m_fp32 = 1 if attn_mask.dtype == torch.float32 else 0
+        msb, msh, msq = (0 if attn_mask.shape[i] == 1 else attn_mask.stride(i) for i in range(3))
     with _Timed("attention", 4.0 * B * Hq * Sq * Sk * D * (0.5 if causal else 1.0), "flop",
                 lambda: f"attn B{B} H{Hq} Sq{Sq} Sk{Sk} D{D}" + (" causal" if causal else "")):
         check(lib.b200mix_sdpa(_p(q), _p(k), _p(v), _p(out), B, Hq, Hkv, Sq, Sk, D, q.stride(0), q.stride(1),
                                q.stride(2), k.stride(0), k.stride(1), k.stride(2), v.stride(0), v.stride(1),
                                v.stride(2), out.stride(0), out.stride(1), out.stride(2), float(scale),
-                               1 if causal else 0, _p(cu_seqlens), nseq, _p(kv_lens), _stream()), "b200mix_sdpa")
+                               1 if causal else 0, _p(cu_seqlens), nseq, _p(kv_lens), _p(attn_mask), m_fp32, msb, msh,
+                               msq, _stream()), "b200mix_sdpa")
     _count()
     return out
 
@@ -249,7 +264,8 @@ def groupnorm_nhwc(x1: torch.Tensor, gamma, beta, *, x2=None, groups=32, eps=1e-
     assert x1.is_contiguous() and (x2 is None or x2.is_contiguous())
     if out is None:
         out = torch.empty(*x1.shape[:-1], C1 + C2, device=x1.device, dtype=bf16)
-    key = (x1.device, B * groups)
+    # per-(device, stream, B, groups) scratch: two streams never share partial sums, and the size is exact for the key
+    key = (x1.device, torch.cuda.current_stream().cuda_stream, B, groups)
     st = _gn_scratch.get(key)
     if st is None:
         st = torch.empty((1024 + B) * groups * 2, device=x1.device, dtype=torch.float64)
@@ -343,6 +359,25 @@ def nhwc_to_nchw(x: torch.Tensor, out_dtype=torch.float32, out=None):
         out = torch.empty(B, C, H, W, device=x.device, dtype=out_dtype)
     check(lib.b200mix_nhwc_to_nchw(_p(x), _p(out), 1 if out.dtype == torch.float32 else 0, B, C, H, W, _stream()),
           "b200mix_nhwc_to_nchw")
+    _count()
+    return out
+
+
+def add_residual_nhwc(a: torch.Tensor, r: torch.Tensor, *, r_nchw: bool, out=None) -> torch.Tensor:
+    """a: bf16 NHWC [B,H,W,C]; r: the same values as NHWC bf16, or NCHW fp32 / bf16 [B,C,H,W] (r_nchw). Returns a + r."""
+    _req(a, bf16, "a")
+    B, H, W, C = a.shape
+    want = (B, C, H, W) if r_nchw else (B, H, W, C)
+    if tuple(r.shape) != want:
+        raise ValueError(f"residual shape {tuple(r.shape)} does not match the activation {want}")
+    if r.dtype not in (torch.float32, bf16):
+        r = r.float()
+    r = r.to(a.device).contiguous()
+    assert a.is_contiguous()
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib.b200mix_add_residual_nhwc(_p(a), _p(r), 1 if r.dtype == torch.float32 else 0, 1 if r_nchw else 0, _p(out),
+                                        B, C, H, W, _stream()), "b200mix_add_residual_nhwc")
     _count()
     return out
 

@@ -81,6 +81,15 @@ class SD3Transformer2DModel:
         lin("proj_out", D, p * p * self.out_channels)
         return S
 
+    def default_missing_parameters(self, sd) -> Dict[str, Any]:
+        """AdaLayerNormContinuous builds its LayerNorm with weight_attr=False, bias_attr=True on Paddle, so Paddle
+        archives carry a `norm.bias` that torch-format (format='pt') SD3 archives do not have; the reference leaves it
+        at its zero initialisation in that case (from_pretrained ignores missing keys with a default)."""
+        D = self.inner_dim
+        last = self.config.num_layers - 1
+        return {k: torch.zeros(D) for k in ("norm_out.norm.bias", f"transformer_blocks.{last}.norm1_context.norm.bias")
+                if k not in sd}
+
     def init_synthetic_weights(self, seed: int = 1, device: Union[int, str] = 0):
         dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         g = torch.Generator(device=dev).manual_seed(seed)

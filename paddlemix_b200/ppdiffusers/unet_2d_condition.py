@@ -42,6 +42,17 @@ class FrozenDict(dict):
         raise Exception(f"You cannot use ``__setattr__`` on a {self.__class__.__name__} instance.")
 
 
+# reference defaults of the UNet2DConditionModel constructor arguments this mirror does not implement
+# (ppdiffusers/models/unet_2d_condition.py:172-228)
+_REFERENCE_DEFAULTS = dict(
+    dual_cross_attention=False, encoder_hid_dim=None, encoder_hid_dim_type=None, class_embed_type=None,
+    num_class_embeds=None, upcast_attention=False, resnet_time_scale_shift="default", resnet_skip_time_act=False,
+    time_embedding_type="positional", time_embedding_dim=None, time_embedding_act_fn=None, timestep_post_act=None,
+    time_cond_proj_dim=None, conv_in_kernel=3, conv_out_kernel=3, mid_block_only_cross_attention=None,
+    cross_attention_norm=None, addition_embed_type_num_heads=64, class_embeddings_concat=False,
+    reverse_transformer_layers_per_block=None, attention_type="default")
+
+
 def _tup(v, n):
     return tuple(v) if isinstance(v, (tuple, list)) else (v,) * n
 
@@ -66,9 +77,7 @@ class AttnProcessorB200:
     proc(attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, **cross_attention_kwargs)."""
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, **kwargs):
-        if attention_mask is not None:
-            raise NotImplementedError("attention_mask is not supported by AttnProcessorB200 (txt2img passes none)")
-        return attn.fused_forward(hidden_states, encoder_hidden_states)
+        return attn.fused_forward(hidden_states, encoder_hidden_states, attention_mask=attention_mask)
 
 
 class Attention:
@@ -126,8 +135,28 @@ class Attention:
         w = self.w_q if self.is_cross else self.w_qkv[: self.inner]
         return ops.linear(x, w)
 
-    def fused_forward(self, x, ctx=None):
-        """x: [B,S,C] bf16. Returns attention output after to_out (no residual), as the reference processors do."""
+    def prepare_attention_mask(self, attention_mask, target_length, batch_size):
+        """attention_processor.py:588-630 for the bias form the UNet hands down ([B, 1, key_tokens], :916-927): returns an
+        additive [B, 1|heads, 1|query_tokens, key_tokens] bias for ops.sdpa (the head axis stays broadcast instead of
+        being materialised by repeat_interleave). A mask whose length differs from the key length cannot be applied
+        (the reference pads it by `target_length` zeros, :618-623, which only fits UnCLIP's prepended tokens)."""
+        if attention_mask is None:
+            return None
+        m = attention_mask
+        if m.dim() == 2:
+            m = m[:, None, None, :]
+        elif m.dim() == 3:
+            m = m[:, None, :, :]
+        if m.shape[-1] != target_length:
+            raise ValueError(f"attention mask has {m.shape[-1]} key positions, the attention layer {self.name} has "
+                             f"{target_length}")
+        if m.shape[0] not in (1, batch_size):
+            raise ValueError(f"attention mask batch {m.shape[0]} does not match the input batch {batch_size}")
+        return m if m.dtype in (torch.float32, bf16) else m.float()
+
+    def fused_forward(self, x, ctx=None, residual=None, attention_mask=None):
+        """x: [B,S,C] bf16. Returns attention output after to_out, as the reference processors do; `residual` (optional)
+        is added in the out-projection's epilogue."""
         from .. import ops
         B, S, C = x.shape
         H, dp = self.heads, self.head_pad
@@ -137,22 +166,13 @@ class Attention:
         else:
             q = ops.linear(x, self.w_q).unflatten(-1, (H, dp))
             k, v = self._kv
-        o = ops.sdpa(q, k, v, scale=self.scale)
-        return ops.linear(o.reshape(B, S, H * dp), self.w_o, self.b_o)
-
-    def fused_forward_residual(self, x, residual):
-        """Same as fused_forward but with the residual add fused into the out-projection epilogue."""
-        from .. import ops
-        B, S, C = x.shape
-        H, dp = self.heads, self.head_pad
-        if not self.is_cross:
-            qkv = ops.linear(x, self.w_qkv)
-            q, k, v = (qkv[:, :, i * self.inner:(i + 1) * self.inner].unflatten(-1, (H, dp)) for i in range(3))
-        else:
-            q = ops.linear(x, self.w_q).unflatten(-1, (H, dp))
-            k, v = self._kv
-        o = ops.sdpa(q, k, v, scale=self.scale)
+        mask = self.prepare_attention_mask(attention_mask, k.shape[1], B)
+        o = ops.sdpa(q, k, v, scale=self.scale, attn_mask=mask)
         return ops.linear(o.reshape(B, S, H * dp), self.w_o, self.b_o, residual=residual)
+
+    def fused_forward_residual(self, x, residual, attention_mask=None):
+        """Same as fused_forward but with the residual add fused into the out-projection epilogue."""
+        return self.fused_forward(x, None, residual=residual, attention_mask=attention_mask)
 
 
 class _Norm:
@@ -275,20 +295,23 @@ class _BasicTransformerBlock:
         self.ff1_w = torch.stack([w[:half], w[half:]], 1).reshape(2 * half, -1).contiguous().to(dev, bf16)
         self.ff1_b = torch.stack([b[:half], b[half:]], 1).reshape(2 * half).contiguous().to(dev)
 
-    def __call__(self, h, ctx, cross_attention_kwargs):
+    def __call__(self, h, ctx, cross_attention_kwargs, attention_mask=None, encoder_attention_mask=None):
+        """attention.py:352-489: attn1 gets `attention_mask`, attn2 gets `encoder_attention_mask` (:411-441)."""
         from .. import ops
         from .._lib import GLU_GEGLU
         kw = cross_attention_kwargs or {}
         n = ops.layernorm(h, self.norm1.w, self.norm1.b, eps=1e-5)
         if type(self.attn1.processor) is AttnProcessorB200 and not kw:
-            h = self.attn1.fused_forward_residual(n, h)
+            h = self.attn1.fused_forward_residual(n, h, attention_mask)
         else:
-            h = _add(self.attn1.processor(self.attn1, n, encoder_hidden_states=None, attention_mask=None, **kw), h)
+            h = _add(self.attn1.processor(self.attn1, n, encoder_hidden_states=None, attention_mask=attention_mask,
+                                          **kw), h)
         n = ops.layernorm(h, self.norm2.w, self.norm2.b, eps=1e-5)
         if type(self.attn2.processor) is AttnProcessorB200 and not kw:
-            h = self.attn2.fused_forward_residual(n, h)
+            h = self.attn2.fused_forward_residual(n, h, encoder_attention_mask)
         else:
-            h = _add(self.attn2.processor(self.attn2, n, encoder_hidden_states=ctx, attention_mask=None, **kw), h)
+            h = _add(self.attn2.processor(self.attn2, n, encoder_hidden_states=ctx,
+                                          attention_mask=encoder_attention_mask, **kw), h)
         n = ops.layernorm(h, self.norm3.w, self.norm3.b, eps=1e-5)
         ff = ops.linear(n, self.ff1_w, self.ff1_b, glu=GLU_GEGLU)
         return ops.linear(ff, self.ff2.w, self.ff2.b, residual=h)
@@ -319,13 +342,13 @@ class _Transformer2D:
         for m in (self.norm, self.proj_in, self.proj_out, *self.blocks):
             m.load(P, dev)
 
-    def __call__(self, x, ctx, cross_attention_kwargs):
+    def __call__(self, x, ctx, cross_attention_kwargs, attention_mask=None, encoder_attention_mask=None):
         from .. import ops
         B, H, W, C = x.shape
         n = ops.groupnorm_nhwc(x, self.norm.w, self.norm.b, groups=self.groups, eps=1e-6, silu=False)
         h = ops.linear(n.reshape(B, H * W, C), self.proj_in.w, self.proj_in.b)
         for blk in self.blocks:
-            h = blk(h, ctx, cross_attention_kwargs)
+            h = blk(h, ctx, cross_attention_kwargs, attention_mask, encoder_attention_mask)
         out = ops.linear(h, self.proj_out.w, self.proj_out.b, residual=x.reshape(B, H * W, C))
         return out.reshape(B, H, W, C)
 
@@ -354,9 +377,19 @@ class UNet2DConditionModel:
                              "`num_attention_heads` because of a naming issue as described in "
                              "https://github.com/huggingface/diffusers/issues/2011#issuecomment-1547958131. Passing "
                              "`num_attention_heads` will only be supported in diffusers v0.19.")
+        # the remaining reference constructor arguments (unet_2d_condition.py:172-228) are accepted only at their
+        # reference defaults: each is compared with ITS OWN default by type and value (True == 1.0 must not pass)
         for k, v in unsupported.items():
-            if v not in (None, False, "default", "positional", 3, 1.0, 64):
-                raise NotImplementedError(f"UNet2DConditionModel(b200): config option {k}={v!r} is outside the hot path")
+            if k.startswith("_"):  # _class_name / _ppdiffusers_version bookkeeping of config.json
+                continue
+            if k == "upcast_attention" and isinstance(v, bool):
+                continue  # scores are always accumulated and soft-maxed in fp32 here (attention.cu), i.e. "upcast"
+            if k not in _REFERENCE_DEFAULTS:
+                raise NotImplementedError(f"UNet2DConditionModel(b200): unknown config option {k}={v!r}")
+            d = _REFERENCE_DEFAULTS[k]
+            if not (v is d or (type(v) is type(d) and v == d)):
+                raise NotImplementedError(f"UNet2DConditionModel(b200): config option {k}={v!r} is outside the hot path "
+                                          f"(only the reference default {d!r} is supported)")
         if len(down_block_types) != len(up_block_types):
             raise ValueError(f"Must provide the same number of `down_block_types` as `up_block_types`. "
                              f"`down_block_types`: {down_block_types}. `up_block_types`: {up_block_types}.")
@@ -610,37 +643,78 @@ class UNet2DConditionModel:
             v = kv_all[:, :, a._kv_off + a.inner: a._kv_off + 2 * a.inner].unflatten(-1, (a.heads, a.head_pad))
             a._kv = (k, v)
 
-    def forward_nhwc(self, x_nhwc, timestep, ctx, added_cond_kwargs=None, cross_attention_kwargs=None):
-        """x_nhwc: bf16/fp32 [B,H,W,Cin]; ctx: bf16 [B,L,Dctx]. Returns bf16 [B,H,W,Cout]."""
+    def forward_nhwc(self, x_nhwc, timestep, ctx, added_cond_kwargs=None, cross_attention_kwargs=None,
+                     attention_mask=None, encoder_attention_mask=None, down_block_additional_residuals=None,
+                     mid_block_additional_residual=None, down_intrablock_additional_residuals=None,
+                     residuals_nchw=True):
+        """x_nhwc: bf16/fp32 [B,H,W,Cin]; ctx: bf16 [B,L,Dctx]. Returns bf16 [B,H,W,Cout].
+        attention_mask / encoder_attention_mask: additive biases [B,1,keys] (already converted, see forward()).
+        ControlNet / T2I-Adapter residuals (unet_2d_condition.py:1078-1155) are in the caller's NCHW layout unless
+        `residuals_nchw` is False."""
         from .. import ops
         B = x_nhwc.shape[0]
         temb_all = self._embeddings(timestep, B, added_cond_kwargs)
         self._project_context(ctx)
         kw = cross_attention_kwargs
+        am, eam = attention_mask, encoder_attention_mask
+        add = lambda t, r: ops.add_residual_nhwc(t, r, r_nchw=residuals_nchw)  # noqa: E731
+        is_controlnet = mid_block_additional_residual is not None and down_block_additional_residuals is not None
+        is_adapter = down_intrablock_additional_residuals is not None
+        if not is_adapter and mid_block_additional_residual is None and down_block_additional_residuals is not None:
+            # legacy T2I-Adapter usage through the ControlNet argument (:1085-1095)
+            down_intrablock_additional_residuals, is_adapter = down_block_additional_residuals, True
+        intra = list(down_intrablock_additional_residuals) if is_adapter else []
         h = ops.conv3x3_small_cin(x_nhwc, self.conv_in.w, self.conv_in.b)
         skips = [h]
         for blk in self.down:
+            extra = intra.pop(0) if (blk.attns and intra) else None  # CrossAttnDownBlock2D: after the last pair
             for j, r in enumerate(blk.resnets):
                 h = r(h, temb_all)
                 if blk.attns:
-                    h = blk.attns[j](h, ctx, kw)
+                    h = blk.attns[j](h, ctx, kw, am, eam)
+                    if extra is not None and j == len(blk.resnets) - 1:
+                        h = add(h, extra)
                 skips.append(h)
             if blk.down is not None:
                 h = ops.conv3x3(h, blk.down.w, blk.down.b, stride=2)
                 skips.append(h)
+            if not blk.attns and intra:  # DownBlock2D: added to the block output, which is also its last skip (:1118-1122)
+                h = add(h, intra.pop(0))
+                skips[-1] = h
+        if is_controlnet:
+            if len(down_block_additional_residuals) != len(skips):
+                raise ValueError(f"expected {len(skips)} down_block_additional_residuals, got "
+                                 f"{len(down_block_additional_residuals)}")
+            skips = [add(s_, r_) for s_, r_ in zip(skips, down_block_additional_residuals)]
         h = self.mid.res0(h, temb_all)
-        h = self.mid.attn(h, ctx, kw)
+        h = self.mid.attn(h, ctx, kw, am, eam)
         h = self.mid.res1(h, temb_all)
+        if intra and tuple(intra[0].shape) == ((h.shape[0], h.shape[3], h.shape[1], h.shape[2]) if residuals_nchw
+                                               else tuple(h.shape)):  # T2I-Adapter-XL (:1145-1151)
+            h = add(h, intra.pop(0))
+        if is_controlnet:
+            h = add(h, mid_block_additional_residual)
         for blk in self.up:
             for j, r in enumerate(blk.resnets):
                 h = r(h, temb_all, skip=skips.pop())
                 if blk.attns:
-                    h = blk.attns[j](h, ctx, kw)
+                    h = blk.attns[j](h, ctx, kw, am, eam)
             if blk.up is not None:
                 h = ops.conv3x3(ops.upsample_nearest2x(h), blk.up.w, blk.up.b)
         n = ops.groupnorm_nhwc(h, self.norm_out.w, self.norm_out.b, groups=self.config.norm_num_groups,
                                eps=self.config.norm_eps, silu=True)
         return ops.conv3x3(n, self.conv_out.w, self.conv_out.b)
+
+    @staticmethod
+    def _mask_to_bias(mask, dev):
+        """unet_2d_condition.py:916-927: a [batch, key_tokens] keep-mask (1 = keep, 0 = discard; bool / int / float)
+        becomes the additive bias (1 - mask) * -10000 with a singleton query axis; anything else is already a bias."""
+        if mask is None:
+            return None
+        mask = mask.to(dev)
+        if mask.dim() == 2:
+            return ((1.0 - mask.to(torch.float32)) * -10000.0).unsqueeze(1)
+        return mask if mask.dtype in (torch.float32, bf16) else mask.to(torch.float32)
 
     def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, timestep_cond=None,
                 attention_mask=None, cross_attention_kwargs: Optional[Dict[str, Any]] = None,
@@ -651,13 +725,10 @@ class UNet2DConditionModel:
         config.data_format == "NHWC") host or device tensor; timestep: number, 0-d or 1-d tensor; returns
         UNet2DConditionOutput(sample) or (sample,) in bf16 with the input's layout."""
         from .. import ops
-        for name, v in (("class_labels", class_labels), ("timestep_cond", timestep_cond),
-                        ("attention_mask", attention_mask), ("encoder_attention_mask", encoder_attention_mask),
-                        ("down_block_additional_residuals", down_block_additional_residuals),
-                        ("mid_block_additional_residual", mid_block_additional_residual),
-                        ("down_intrablock_additional_residuals", down_intrablock_additional_residuals)):
+        for name, v in (("class_labels", class_labels), ("timestep_cond", timestep_cond)):
             if v is not None:
-                raise NotImplementedError(f"UNet2DConditionModel(b200).forward: `{name}` is outside the hot path")
+                raise NotImplementedError(f"UNet2DConditionModel(b200).forward: `{name}` needs a class / condition "
+                                          "embedding this configuration family does not have")
         if self.device is None:
             raise RuntimeError("load_state_dict() must be called before forward()")
         dev = self.device
@@ -667,7 +738,13 @@ class UNet2DConditionModel:
         ctx = encoder_hidden_states.to(device=dev, dtype=bf16).contiguous()
         nhwc_in = self.config.data_format == "NHWC"
         x = sample.contiguous() if nhwc_in else ops.nchw_to_nhwc(sample.contiguous())
-        y = self.forward_nhwc(x, timestep, ctx, added_cond_kwargs, cross_attention_kwargs)
+        y = self.forward_nhwc(x, timestep, ctx, added_cond_kwargs, cross_attention_kwargs,
+                              attention_mask=self._mask_to_bias(attention_mask, dev),
+                              encoder_attention_mask=self._mask_to_bias(encoder_attention_mask, dev),
+                              down_block_additional_residuals=down_block_additional_residuals,
+                              mid_block_additional_residual=mid_block_additional_residual,
+                              down_intrablock_additional_residuals=down_intrablock_additional_residuals,
+                              residuals_nchw=not nhwc_in)
         out = y if nhwc_in else ops.nhwc_to_nchw(y, out_dtype=bf16)
         if not return_dict:
             return (out,)

@@ -29,7 +29,8 @@ class Qwen2VLConfig(FrozenDict):
     def __init__(self, hidden_size=3584, intermediate_size=18944, num_hidden_layers=28, num_attention_heads=28,
                  num_key_value_heads=4, vocab_size=152064, rms_norm_eps=1e-6, rope_theta=1000000.0,
                  mrope_section=(16, 24, 24), image_token_id=151655, video_token_id=151656,
-                 vision_start_token_id=151652, vision_end_token_id=151653, vision=None, **kw):
+                 vision_start_token_id=151652, vision_end_token_id=151653, vision=None, tie_word_embeddings=False,
+                 **kw):
         vision = dict(depth=32, embed_dim=1280, num_heads=16, mlp_ratio=4, in_channels=3, patch_size=14,
                       temporal_patch_size=2, spatial_merge_size=2, hidden_act="quick_gelu") if vision is None else dict(vision)
         super().__init__(hidden_size=hidden_size, intermediate_size=intermediate_size,
@@ -37,7 +38,8 @@ class Qwen2VLConfig(FrozenDict):
                          num_key_value_heads=num_key_value_heads, vocab_size=vocab_size, rms_norm_eps=rms_norm_eps,
                          rope_theta=rope_theta, mrope_section=tuple(mrope_section), image_token_id=image_token_id,
                          video_token_id=video_token_id, vision_start_token_id=vision_start_token_id,
-                         vision_end_token_id=vision_end_token_id, vision=FrozenDict(vision))
+                         vision_end_token_id=vision_end_token_id, vision=FrozenDict(vision),
+                         tie_word_embeddings=bool(tie_word_embeddings))
 
 
 @dataclass
@@ -130,6 +132,13 @@ class Qwen2VLForConditionalGeneration:
         S["model.norm.weight"] = (H,)
         lin("lm_head", H, c.vocab_size, bias=False)
         return S
+
+    def default_missing_parameters(self, sd) -> Dict[str, Any]:
+        """config.tie_word_embeddings (Qwen2-VL-2B): the archive has no lm_head.weight and the reference ties it to the
+        embedding table (modeling_qwen2_vl.py:1188); in the Paddle Linear layout that is embed_tokens.weight^T."""
+        if self.config.tie_word_embeddings and "lm_head.weight" not in sd and "model.embed_tokens.weight" in sd:
+            return {"lm_head.weight": sd["model.embed_tokens.weight"].t()}
+        return {}
 
     def init_synthetic_weights(self, seed: int = 1, device: Union[int, str] = 0):
         dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)

@@ -121,12 +121,19 @@ def write_safetensors(path: str, tensors: Dict[str, torch.Tensor], metadata: Opt
 # .pdparams (paddle.save pickle of numpy arrays)
 # ---------------------------------------------------------------------------------------------------------------------
 class _NumpyOnlyUnpickler(pickle.Unpickler):
-    """A `.pdparams` file needs nothing but numpy / builtins / collections to unpickle; anything else is refused."""
-    _ALLOWED = ("numpy", "builtins", "collections", "_codecs", "copyreg")
+    """A `.pdparams` file (paddle.save of a dict of numpy arrays) needs exactly these globals to unpickle; every other
+    (module, name) pair is refused. Names are matched exactly - protocol-4 STACK_GLOBAL accepts dotted names
+    (`numpy._core._methods` + `os.system` resolves through the submodule's attributes), so a package-level allow-list
+    is an arbitrary-code-execution hole."""
+    _ALLOWED = {
+        ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+        ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+        ("numpy", "ndarray"), ("numpy", "dtype"),
+        ("collections", "OrderedDict"), ("_codecs", "encode"),
+    }
 
     def find_class(self, module, name):
-        if module.split(".")[0] not in self._ALLOWED or (module == "builtins" and name in ("eval", "exec", "open",
-                                                                                            "__import__", "compile")):
+        if (module, name) not in self._ALLOWED or "." in name:
             raise CheckpointError(f"refusing to unpickle {module}.{name} from a parameter file")
         return super().find_class(module, name)
 
@@ -246,6 +253,20 @@ def load_pretrained(model, path: str, device=0, layout: str = "auto", strict: bo
         raise CheckpointError(f"layout must be auto, torch or paddle (got {layout!r})")
     if layout == "torch":
         sd = torch_to_paddle_layout(model, sd)
+    # parameters the reference leaves at their constructor default when the archive does not hold them (Paddle-only
+    # LayerNorm biases of torch-format SD3 archives, the tied lm_head of Qwen2-VL-2B): the model says how to fill them
+    fill = getattr(model, "default_missing_parameters", None)
+    defaulted = []
+    if fill is not None:
+        for k, v in fill(sd).items():
+            if k not in sd:
+                sd[k] = v
+                defaulted.append(k)
     report = check_against_model(model, sd, strict=strict)
+    if report["missing"]:  # strict=False: zero-fill what is still missing (reported), like set_state_dict does
+        want = model.state_dict_shapes()
+        for k in report["missing"]:
+            sd[k] = torch.zeros(want[k])
+    report["defaulted"] = defaulted
     model.load_state_dict(sd, device=device)
     return report

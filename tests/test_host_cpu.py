@@ -108,6 +108,15 @@ def test_config_errors_mirror_reference():
         m.config.in_channels = 3
     with pytest.raises(RuntimeError):
         m.forward(torch.zeros(1, 4, 8, 8), 1, torch.zeros(1, 77, 1280))
+    # options outside the hot path are refused unless they sit at the reference's own default; True == 1.0 / 0 == False
+    # style coincidences must not slip through (each option is compared with ITS default, by type and value)
+    for kw in (dict(dual_cross_attention=True), dict(resnet_skip_time_act=True), dict(class_embeddings_concat=True),
+               dict(class_embed_type="timestep"), dict(conv_in_kernel=5), dict(conv_in_kernel=3.0),
+               dict(time_embedding_type="fourier"), dict(attention_type="gated"), dict(not_a_reference_option=None)):
+        with pytest.raises(NotImplementedError):
+            UNet2DConditionModel(**kw)
+    UNet2DConditionModel(dual_cross_attention=False, conv_in_kernel=3, upcast_attention=True, class_embed_type=None,
+                         _class_name="UNet2DConditionModel")
 
 
 def test_flops_match_survey():

@@ -99,6 +99,77 @@ def test_special_attn_processor():
     assert torch.equal(model(x.cuda(), 10, ctx.cuda()).sample, base)
 
 
+@pytest.mark.parametrize("mask_dtype", [torch.bool, torch.int64, torch.float32])
+def test_model_xattn_mask(mask_dtype):
+    """Port of test_models_unet_2d_condition.py:486-519: a keep-all encoder_attention_mask == no mask; dropping the last
+    context token changes the output; masking the last token == truncating it out of the condition. The reference's
+    rtol 1e-3 / atol 1e-5 is for fp32; here both sides are the same bf16 kernels, so the mask-vs-truncate pair is
+    compared at bf16 resolution (2e-2 of the output range), and both against the fp32 oracle with the mask."""
+    cfg, P, model = make("tiny_sd")
+    x, ctx, _ = inputs(cfg, 2, 32, 77)
+    B, L = ctx.shape[:2]
+    full = model(x.cuda(), 10, ctx.cuda()).sample
+    scale = full.float().abs().max().item()
+    keep_all = torch.ones(B, L).to(mask_dtype)
+    assert torch.equal(model(x.cuda(), 10, ctx.cuda(), encoder_attention_mask=keep_all.cuda()).sample, full)
+    trunc = model(x.cuda(), 10, ctx[:, :-1].contiguous().cuda()).sample
+    assert (trunc.float() - full.float()).abs().max().item() > 1e-3 * scale
+    mask_last = (torch.arange(L) < L - 1).expand(B, -1).to(mask_dtype)
+    masked = model(x.cuda(), 10, ctx.cuda(), encoder_attention_mask=mask_last.cuda()).sample
+    assert (masked.float() - trunc.float()).abs().max().item() <= 2e-2 * scale
+    ref = O.unet_forward(cfg, P, x, 10, ctx, encoder_attention_mask=mask_last)
+    compare(masked, ref, "encoder_attention_mask vs oracle")
+    # a ragged key-padding mask (different per batch element) and a self-attention mask over the image tokens
+    ragged = torch.ones(B, L)
+    ragged[0, 40:] = 0
+    ragged[1, 5:9] = 0
+    out = model(x.cuda(), 10, ctx.cuda(), encoder_attention_mask=ragged.cuda()).sample
+    compare(out, O.unet_forward(cfg, P, x, 10, ctx, encoder_attention_mask=ragged), "ragged encoder_attention_mask")
+
+
+def test_controlnet_and_adapter_residuals():
+    """down_block_additional_residuals + mid_block_additional_residual (ControlNet) and
+    down_intrablock_additional_residuals (T2I-Adapter), unet_2d_condition.py:1078-1155, against the oracle."""
+    cfg, P, model = make("tiny_xl")
+    B, H = 2, 32
+    x, ctx, added = inputs(cfg, B, H, 77)
+    addc = {k: v.cuda() for k, v in added.items()}
+    L = O.unet_layout(cfg)
+    g = torch.Generator().manual_seed(7)
+    # skip tensors: conv_in output, then per down block its resnet outputs (+ the downsampler output)
+    shapes, hw, ch = [(cfg["block_out_channels"][0], H)], H, None
+    for d in L["down"]:
+        for _ in range(d["layers"]):
+            shapes.append((d["out_ch"], hw))
+        if d["downsample"]:
+            hw //= 2
+            shapes.append((d["out_ch"], hw))
+    down_res = [(0.3 * torch.randn(B, c, s, s, generator=g)).to(bf16).float() for c, s in shapes]
+    mid_res = (0.3 * torch.randn(B, L["mid"]["ch"], hw, hw, generator=g)).to(bf16).float()
+    out = model(x.cuda(), 481, ctx.cuda(), added_cond_kwargs=addc, down_block_additional_residuals=[r.cuda() for r in down_res],
+                mid_block_additional_residual=mid_res.cuda()).sample
+    ref = O.unet_forward(cfg, P, x, 481, ctx, added, down_block_additional_residuals=down_res,
+                         mid_block_additional_residual=mid_res)
+    compare(out, ref, "controlnet residuals")
+    base = model(x.cuda(), 481, ctx.cuda(), added_cond_kwargs=addc).sample
+    assert (out.float() - base.float()).abs().max().item() > 1e-2 * base.float().abs().max().item()
+    # T2I-Adapter: one residual per down block (block output resolution / channels)
+    intra, hw = [], H
+    for d in L["down"]:
+        if d["type"] == "CrossAttnDownBlock2D":
+            intra.append((0.3 * torch.randn(B, d["out_ch"], hw, hw, generator=g)).to(bf16).float())
+            if d["downsample"]:
+                hw //= 2
+        else:
+            if d["downsample"]:
+                hw //= 2
+            intra.append((0.3 * torch.randn(B, d["out_ch"], hw, hw, generator=g)).to(bf16).float())
+    out2 = model(x.cuda(), 481, ctx.cuda(), added_cond_kwargs=addc,
+                 down_intrablock_additional_residuals=[r.cuda() for r in intra]).sample
+    ref2 = O.unet_forward(cfg, P, x, 481, ctx, added, down_intrablock_additional_residuals=list(intra))
+    compare(out2, ref2, "t2i-adapter residuals")
+
+
 def test_graphed_pipeline_matches_eager_and_oracle_loop():
     from oracle.schedulers import DDIMScheduler as ODDIM
     from paddlemix_b200.ppdiffusers.pipelines import StableDiffusionPipeline

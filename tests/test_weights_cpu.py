@@ -91,6 +91,23 @@ def test_pdparams_reader(tmp_path):
         W.read_pdparams(p)
 
 
+def test_pdparams_reader_refuses_dotted_and_submodule_globals(tmp_path):
+    """Protocol-4 STACK_GLOBAL resolves dotted names through module attributes: ('numpy._core._methods', 'os.getcwd')
+    reaches os via a numpy submodule. The allow-list is exact (module, name) pairs, so all of these are refused."""
+    def payload(module, name):  # PROTO 4, SHORT_BINUNICODE module, SHORT_BINUNICODE name, STACK_GLOBAL, EMPTY_TUPLE, REDUCE, STOP
+        m, n = module.encode(), name.encode()
+        return b"\x80\x04" + b"\x8c" + bytes([len(m)]) + m + b"\x8c" + bytes([len(n)]) + n + b"\x93" + b")" + b"R" + b"."
+
+    for module, name in (("numpy._core._methods", "os.getcwd"), ("numpy.core._methods", "os.getcwd"),
+                         ("builtins", "getattr"), ("builtins", "eval"), ("numpy", "load"),
+                         ("numpy.lib.npyio", "load"), ("collections", "OrderedDict.fromkeys"), ("copyreg", "_reconstructor")):
+        p = str(tmp_path / "evil.pdparams")
+        with open(p, "wb") as f:
+            f.write(payload(module, name))
+        with pytest.raises(W.CheckpointError):
+            W.read_pdparams(p)
+
+
 def _tiny_unet():
     from paddlemix_b200.ppdiffusers.unet_2d_condition import UNet2DConditionModel
     cfg = O.UNET_CONFIGS["tiny_xl"]
