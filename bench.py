@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+"""bench.py — BASELINE.json's metric on BASELINE.json's configs.
 
-Workload (configs[1]): SD-XL base 1.0 UNet2DConditionModel, batch 8 per GPU, 1024x1024 (latent 128x128), DDIM
+Main workload (configs[1]): SD-XL base 1.0 UNet2DConditionModel, batch 8 per GPU, 1024x1024 (latent 128x128), DDIM
 (50-step schedule), bf16, synthetic inputs and random-init weights of the SDXL architecture. One bench "step" = one
 denoising timestep = one UNet forward over the batch + the fused DDIM update. Metric = denoiser-forward latents/s
 (images pushed through one denoiser forward per second, whole job); finished latents/s = that / 50.
@@ -9,8 +9,18 @@ denoising timestep = one UNet forward over the batch + the fused DDIM update. Me
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
 N > 1 is launched by `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...`: one rank per GPU,
-images sharded (8 per rank, weights replicated, weak scaling), no per-step communication, one all_gather of the
-finished latents at the end (outside the timed steps, like the reference's pipeline exit).
+images sharded, weights replicated, no per-step communication, one NCCL all_gather of the finished latents.
+
+The same JSON line carries, as extra keys (all timed with CUDA events, max over ranks):
+  job            K steps + the all_gather of the finished latents + the D2H copy of the gathered result on rank 0
+                 (the path's only collective INSIDE a timed region)
+  sdxl_strong    strong scaling of configs[1]: the global batch stays 8, each rank takes 8 / N images
+  sd3_b32        configs[2]: SD3-medium MMDiT, global batch 32 (32 / N images per rank), 1024^2, FlowMatchEuler-28 step,
+                 plus its own job-level number with the all_gather
+  stdit2_b4      configs[4]: STDiT2-XL, 16 x 512^2, global batch 4 over min(N, 4) GPUs
+  qwen2vl_prefill  configs[3] (N = 1): Qwen2-VL-7B prefill tokens/s
+  cpu_baseline / parity (N = 1): the CPU restatement of the reference on ONE full 1024^2 image, and the GPU output on
+                 the same weights / inputs compared with it (cosine, max-rel; tolerance cosine >= 0.999, max-rel <= 0.04)
 """
 import argparse
 import json
@@ -31,9 +41,16 @@ SDXL = dict(down_block_types=("DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnD
             cross_attention_dim=2048, transformer_layers_per_block=(1, 2, 10), attention_head_dim=(5, 10, 20),
             use_linear_projection=True, addition_embed_type="text_time", addition_time_embed_dim=256,
             projection_class_embeddings_input_dim=2816)
+SD3_MEDIUM = dict(sample_size=128, patch_size=2, in_channels=16, num_layers=24, attention_head_dim=64,
+                  num_attention_heads=24, joint_attention_dim=4096, caption_projection_dim=1536,
+                  pooled_projection_dim=2048, out_channels=16, pos_embed_max_size=192)
 DDIM = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
             set_alpha_to_one=False, steps_offset=1)
 SDXL_TFLOP_PER_SAMPLE = 6.761  # 2*MAC over conv/linear/QK^T/PV, SURVEY.md §8d (oracle.unet.unet_flops reproduces it)
+SD3_TFLOP_PER_SAMPLE = 8.437
+STDIT2_TFLOP_PER_SAMPLE = 24.39
+PARITY_TOL = {"cosine_min": 0.999, "max_rel_err": 0.04}
+REF_STEPS, REF_WARMUP = 3, 1  # reference / cpu_baseline legs: fixed sample count, independent of --steps
 
 
 class ClockSampler(threading.Thread):
@@ -66,13 +83,16 @@ class ClockSampler(threading.Thread):
 
 
 def igemm_traffic_per_launch():
-    """DRAM bytes (read + write) per igemm launch, averaged over the launches of one SDXL forward, from the committed ncu
-    pass profiles/r01_igemm_dram_traffic.json (tools/gpu_ncu.sh); None if that file is absent. Not measured live."""
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_igemm_dram_traffic.json")) as f:
-            return json.load(f)["dram_bytes_per_launch"]
-    except Exception:  # noqa: BLE001
-        return None
+    """DRAM bytes (read + write) per igemm launch, averaged over the launches of one SDXL forward. NOT measured in this
+    run: it comes from a committed `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` pass of the same forward
+    (tools/gpu_ncu.sh); returns (value, source file) or (None, None)."""
+    for name in ("r02_igemm_dram_traffic.json", "r01_igemm_dram_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f)["dram_bytes_per_launch"], f"profiles/{name} (ncu pass, not measured in this run)"
+        except Exception:  # noqa: BLE001
+            continue
+    return None, None
 
 
 def measured_peaks():
@@ -84,81 +104,353 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_forward_time(threads, budget_s=150.0, steps=1, warmup=0):
-    """Times the CPU restatement of the reference's UNet forward (oracle, kind='port'; PaddlePaddle itself is not
-    installable here) on a bounded sample of the workload: ONE image (B=1) of the SDXL 1024^2 forward per step.
-    Falls back to a 512^2 image, rescaled by the FLOP ratio and labelled as such, if one full-size image would not
-    fit the time budget."""
+# CPU restatement of the reference (oracle, kind = "port"): one full-size image, fixed sample count
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_forward(steps=REF_STEPS, warmup=REF_WARMUP, keep=False):
+    """Times the CPU restatement of the reference's UNet forward (oracle/unet.py; PaddlePaddle itself is not
+    installable here) on a bounded sample of the workload: ONE image (B = 1) of the SDXL 1024^2 forward, `warmup`
+    untimed + `steps` timed passes. The thread count is chosen once by a short probe at latent 64x64 (all logical cores
+    vs half of them: oversubscribed SMT threads are often slower for oneDNN); the SAME policy runs in the cpu_baseline
+    leg and in --impl reference. Returns a dict; with keep=True also the weights, inputs and the fp32 output (for the
+    parity leg)."""
     import torch
 
     from oracle import unet as O
-    torch.set_num_threads(threads)
+    ncpu = os.cpu_count() or 1
     cfg = O.UNET_CONFIGS["sdxl"]
-    shapes = O.unet_param_shapes(cfg)
-    g = torch.Generator().manual_seed(1)
-    P = {}
-    for name, shp in shapes.items():  # fast init (values do not matter for timing; dense fp32)
-        P[name] = torch.empty(shp).uniform_(-0.02, 0.02, generator=g)
-    H = 128
-    x = torch.randn(1, 4, H, H, generator=g)
-    ctx = torch.randn(1, 77, 2048, generator=g)
-    added = {"text_embeds": torch.randn(1, 1280, generator=g), "time_ids": torch.tensor([[1024., 1024., 0, 0, 1024., 1024.]])}
-    # probe at 512^2 (1.59 TFLOP) to size the sample and to pick the thread count (all logical cores vs one per
-    # physical core: oversubscribed SMT threads are often slower for oneDNN / MKL)
-    probe, best_threads = None, threads
-    for nt in sorted({threads, max(1, threads // 2)}, reverse=True):
+    P = O.init_params(O.unet_param_shapes(cfg), seed=1)  # fan-in scaled, bf16-representable values
+    g = torch.Generator().manual_seed(7)
+    bf = torch.bfloat16
+    x = torch.randn(1, 4, 128, 128, generator=g).to(bf).float()
+    ctx = torch.randn(1, 77, 2048, generator=g).to(bf).float()
+    added = {"text_embeds": torch.randn(1, 1280, generator=g).to(bf).float(),
+             "time_ids": torch.tensor([[1024., 1024., 0, 0, 1024., 1024.]])}
+    best, threads = None, ncpu
+    for nt in sorted({ncpu, max(1, ncpu // 2)}, reverse=True):
         torch.set_num_threads(nt)
         t0 = time.perf_counter()
         with torch.no_grad():
             O.unet_forward(cfg, P, x[:, :, :64, :64], 981, ctx, added)
         dtp = time.perf_counter() - t0
-        if probe is None or dtp < probe:
-            probe, best_threads = dtp, nt
-    torch.set_num_threads(best_threads)
-    cpu_reference_forward_time.threads_used = best_threads
-    est_full = probe * (O.unet_flops(cfg, 1, 128, 128, 77) / O.unet_flops(cfg, 1, 64, 64, 77))
-    full = est_full * (steps + warmup) <= budget_s
-    xin = x if full else x[:, :, :64, :64]
-    scale = 1.0 if full else O.unet_flops(cfg, 1, 64, 64, 77) / O.unet_flops(cfg, 1, 128, 128, 77)
+        if best is None or dtp < best:
+            best, threads = dtp, nt
+    torch.set_num_threads(threads)
     with torch.no_grad():
         for _ in range(warmup):
-            O.unet_forward(cfg, P, xin, 981, ctx, added)
+            ref = O.unet_forward(cfg, P, x, 981, ctx, added)
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.unet_forward(cfg, P, xin, 981, ctx, added)
+            ref = O.unet_forward(cfg, P, x, 981, ctx, added)
         dt = (time.perf_counter() - t0) / steps
-    sample = ("1 image (B=1) SDXL UNet forward at 1024x1024 (latent 128x128), fp32, torch-CPU restatement of the reference"
-              if full else
-              "1 image SDXL UNet forward at 512x512 (latent 64x64), fp32, rescaled to 1024^2 by the FLOP ratio 1.589/6.761 (extrapolated)")
-    return (1.0 / dt) * scale, dt, sample
-
-
-cpu_reference_forward_time.threads_used = None
+    out = {"value": 1.0 / dt, "seconds_per_sample": dt, "cores": threads, "kind": "port",
+           "sample": (f"1 image (B=1) SDXL UNet forward at 1024x1024 (latent 128x128), fp32, torch-CPU restatement of the "
+                      f"reference (oracle/unet.py), {warmup} warm-up + {steps} timed passes, {threads} threads")}
+    if keep:
+        out["_keep"] = (cfg, P, x, ctx, added, ref)
+    return out
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores. The reference is pure
-    Python on PaddlePaddle, which cannot be installed offline, so this runs the oracle port (cpu_baseline.kind='port')."""
+    Python on PaddlePaddle, which cannot be installed offline, so this runs the oracle port (cpu_baseline.kind='port')
+    on the same config as the b200 arm's cpu_baseline leg: one full 1024^2 image, fixed sample count."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    threads = os.cpu_count() or 1
-    value, dt, sample = cpu_reference_forward_time(threads, budget_s=240.0, steps=max(1, args.steps), warmup=min(args.warmup, 1))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    r = cpu_reference_forward()
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": REF_STEPS, "warmup": REF_WARMUP, "ms_per_step": r["seconds_per_sample"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "SDXL-base UNet2DConditionModel forward, 1024x1024, DDIM timestep (configs[1])",
-                       "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_reference_forward_time.threads_used or threads,
-                             "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                       "sample": r["sample"], "requested_steps": args.steps, "requested_warmup": args.warmup},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def bench_qwen2vl_prefill(dev, steps=5, warmup=3):
+# helpers shared by the GPU sections
+# ------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    """Process-group context of one rank."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.dist = dist
+
+    def sync_all(self):
+        import torch
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+            torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, *vals):
+        import torch
+        t = torch.tensor(list(vals), device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def timed(self, fn, steps, warmup):
+        """W untimed calls, then exactly K calls between barrier + synchronize on both sides, CUDA events; ms total
+        (max over ranks)."""
+        import torch
+        for i in range(warmup):
+            fn(i)
+        self.sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        self.sync_all()
+        return self.max_over_ranks(e0.elapsed_time(e1))[0]
+
+
+def sdxl_setup(c, B, height):
+    """Model, graph, scheduler and pinned host inputs of the SDXL workload for B images on this rank."""
+    import torch
+
+    from paddlemix_b200.ppdiffusers.pipelines import GraphedUNet
+    from paddlemix_b200.ppdiffusers.schedulers import DDIMScheduler
+    H, L = height // 8, 77
+    g = torch.Generator().manual_seed(2 + c.rank)
+    s = {"B": B, "H": H}
+    s["lat_h"] = torch.randn(B, 4, H, H, generator=g).pin_memory()
+    s["ctx_h"] = torch.randn(B, L, 2048, generator=g).to(torch.bfloat16).pin_memory()
+    s["te_h"] = torch.randn(B, 1280, generator=g).to(torch.bfloat16).pin_memory()
+    s["ids_h"] = torch.tensor([[float(height), float(height), 0, 0, float(height), float(height)]] * B).pin_memory()
+    s["out_h"] = torch.empty(B, 4, H, H).pin_memory()
+    sched = DDIMScheduler(**DDIM)
+    sched.set_timesteps(50)
+    s["sched"], s["timesteps"] = sched, [int(t) for t in sched.timesteps]
+    return s
+
+
+def sdxl_section(c, unet, B, height, steps, warmup, with_e2e=True, sample_clocks=False):
+    """Device-resident steps, end-to-end steps (host buffers), job-level (steps + all_gather + D2H) for B images/rank."""
+    import torch
+
+    from paddlemix_b200 import ops
+    from paddlemix_b200.ppdiffusers.pipelines import GraphedUNet, all_gather_latents
+    dev = c.dev
+    s = sdxl_setup(c, B, height)
+    H, sched, timesteps = s["H"], s["sched"], s["timesteps"]
+    den = GraphedUNet(unet, (B, 4, H, H), (B, 77, 2048), {"text_embeds": (B, 1280), "time_ids": (B, 6)})
+    state = {"lat": s["lat_h"].to(dev), "nxt": torch.empty(B, 4, H, H, device=dev)}
+    den(state["lat"], 981.0, s["ctx_h"].to(dev), {"text_embeds": s["te_h"].to(dev), "time_ids": s["ids_h"].to(dev)})
+
+    def step_resident(i):
+        t = timesteps[i % len(timesteps)]
+        eps = den(state["lat"], float(t))
+        sched.step(eps, t, state["lat"], out=state["nxt"])
+        state["lat"], state["nxt"] = state["nxt"], state["lat"]
+
+    sampler = ClockSampler(c.local) if (sample_clocks and c.rank == 0) else None
+    for i in range(warmup):
+        step_resident(i)
+    c.sync_all()
+    if sampler:
+        sampler.start()
+    n0 = ops.launches()
+    ms = c.timed(step_resident, steps, 0)
+    launches = ops.launches() - n0
+    if sampler:
+        sampler.stop_flag = True
+    res = {"ms": ms, "launches": launches, "clocks": sampler.summary() if sampler else None, "den": den, "state": s}
+
+    # job level: K steps + the path's only collective (all_gather of the finished latents) + D2H of the gathered result
+    gathered_h = torch.empty(B * c.world, 4, H, H).pin_memory() if c.rank == 0 else None
+
+    def job(_):
+        for i in range(steps):
+            step_resident(i)
+        fin = all_gather_latents(state["lat"])
+        if c.rank == 0:
+            gathered_h.copy_(fin, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    job(0)  # warm-up (NCCL communicator set-up, pinned buffers)
+    t0 = time.perf_counter()
+    ms_job = c.timed(job, 1, 0)
+    wall_job = (time.perf_counter() - t0) * 1e3
+    c.sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fin = all_gather_latents(state["lat"])
+    if c.rank == 0:
+        gathered_h.copy_(fin, non_blocking=True)
+    e1.record()
+    c.sync_all()
+    ms_coll = c.max_over_ranks(e0.elapsed_time(e1))[0]
+    res["job"] = {"steps": steps, "ms_total": round(ms_job, 3), "wall_ms_total": round(c.max_over_ranks(wall_job)[0], 3),
+                  "ms_allgather_plus_d2h": round(ms_coll, 3), "value": round(B * c.world * steps / (ms_job * 1e-3), 3),
+                  "unit": UNIT, "gathered_bytes": B * c.world * 4 * H * H * 4,
+                  "what": "K timesteps + all_gather of the finished latents (NCCL) + D2H of the gathered tensor on rank 0"}
+
+    if with_e2e:
+        def step_e2e(i):
+            t = timesteps[i % len(timesteps)]
+            x = s["lat_h"].to(dev, non_blocking=True)
+            eps = den(x, float(t), s["ctx_h"].to(dev, non_blocking=True),
+                      {"text_embeds": s["te_h"].to(dev, non_blocking=True), "time_ids": s["ids_h"].to(dev, non_blocking=True)})
+            out = sched.step(eps, t, x)
+            s["out_h"].copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller reads the result every step
+
+        for i in range(min(warmup, 3)):
+            step_e2e(i)
+        c.sync_all()
+        t0 = time.perf_counter()
+        ms_e2e = c.timed(step_e2e, steps, 0)
+        wall = c.max_over_ranks((time.perf_counter() - t0) * 1e3)[0]
+        res["e2e"] = {"ms": ms_e2e, "wall_ms": wall,
+                      "h2d": s["lat_h"].numel() * 4 + s["ctx_h"].numel() * 2 + s["te_h"].numel() * 2 + s["ids_h"].numel() * 4,
+                      "d2h": s["out_h"].numel() * 4}
+    return res
+
+
+def roofline_section(c, unet, B, height):
+    """Per-launch CUDA events in one eager forward: achieved rate of every kernel family, igemm as the dominant kernel."""
+    import torch
+
+    from paddlemix_b200 import ops
+    dev = c.dev
+    H = height // 8
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn(B, 4, H, H, generator=g).to(dev)
+    x_nhwc = ops.nchw_to_nhwc(lat)
+    added = {"text_embeds": torch.randn(B, 1280, generator=g).to(torch.bfloat16).to(dev),
+             "time_ids": torch.tensor([[float(height), float(height), 0, 0, float(height), float(height)]] * B).to(dev)}
+    tt = torch.full((B,), 981.0, device=dev)
+    ctx_d = torch.randn(B, 77, 2048, generator=g).to(torch.bfloat16).to(dev)
+    unet.forward_nhwc(x_nhwc, tt, ctx_d, added)  # eager warm-up
+    torch.cuda.synchronize(dev)
+    ops.profile_begin()
+    unet.forward_nhwc(x_nhwc, tt, ctx_d, added)
+    prof = ops.profile_end()
+    peak_tf, peak_gbs, how = measured_peaks()
+    ig = prof.get("igemm")
+    if not ig:
+        return None
+    ach = ig["work"] / (ig["ms"] * 1e-3) / 1e12
+    total_ms = sum(v["ms"] for v in prof.values())
+    traffic, tsrc = igemm_traffic_per_launch()
+    fam = {}
+    for k, v in prof.items():
+        flop = v["unit"] == "flop"
+        a = v["work"] / (v["ms"] * 1e-3) / (1e12 if flop else 1e9)
+        fam[k] = {"ms": round(v["ms"], 3), "achieved": round(a, 1), "unit": "TFLOP/s" if flop else "GB/s",
+                  "frac": round(a / (peak_tf if flop else peak_gbs), 4), "launches": v["calls"]}
+    return {"kernel": "igemm_kernel (tcgen05 implicit GEMM: linear + conv3x3)", "bound": "tensor",
+            "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
+            "traffic": traffic, "traffic_source": tsrc, "peak_source": how, "launches_per_step": ig["calls"],
+            "avg_launch_ms": round(ig["ms"] / ig["calls"], 4), "share_of_step": round(ig["ms"] / total_ms, 3),
+            "algorithmic_tflop_per_step": round(ig["work"] / 1e12, 2), "hbm_peak_gbs": peak_gbs,
+            "by_kernel": fam}
+
+
+def sd3_section(c, steps, warmup, global_batch=32):
+    """configs[2]: SD3-medium MMDiT, global batch 32 sharded over the ranks, 1024^2, FlowMatchEuler (28-step schedule);
+    one step = one MMDiT forward over the rank's images + the fused Euler update; job = steps + all_gather + D2H."""
+    import torch
+
+    from paddlemix_b200 import ops
+    from paddlemix_b200.ppdiffusers.pipelines import all_gather_latents, shard_batch
+    from paddlemix_b200.ppdiffusers.schedulers import FlowMatchEulerDiscreteScheduler
+    from paddlemix_b200.ppdiffusers.transformer_sd3 import SD3Transformer2DModel
+    dev = c.dev
+    lo, hi = shard_batch(global_batch, c.rank, c.world)
+    B = hi - lo
+    model = SD3Transformer2DModel(**SD3_MEDIUM).init_synthetic_weights(seed=3, device=c.local)
+    g = torch.Generator().manual_seed(20 + c.rank)
+    lat = torch.randn(B, 16, 128, 128, generator=g).to(dev)
+    nxt = torch.empty_like(lat)
+    ctx = torch.randn(B, 154, 4096, generator=g).to(torch.bfloat16).to(dev)
+    pooled = torch.randn(B, 2048, generator=g).to(torch.bfloat16).to(dev)
+    sched = FlowMatchEulerDiscreteScheduler(shift=3.0)
+    sched.set_timesteps(28)
+    ts = list(sched.timesteps)
+    tvec = torch.empty(B, device=dev, dtype=torch.float32)
+    st = {"lat": lat, "nxt": nxt}
+
+    def step(i):
+        t = ts[i % len(ts)]
+        tvec.fill_(float(t))
+        v = model(hidden_states=st["lat"], timestep=tvec, encoder_hidden_states=ctx, pooled_projections=pooled,
+                  return_dict=False)[0]
+        sched.step(v, t, st["lat"], out=st["nxt"])
+        st["lat"], st["nxt"] = st["nxt"], st["lat"]
+
+    n0 = ops.launches()
+    ms = c.timed(step, steps, warmup)
+    launches = (ops.launches() - n0) // (steps + warmup)
+    gathered_h = torch.empty(global_batch, 16, 128, 128).pin_memory() if c.rank == 0 else None
+
+    def job(_):
+        for i in range(steps):
+            step(i)
+        fin = all_gather_latents(st["lat"])
+        if c.rank == 0:
+            gathered_h.copy_(fin, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    job(0)
+    ms_job = c.timed(job, 1, 0)
+    del model
+    torch.cuda.empty_cache()
+    per_step = ms / steps
+    return {"metric": "denoiser_forward_latents_per_sec_sd3_medium_1024", "value": round(global_batch / (per_step * 1e-3), 2),
+            "unit": UNIT, "ms_per_step": round(per_step, 3), "scaling": "strong", "n_gpus": c.world,
+            "model_tflops_per_sec": round(SD3_TFLOP_PER_SAMPLE * global_batch / (per_step * 1e-3), 1),
+            "gpu_launches_per_step": launches,
+            "job": {"steps": steps, "ms_total": round(ms_job, 3), "value": round(global_batch * steps / (ms_job * 1e-3), 2),
+                    "unit": UNIT, "what": "K steps + all_gather of the finished latents + D2H on rank 0"},
+            "config": {"workload": "SD3-medium MMDiT (24 layers, 4096 image + 154 text tokens) forward + fused FlowMatchEuler "
+                                   "update per timestep (configs[2])", "global_batch": global_batch, "batch_per_gpu": B,
+                       "resolution": "1024x1024", "scheduler": "FlowMatchEulerDiscrete 28 steps, shift 3.0", "cfg": "off",
+                       "parallelism": f"dp{c.world} (images sharded, weights replicated, one all_gather of finished latents)",
+                       "weights": "random init, SD3-medium architecture (2.0 B params)", "dtype": "bf16", "cuda_graph": False}}
+
+
+def stdit2_section(c, steps, warmup, global_batch=4):
+    """configs[4]: Open-Sora STDiT2-XL, 16 frames x 512^2 (latent 64x64 -> 16 x 1024 tokens), 120 text tokens, global
+    batch 4 sharded over min(N, 4) ranks (ranks beyond the 4th hold one extra sample each: weak beyond N = 4)."""
+    import torch
+
+    from paddlemix_b200.opensora import STDiT2
+    dev = c.dev
+    B = max(1, global_batch // c.world)
+    total = B * c.world
+    m = STDiT2(dict(qk_norm=True)).init_synthetic_weights(seed=5, device=c.local)
+    g = torch.Generator().manual_seed(30 + c.rank)
+    x = torch.randn(B, 4, 16, 64, 64, generator=g).to(dev)
+    y = torch.randn(B, 1, 120, 4096, generator=g).to(torch.bfloat16).to(dev)
+    kw = dict(num_frames=torch.full((B,), 16.0), height=torch.full((B,), 512.0), width=torch.full((B,), 512.0),
+              ar=torch.full((B,), 1.0), fps=torch.full((B,), 24.0))
+    t = torch.full((B,), 500.0, device=dev)
+    ms = c.timed(lambda i: m(x, t, y, **kw), steps, warmup)
+    del m
+    torch.cuda.empty_cache()
+    per = ms / steps
+    return {"metric": "denoiser_forward_samples_per_sec_stdit2_xl_16x512", "value": round(total / (per * 1e-3), 3),
+            "unit": "video-latents/s", "ms_per_step": round(per, 3), "n_gpus": c.world,
+            "model_tflops_per_sec": round(STDIT2_TFLOP_PER_SAMPLE * total / (per * 1e-3), 1),
+            "config": {"workload": "Open-Sora STDiT2-XL forward, 16 frames x 512x512 (16 x 1024 tokens), 120 text tokens "
+                                   "(configs[4])", "global_batch": total, "batch_per_gpu": B, "dtype": "bf16"}}
+
+
+def bench_qwen2vl_prefill(dev, steps=20, warmup=5):
     """Second half of BASELINE.json's metric: Qwen2-VL-7B prefill tokens/s (configs[3]: 4 x (one 448x448 image +
     512 text tokens) = 4 x 768 tokens, bf16, 1 x B200, ViT + 28 decoder layers + lm_head over all positions)."""
     import torch
@@ -181,7 +473,7 @@ def bench_qwen2vl_prefill(dev, steps=5, warmup=3):
     ids_d = ids_h.to(dev).reshape(-1)
     idx_d = (ids_h.reshape(-1) == c.image_token_id).nonzero().reshape(-1).to(dev)
     pv_d = pv_h.to(dev)
-    for _ in range(warmup):
+    for _ in range(warmup):  # also brings the clocks back up after an idle phase
         logits = model.prefill_device(ids_d, B, S, cos, sin, pv_d, grid, idx_d)
     torch.cuda.synchronize(dev)
     n0 = ops.launches()
@@ -193,206 +485,168 @@ def bench_qwen2vl_prefill(dev, steps=5, warmup=3):
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / steps
     launches = (ops.launches() - n0) // steps
-    # end to end through the public forward(): host token ids + pixel values in, last-position logits out
+    # end to end through the public forward(): host token ids + pixel values in, logits of the LAST position out (what
+    # generation consumes, modeling_qwen2_vl.py generate path; the forward itself produces all positions on the device)
     out_h = torch.empty(B, c.vocab_size).pin_memory()
-    for _ in range(2):
-        model(input_ids=ids_h, pixel_values=pv_h, image_grid_thw=torch.tensor(grid))
+    gt = torch.tensor(grid)
+    for _ in range(3):
+        model(input_ids=ids_h, pixel_values=pv_h, image_grid_thw=gt)
     torch.cuda.synchronize(dev)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    f0.record()
     for _ in range(steps):
-        out = model(input_ids=ids_h, pixel_values=pv_h, image_grid_thw=torch.tensor(grid))
+        out = model(input_ids=ids_h, pixel_values=pv_h, image_grid_thw=gt)
         out_h.copy_(out.logits[:, -1], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    ms_e2e = (time.perf_counter() - t0) * 1e3 / steps
+    f1.record()
+    torch.cuda.synchronize(dev)
+    wall_e2e = (time.perf_counter() - t0) * 1e3 / steps
+    ms_e2e = max(f0.elapsed_time(f1) / steps, wall_e2e)
     tflop = 12.58 * B  # oracle.qwen2vl.qwen2vl_flops for this input (SURVEY.md §8d quotes 12.46 per 768-token sample)
     del model, logits
     torch.cuda.empty_cache()
     return {"metric": "qwen2vl_7b_prefill_tokens_per_sec", "value": round(B * S / (ms * 1e-3), 1), "unit": "tokens/s",
-            "ms_per_prefill": round(ms, 3), "model_tflops_per_sec": round(tflop / (ms * 1e-3), 1),
+            "ms_per_prefill": round(ms, 3), "model_tflops_per_sec": round(tflop / (ms * 1e-3), 1), "steps": steps,
+            "warmup": warmup,
             "config": {"workload": "Qwen2-VL-7B prefill, 4 x (448x448 image -> 1024 patches -> 256 merged tokens + 512 "
                                    "text tokens) = 3072 tokens, ViT + LLM + lm_head (all positions, fp32 logits) (configs[3])",
                        "weights": "random init, Qwen2-VL-7B architecture (8.3 B params)", "dtype": "bf16"},
             "gpu_launches": launches,
             "e2e": {"value": round(B * S / (ms_e2e * 1e-3), 1), "unit": "tokens/s", "ms_per_prefill": round(ms_e2e, 3),
-                    "h2d_bytes_per_step": pv_h.numel() * 2 + ids_h.numel() * 8, "d2h_bytes_per_step": out_h.numel() * 4}}
+                    "wall_ms_per_prefill": round(wall_e2e, 3),
+                    "h2d_bytes_per_step": pv_h.numel() * 2 + ids_h.numel() * 8, "d2h_bytes_per_step": out_h.numel() * 4,
+                    "d2h": "last-position logits [B, vocab] fp32"}}
+
+
+def parity_section(c, keep):
+    """C2 parity in the bench run: the GPU model on the cpu_baseline leg's weights / inputs vs its fp32 output."""
+    import torch
+
+    from paddlemix_b200.ppdiffusers.unet_2d_condition import UNet2DConditionModel
+    cfg, P, x, ctx, added, ref = keep
+    keys = ("in_channels", "out_channels", "flip_sin_to_cos", "freq_shift", "down_block_types", "up_block_types",
+            "block_out_channels", "layers_per_block", "norm_num_groups", "norm_eps", "cross_attention_dim",
+            "transformer_layers_per_block", "attention_head_dim", "use_linear_projection", "addition_embed_type",
+            "addition_time_embed_dim", "projection_class_embeddings_input_dim", "resnet_out_scale_factor")
+    model = UNet2DConditionModel(**{k: cfg[k] for k in keys}).load_state_dict(P, device=c.local)
+    out = model(x.to(c.dev), 981, ctx.to(c.dev), added_cond_kwargs={k: v.to(c.dev) for k, v in added.items()}).sample
+    o = out.float().cpu()
+    cos = torch.nn.functional.cosine_similarity(o.flatten().double(), ref.flatten().double(), dim=0).item()
+    err = (o - ref).abs().max().item() / ref.abs().max().item()
+    del model
+    torch.cuda.empty_cache()
+    return {"config": "configs[1] shape: SDXL-base UNet, latent 128x128, B=1, t=981 (GPU bf16 kernels vs CPU fp32 oracle, "
+                      "same weights and inputs)", "cosine": round(cos, 6), "max_rel_err": round(err, 5),
+            "tolerance": PARITY_TOL, "pass": bool(cos >= PARITY_TOL["cosine_min"] and err <= PARITY_TOL["max_rel_err"]),
+            "more": "tests/test_baseline_parity_gpu.py covers configs[1..4] shapes; profiles/ holds the recorded values"}
 
 
 def run_b200(args):
     import torch
-    import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    from paddlemix_b200 import ops
-    from paddlemix_b200.ppdiffusers.pipelines import GraphedUNet, all_gather_latents
-    from paddlemix_b200.ppdiffusers.schedulers import DDIMScheduler
+    c = Ctx()
     from paddlemix_b200.ppdiffusers.unet_2d_condition import UNet2DConditionModel
+    world, rank = c.world, c.rank
+    B, height = args.batch, args.height
+    unet = UNet2DConditionModel(**SDXL).init_synthetic_weights(seed=1, device=c.local)
 
-    B, H, L = args.batch, args.height // 8, 77
-    unet = UNet2DConditionModel(**SDXL).init_synthetic_weights(seed=1, device=local)
-    sched = DDIMScheduler(**DDIM)
-    sched.set_timesteps(50)
-    g = torch.Generator().manual_seed(2 + rank)
-    lat_h = torch.randn(B, 4, H, H, generator=g).pin_memory()
-    ctx_h = torch.randn(B, L, 2048, generator=g).to(torch.bfloat16).pin_memory()
-    te_h = torch.randn(B, 1280, generator=g).to(torch.bfloat16).pin_memory()
-    ids_h = torch.tensor([[float(args.height), float(args.height), 0, 0, float(args.height), float(args.height)]] * B).pin_memory()
-    out_h = torch.empty(B, 4, H, H).pin_memory()
+    main = sdxl_section(c, unet, B, height, args.steps, args.warmup, with_e2e=True, sample_clocks=True)
+    ms, ms_e2e = main["ms"], main["e2e"]["ms"]
+    roof = roofline_section(c, unet, B, height) if rank == 0 else None
 
-    den = GraphedUNet(unet, (B, 4, H, H), (B, L, 2048), {"text_embeds": (B, 1280), "time_ids": (B, 6)})
-    lat = lat_h.to(dev)
-    nxt = torch.empty_like(lat)
-    den(lat, 981.0, ctx_h.to(dev), {"text_embeds": te_h.to(dev), "time_ids": ids_h.to(dev)})
-    timesteps = [int(t) for t in sched.timesteps]
+    extras = {}
+    if not args.no_extras:
+        # strong scaling of configs[1]: global batch 8 stays fixed, 8 / N images per rank
+        if world > 1 and 8 % world == 0:
+            del main["den"]
+            torch.cuda.empty_cache()
+            bs = 8 // world
+            st = sdxl_section(c, unet, bs, height, args.steps, args.warmup, with_e2e=False)
+            extras["sdxl_strong"] = {"metric": METRIC, "scaling": "strong", "global_batch": 8, "batch_per_gpu": bs,
+                                     "value": round(8 * args.steps / (st["ms"] * 1e-3), 3), "unit": UNIT,
+                                     "ms_per_step": round(st["ms"] / args.steps, 3), "n_gpus": world, "job": st["job"]}
+            del st
+        elif world == 1:
+            extras["sdxl_strong"] = {"metric": METRIC, "scaling": "strong", "global_batch": 8, "batch_per_gpu": 8,
+                                     "value": round(B * args.steps / (ms * 1e-3), 3), "unit": UNIT,
+                                     "ms_per_step": round(ms / args.steps, 3), "n_gpus": 1,
+                                     "note": "N = 1: identical to the main (weak) workload"}
+    job = main["job"]
+    clocks = main["clocks"]
+    launches = main["launches"]
+    h2d, d2h, wall_e2e = main["e2e"]["h2d"], main["e2e"]["d2h"], main["e2e"]["wall_ms"]
+    del main, unet
+    torch.cuda.empty_cache()
 
-    def step_resident(i, lat, nxt):
-        t = timesteps[i % len(timesteps)]
-        eps = den(lat, float(t))
-        sched.step(eps, t, lat, out=nxt)
-        return nxt, lat
-
-    def sync_all():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
-
-    # ---- device-resident timing: W warm-up, then exactly K steps bracketed by barrier + synchronize ----
-    for i in range(args.warmup):
-        lat, nxt = step_resident(i, lat, nxt)
-    sync_all()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    n0 = ops.launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        lat, nxt = step_resident(args.warmup + i, lat, nxt)
-    e1.record()
-    sync_all()
-    launches = ops.launches() - n0
-    ms = e0.elapsed_time(e1)
-    if sampler:
-        sampler.stop_flag = True
-    finished = all_gather_latents(lat)  # the path's only collective: finished latents of every rank
-    assert finished.shape[0] == B * world
-
-    # ---- end-to-end through the public API with host buffers: H2D of the step's inputs + D2H of its result ----
-    def step_e2e(i):
-        t = timesteps[i % len(timesteps)]
-        x = lat_h.to(dev, non_blocking=True)
-        eps = den(x, float(t), ctx_h.to(dev, non_blocking=True),
-                  {"text_embeds": te_h.to(dev, non_blocking=True), "time_ids": ids_h.to(dev, non_blocking=True)})
-        out = sched.step(eps, t, x)
-        out_h.copy_(out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the result every step
-
-    for i in range(min(args.warmup, 3)):
-        step_e2e(i)
-    sync_all()
-    k2 = args.steps
-    t0 = time.perf_counter()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for i in range(k2):
-        step_e2e(i)
-    f1.record()
-    sync_all()
-    ms_e2e = max(f0.elapsed_time(f1), 0.0)
-    wall_e2e = (time.perf_counter() - t0) * 1e3
-    ms_e2e = max(ms_e2e, wall_e2e * 0.0 + ms_e2e)
-    h2d = lat_h.numel() * 4 + ctx_h.numel() * 2 + te_h.numel() * 2 + ids_h.numel() * 4
-    d2h = out_h.numel() * 4
-
-    # ---- max over ranks ----
-    tms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = tms.tolist()
-
-    # ---- roofline of the dominant kernel (tcgen05 implicit GEMM): per-launch CUDA events in one eager forward ----
-    roof = None
-    prof = {}
-    if rank == 0:
-        x_nhwc = ops.nchw_to_nhwc(lat)
-        added = {"text_embeds": te_h.to(dev), "time_ids": ids_h.to(dev)}
-        tt = torch.full((B,), 981.0, device=dev)
-        ctx_d = ctx_h.to(dev)
-        unet.forward_nhwc(x_nhwc, tt, ctx_d, added)  # eager warm-up
-        torch.cuda.synchronize(dev)
-        ops.profile_begin()
-        unet.forward_nhwc(x_nhwc, tt, ctx_d, added)
-        prof = ops.profile_end()
-        peak_tf, peak_gbs, how = measured_peaks()
-        ig = prof.get("igemm")
-        if ig:
-            ach = ig["work"] / (ig["ms"] * 1e-3) / 1e12
-            total_ms = sum(v["ms"] for v in prof.values())
-            roof = {"kernel": "igemm_kernel (tcgen05 implicit GEMM: linear + conv3x3)", "bound": "tensor",
-                    "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
-                    "traffic": igemm_traffic_per_launch(), "peak_source": how, "launches_per_step": ig["calls"],
-                    "avg_launch_ms": round(ig["ms"] / ig["calls"], 4), "share_of_step": round(ig["ms"] / total_ms, 3),
-                    "algorithmic_tflop_per_step": round(ig["work"] / 1e12, 2),
-                    "by_kernel_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
-                    "by_kernel_achieved": {k: (round(v["work"] / (v["ms"] * 1e-3) / (1e12 if v["unit"] == "flop" else 1e9), 1),
-                                               "TFLOP/s" if v["unit"] == "flop" else "GB/s") for k, v in prof.items()}}
+    if not args.no_extras:
+        try:
+            extras["sd3_b32"] = sd3_section(c, steps=min(args.steps, 10), warmup=3)
+        except Exception as ex:  # noqa: BLE001
+            extras["sd3_b32"] = {"error": repr(ex)[:300]}
+        try:
+            extras["stdit2_b4"] = stdit2_section(c, steps=min(args.steps, 10), warmup=3)
+        except Exception as ex:  # noqa: BLE001
+            extras["stdit2_b4"] = {"error": repr(ex)[:300]}
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            c.dist.destroy_process_group()
         return
-
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        try:
-            v, dt, sample = cpu_reference_forward_time(os.cpu_count() or 1, budget_s=40.0)
-            cpu = {"value": v, "unit": UNIT, "cores": cpu_reference_forward_time.threads_used or os.cpu_count() or 1,
-                   "kind": "port", "sample": sample, "seconds_per_sample": round(dt, 2)}
-        except Exception as ex:  # the baseline is a report, never a reason to lose the GPU number
-            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {ex}"}
 
     qwen = None
     if world == 1 and not args.no_qwen:
-        del den, unet
-        torch.cuda.empty_cache()
         try:
-            qwen = bench_qwen2vl_prefill(dev)
-        except Exception as ex:
+            qwen = bench_qwen2vl_prefill(c.dev)
+        except Exception as ex:  # noqa: BLE001
             qwen = {"metric": "qwen2vl_7b_prefill_tokens_per_sec", "value": None, "error": repr(ex)[:300]}
 
+    cpu = parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = cpu_reference_forward(keep=True)
+            keep = r.pop("_keep")
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                   "seconds_per_sample": round(r["seconds_per_sample"], 2)}
+            try:
+                parity = parity_section(c, keep)
+            except Exception as ex:  # noqa: BLE001
+                parity = {"error": repr(ex)[:300]}
+        except Exception as ex:  # the baseline is a report, never a reason to lose the GPU number
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {ex}"}
+
     value = B * world * args.steps / (ms * 1e-3)
-    e2e = B * world * k2 / (ms_e2e * 1e-3)
-    step_tflop = SDXL_TFLOP_PER_SAMPLE * B * (args.height / 1024.0) ** 2 if args.height == 1024 else None
+    ms_e2e_eff = max(ms_e2e, wall_e2e)  # device events and the host clock around the same loop: report the larger
+    e2e = B * world * args.steps / (ms_e2e_eff * 1e-3)
+    step_tflop = SDXL_TFLOP_PER_SAMPLE * B if height == 1024 else None
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "SDXL-base UNet2DConditionModel forward + fused DDIM update per timestep (configs[1])",
-                   "batch_per_gpu": B, "global_batch": B * world, "resolution": f"{args.height}x{args.height}",
-                   "latent": f"{H}x{H}", "scheduler": "DDIM 50 steps (scaled_linear, steps_offset 1)", "cfg": "off (UNet rows = batch)",
+                   "batch_per_gpu": B, "global_batch": B * world, "resolution": f"{height}x{height}",
+                   "latent": f"{height // 8}x{height // 8}", "scheduler": "DDIM 50 steps (scaled_linear, steps_offset 1)",
+                   "cfg": "off (UNet rows = batch)",
                    "parallelism": f"dp{world} (images sharded, weights replicated, one all_gather of finished latents)",
                    "weights": "random init, SDXL-base architecture (2.57 B params)", "cuda_graph": True,
                    "l2": "no explicit flush: 5.1 GB of weights + >10 GB of activations stream per step (>> 126 MB L2)"},
         "finished_latents_per_sec_50_steps": round(value / 50.0, 4),
         "model_tflops_per_sec": None if step_tflop is None else round(step_tflop * world / (ms / args.steps * 1e-3), 1),
-        "clocks": sampler.summary() if sampler else None,
+        "clocks": clocks,
         "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": round(ms_e2e / k2, 3)},
+                "ms_per_step": round(ms_e2e_eff / args.steps, 3), "device_ms_per_step": round(ms_e2e / args.steps, 3),
+                "wall_ms_per_step": round(wall_e2e / args.steps, 3)},
         "gpu_launches": launches,
         "roofline": roof,
+        "job": job,
         "cpu_baseline": cpu,
+        "parity": parity,
         "qwen2vl_prefill": qwen,
     }
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        c.dist.destroy_process_group()
 
 
 def main():
@@ -405,6 +659,7 @@ def main():
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-qwen", action="store_true", help="skip the Qwen2-VL-7B prefill section")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling / SD3 / STDiT2 sections")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -176,6 +176,32 @@ int b200mix_ddim_step(const void* eps_u, const void* eps_c, int32_t eps_fp32, fl
                       float* x_prev, int64_t n, float sqrt_alpha_t, float sqrt_beta_t, float sqrt_alpha_prev,
                       float sqrt_beta_prev, void* stream);
 
+/* DDIM step for every prediction_type (0 = epsilon, 1 = sample, 2 = v_prediction; scheduling_ddim.py:424-443) with
+ * optional clip_sample (clip_sample_range > 0 clips the predicted x0, :446-452; <= 0: off), eta = 0, fused CFG combine:
+ *   epsilon: x0 = (x - sb_t*m)/sa_t, eps = m;  sample: x0 = m, eps = (x - sa_t*x0)/sb_t;
+ *   v_prediction: x0 = sa_t*x - sb_t*m, eps = sa_t*m + sb_t*x;   x_prev = sa_p*clip(x0) + sb_p*eps. */
+int b200mix_ddim_step_ex(const void* m_u, const void* m_c, int32_t m_fp32, float guidance, const float* x, float* x_prev,
+                         int64_t n, float sqrt_alpha_t, float sqrt_beta_t, float sqrt_alpha_prev, float sqrt_beta_prev,
+                         int32_t prediction_type, float clip_sample_range, void* stream);
+
+/* LCMScheduler.step (scheduling_lcm.py:468-545), fused CFG combine: x0 as in b200mix_ddim_step_ex, optional clip,
+ * denoised = c_out*x0 + c_skip*x (boundary-condition scalings :453-459, computed on the host),
+ * x_prev = sa_p*denoised + sb_p*noise (noise = the caller's randn, multi-step) or denoised (noise NULL: last step).
+ * `denoised` (may be NULL) receives the denoised sample (LCMSchedulerOutput.denoised). */
+int b200mix_lcm_step(const void* m_u, const void* m_c, int32_t m_fp32, float guidance, const float* x, const float* noise,
+                     float* x_prev, float* denoised, int64_t n, float sqrt_alpha_t, float sqrt_beta_t, float c_skip,
+                     float c_out, float sqrt_alpha_prev, float sqrt_beta_prev, int32_t prediction_type,
+                     float clip_sample_range, void* stream);
+
+/* rescale_noise_cfg (pipeline_stable_diffusion.py:69-80; pipeline_stable_diffusion_xl.py:1061-1067) in two launches:
+ *   ratio[b] = std(eps_c[b]) / std(noise_cfg[b]),  noise_cfg = eps_u + g*(eps_c - eps_u)   (unbiased std over C,H,W)
+ *   out = noise_cfg;  ratio != NULL: out = guidance_rescale * (noise_cfg*ratio[b]) + (1 - guidance_rescale) * noise_cfg
+ * out is fp32 and feeds any scheduler step kernel with its CFG inputs left NULL. */
+int b200mix_cfg_rescale_ratio(const void* eps_u, const void* eps_c, int32_t eps_fp32, float guidance, float* ratio,
+                              int64_t B, int64_t n_per_sample, void* stream);
+int b200mix_cfg_combine(const void* eps_u, const void* eps_c, int32_t eps_fp32, float guidance, const float* ratio,
+                        float guidance_rescale, int64_t n_per_sample, float* out, int64_t n, void* stream);
+
 /* FlowMatchEuler step (scheduling_flow_match_euler_discrete.py:244-275, s_churn = 0), fp32 state, same operation
  * order as the reference: denoised = x - v*sigma; derivative = (x - denoised)/sigma; x_prev = x + derivative*dt
  * with dt = sigma_next - sigma computed in fp32 on the host. */

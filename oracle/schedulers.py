@@ -152,6 +152,115 @@ class DDIMScheduler:
         return sqrt_alpha_prod * original_samples + sqrt_one_minus * noise
 
 
+def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale=0.0):
+    """pipeline_stable_diffusion.py:69-80: rescale the guided prediction to the per-sample std of the text branch
+    (Paddle's Tensor.std is the unbiased estimator, like torch's) and blend with the unrescaled one."""
+    dims = list(range(1, noise_pred_text.ndim))
+    std_text = noise_pred_text.std(dim=dims, keepdim=True)
+    std_cfg = noise_cfg.std(dim=dims, keepdim=True)
+    noise_pred_rescaled = noise_cfg * (std_text / std_cfg)
+    return guidance_rescale * noise_pred_rescaled + (1 - guidance_rescale) * noise_cfg
+
+
+class LCMScheduler:
+    """scheduling_lcm.py:133-560: __init__ :197-253, set_timesteps :330-450, boundary scalings :453-459, step :461-549.
+    Restated for the default `leading` spacing without thresholding; the multi-step noise is supplied by the caller
+    (the reference draws it from a paddle Generator, which cannot be reproduced here)."""
+    order = 1
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                 original_inference_steps=50, clip_sample=False, clip_sample_range=1.0, set_alpha_to_one=True,
+                 steps_offset=0, prediction_type="epsilon", timestep_scaling=10.0):
+        self.num_train_timesteps, self.original_inference_steps = num_train_timesteps, original_inference_steps
+        self.clip_sample, self.clip_sample_range = clip_sample, clip_sample_range
+        self.prediction_type, self.timestep_scaling = prediction_type, timestep_scaling
+        if beta_schedule == "linear":
+            self.betas = linspace_f32(beta_start, beta_end, num_train_timesteps)
+        elif beta_schedule == "scaled_linear":
+            self.betas = linspace_f32(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps) ** 2
+        elif beta_schedule == "squaredcos_cap_v2":
+            self.betas = betas_for_alpha_bar(num_train_timesteps)
+        else:
+            raise NotImplementedError(beta_schedule)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = cumprod_f32(self.alphas)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps = None
+        self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
+        self._step_index = None
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def set_timesteps(self, num_inference_steps, original_inference_steps=None, strength=1.0):  # :330-450 (2.2)
+        original_steps = original_inference_steps if original_inference_steps is not None else self.original_inference_steps
+        if original_steps > self.num_train_timesteps:
+            raise ValueError("original_steps larger than num_train_timesteps")
+        k = self.num_train_timesteps // original_steps
+        lcm_origin_timesteps = np.asarray(list(range(1, int(original_steps * strength) + 1))) * k - 1
+        skipping_step = len(lcm_origin_timesteps) // num_inference_steps
+        if skipping_step < 1 or num_inference_steps > original_steps:
+            raise ValueError("num_inference_steps too large for the original schedule")
+        self.num_inference_steps = num_inference_steps
+        lcm_origin_timesteps = lcm_origin_timesteps[::-1].copy()
+        inference_indices = np.linspace(0, len(lcm_origin_timesteps), num=num_inference_steps, endpoint=False)
+        inference_indices = np.floor(inference_indices).astype(np.int64)
+        self.timesteps = torch.from_numpy(lcm_origin_timesteps[inference_indices].astype(np.int64))
+        self._step_index = None
+
+    def get_scalings_for_boundary_condition_discrete(self, timestep):  # :453-459 (int64 tensor * float -> fp32 tensor)
+        sigma_data = 0.5
+        scaled_timestep = torch.as_tensor(timestep).to(torch.float32) * self.timestep_scaling
+        c_skip = sigma_data ** 2 / (scaled_timestep ** 2 + sigma_data ** 2)
+        c_out = scaled_timestep / pow_half(scaled_timestep ** 2 + sigma_data ** 2)
+        return c_skip, c_out
+
+    def step(self, model_output, timestep, sample, noise=None):  # :461-549
+        timestep = int(timestep)
+        if self._step_index is None:
+            cand = (self.timesteps == timestep).nonzero()
+            self._step_index = (cand[1] if len(cand) > 1 else cand[0]).item()
+        prev_step_index = self._step_index + 1
+        prev_timestep = int(self.timesteps[prev_step_index]) if prev_step_index < len(self.timesteps) else timestep
+        alpha_prod_t = self.alphas_cumprod[timestep]
+        alpha_prod_t_prev = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        beta_prod_t, beta_prod_t_prev = 1 - alpha_prod_t, 1 - alpha_prod_t_prev
+        c_skip, c_out = self.get_scalings_for_boundary_condition_discrete(timestep)
+        if self.prediction_type == "epsilon":
+            x0 = (sample - pow_half(beta_prod_t) * model_output) / pow_half(alpha_prod_t)
+        elif self.prediction_type == "sample":
+            x0 = model_output
+        elif self.prediction_type == "v_prediction":
+            x0 = pow_half(alpha_prod_t) * sample - pow_half(beta_prod_t) * model_output
+        else:
+            raise ValueError(self.prediction_type)
+        if self.clip_sample:
+            x0 = x0.clip(-self.clip_sample_range, self.clip_sample_range)
+        denoised = c_out * x0 + c_skip * sample
+        if self._step_index != self.num_inference_steps - 1:
+            assert noise is not None, "multi-step LCM needs the caller's noise tensor"
+            prev_sample = pow_half(alpha_prod_t_prev) * denoised + pow_half(beta_prod_t_prev) * noise
+        else:
+            prev_sample = denoised
+        self._step_index += 1
+        return prev_sample, denoised
+
+    def step_scalars(self, timestep):
+        """(sqrt(a_t), sqrt(1-a_t), c_skip, c_out, sqrt(a_prev), sqrt(1-a_prev), is_last) exactly as step() uses them."""
+        timestep = int(timestep)
+        idx = self._step_index
+        if idx is None:
+            cand = (self.timesteps == timestep).nonzero()
+            idx = (cand[1] if len(cand) > 1 else cand[0]).item()
+        prev_timestep = int(self.timesteps[idx + 1]) if idx + 1 < len(self.timesteps) else timestep
+        a_t = self.alphas_cumprod[timestep]
+        a_p = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        c_skip, c_out = self.get_scalings_for_boundary_condition_discrete(timestep)
+        return (pow_half(a_t).item(), pow_half(1 - a_t).item(), c_skip.item(), c_out.item(), pow_half(a_p).item(),
+                pow_half(1 - a_p).item(), idx == self.num_inference_steps - 1)
+
+
 class FlowMatchEulerDiscreteScheduler:
     """scheduling_flow_match_euler_discrete.py: __init__ :64-83, set_timesteps :140-163, step :187-282."""
     order = 1

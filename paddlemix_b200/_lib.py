@@ -69,6 +69,12 @@ SIGNATURES = {
                                   c_void_p],
     "b200mix_ddim_step": [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_int64, c_float, c_float,
                           c_float, c_float, c_void_p],
+    "b200mix_ddim_step_ex": [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_int64, c_float, c_float,
+                             c_float, c_float, c_int32, c_float, c_void_p],
+    "b200mix_lcm_step": [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float,
+                         c_float, c_float, c_float, c_float, c_float, c_int32, c_float, c_void_p],
+    "b200mix_cfg_rescale_ratio": [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_int64, c_int64, c_void_p],
+    "b200mix_cfg_combine": [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_float, c_int64, c_void_p, c_int64, c_void_p],
     "b200mix_euler_step": [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_int64, c_float, c_float,
                            c_void_p],
     "b200mix_scale_model_input": [c_void_p, c_void_p, c_int64, c_float, c_void_p],

@@ -271,6 +271,108 @@ __global__ void ddim_step_kernel(const void* __restrict__ eps_u, const void* __r
   }
 }
 
+// DDIM step for every prediction type (scheduling_ddim.py:424-443) with optional clipping of the predicted x0
+// (:446-452), eta = 0; same operation order as the reference, every operation rounded individually.
+//   epsilon      x0 = (x - sb_t*m) / sa_t            eps = m
+//   sample       x0 = m                               eps = (x - sa_t*x0) / sb_t
+//   v_prediction x0 = sa_t*x - sb_t*m                 eps = sa_t*m + sb_t*x
+//   x_prev = sa_p * clip(x0) + sb_p * eps            (use_clipped_model_output = False: eps is NOT re-derived)
+__global__ void ddim_step_ex_kernel(const void* __restrict__ m_u, const void* __restrict__ m_c, int m_fp32, float guidance,
+                                    const float* __restrict__ x, float* __restrict__ x_prev, long long n, float sa_t,
+                                    float sb_t, float sa_p, float sb_p, int pred_type, float clip) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float m = load_any(m_u, i, m_fp32);
+    if (m_c) {
+      const float mc = load_any(m_c, i, m_fp32);
+      m = __fadd_rn(m, __fmul_rn(guidance, __fsub_rn(mc, m)));
+    }
+    const float xi = x[i];
+    float x0, e;
+    if (pred_type == 0) {
+      x0 = __fdiv_rn(__fsub_rn(xi, __fmul_rn(sb_t, m)), sa_t);
+      e = m;
+    } else if (pred_type == 1) {
+      x0 = m;
+      e = __fdiv_rn(__fsub_rn(xi, __fmul_rn(sa_t, x0)), sb_t);
+    } else {
+      x0 = __fsub_rn(__fmul_rn(sa_t, xi), __fmul_rn(sb_t, m));
+      e = __fadd_rn(__fmul_rn(sa_t, m), __fmul_rn(sb_t, xi));
+    }
+    if (clip > 0.0f) x0 = fminf(fmaxf(x0, -clip), clip);
+    x_prev[i] = __fadd_rn(__fmul_rn(sa_p, x0), __fmul_rn(sb_p, e));
+  }
+}
+
+// LCMScheduler.step (scheduling_lcm.py:468-545): x0 from the model output (as above), optional clip,
+// denoised = c_out*x0 + c_skip*x, then x_prev = sa_p*denoised + sb_p*noise (multi-step; the noise tensor is the
+// caller's randn) or x_prev = denoised on the final step (noise == NULL).
+__global__ void lcm_step_kernel(const void* __restrict__ m_u, const void* __restrict__ m_c, int m_fp32, float guidance,
+                                const float* __restrict__ x, const float* __restrict__ noise, float* __restrict__ x_prev,
+                                float* __restrict__ denoised_out, long long n, float sa_t, float sb_t, float c_skip,
+                                float c_out, float sa_p, float sb_p, int pred_type, float clip) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float m = load_any(m_u, i, m_fp32);
+    if (m_c) {
+      const float mc = load_any(m_c, i, m_fp32);
+      m = __fadd_rn(m, __fmul_rn(guidance, __fsub_rn(mc, m)));
+    }
+    const float xi = x[i];
+    float x0;
+    if (pred_type == 0) x0 = __fdiv_rn(__fsub_rn(xi, __fmul_rn(sb_t, m)), sa_t);
+    else if (pred_type == 1) x0 = m;
+    else x0 = __fsub_rn(__fmul_rn(sa_t, xi), __fmul_rn(sb_t, m));
+    if (clip > 0.0f) x0 = fminf(fmaxf(x0, -clip), clip);
+    const float den = __fadd_rn(__fmul_rn(c_out, x0), __fmul_rn(c_skip, xi));
+    if (denoised_out) denoised_out[i] = den;
+    x_prev[i] = noise ? __fadd_rn(__fmul_rn(sa_p, den), __fmul_rn(sb_p, noise[i])) : den;
+  }
+}
+
+// rescale_noise_cfg (pipeline_stable_diffusion.py:69-80; SDXL pipeline_stable_diffusion_xl.py:1061-1067), first half:
+// per sample b, ratio[b] = std(noise_pred_text[b]) / std(noise_cfg[b]) over all non-batch axes (unbiased std, Paddle's
+// default), with noise_cfg = u + g*(c - u). One CTA per sample, double accumulators, fixed reduction order.
+__global__ void __launch_bounds__(256) cfg_rescale_ratio_kernel(const void* __restrict__ e_u, const void* __restrict__ e_c,
+                                                               int fp32, float guidance, float* __restrict__ ratio,
+                                                               long long nps) {
+  __shared__ double sh[4][256];
+  const long long base = static_cast<long long>(blockIdx.x) * nps;
+  double st = 0.0, qt = 0.0, sc = 0.0, qc = 0.0;
+  for (long long i = threadIdx.x; i < nps; i += blockDim.x) {
+    const float u = load_any(e_u, base + i, fp32), c = load_any(e_c, base + i, fp32);
+    const float cfg = __fadd_rn(u, __fmul_rn(guidance, __fsub_rn(c, u)));
+    st += c, qt += (double)c * c, sc += cfg, qc += (double)cfg * cfg;
+  }
+  sh[0][threadIdx.x] = st, sh[1][threadIdx.x] = qt, sh[2][threadIdx.x] = sc, sh[3][threadIdx.x] = qc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o)
+      for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = (double)nps;
+    const double vt = (sh[1][0] - sh[0][0] * sh[0][0] / n) / (n - 1.0);
+    const double vc = (sh[3][0] - sh[2][0] * sh[2][0] / n) / (n - 1.0);
+    ratio[blockIdx.x] = (float)(sqrt(vt > 0.0 ? vt : 0.0) / sqrt(vc > 0.0 ? vc : 0.0));
+  }
+}
+
+// second half: out = u + g*(c - u), then (ratio given) out = gr * (out * ratio[b]) + (1 - gr) * out   (fp32 output)
+__global__ void cfg_combine_kernel(const void* __restrict__ e_u, const void* __restrict__ e_c, int fp32, float guidance,
+                                   const float* __restrict__ ratio, float gr, long long nps, float* __restrict__ out,
+                                   long long n) {
+  const float one_minus = __fsub_rn(1.0f, gr);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float u = load_any(e_u, i, fp32), c = load_any(e_c, i, fp32);
+    float cfg = __fadd_rn(u, __fmul_rn(guidance, __fsub_rn(c, u)));
+    if (ratio) {
+      const float resc = __fmul_rn(cfg, __ldg(ratio + i / nps));
+      cfg = __fadd_rn(__fmul_rn(gr, resc), __fmul_rn(one_minus, cfg));
+    }
+    out[i] = cfg;
+  }
+}
+
 // EulerDiscreteScheduler.scale_model_input (scheduling_euler_discrete.py:218-241): sample / ((sigma^2 + 1) ** 0.5), the
 // denominator computed on the host in fp32; an IEEE division here, like the reference's tensor / 0-d tensor.
 __global__ void scale_model_input_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float denom) {
@@ -514,6 +616,55 @@ extern "C" int b200mix_ddim_step(const void* eps_u, const void* eps_c, int32_t e
   B200_CHECK_ARG(eps_u && x && x_prev && n > 0, "ddim_step: bad arguments");
   ddim_step_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(eps_u, eps_c, eps_fp32, guidance, x, x_prev, n,
                                                            sqrt_alpha_t, sqrt_beta_t, sqrt_alpha_prev, sqrt_beta_prev);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_ddim_step_ex(const void* m_u, const void* m_c, int32_t m_fp32, float guidance, const float* x,
+                                    float* x_prev, int64_t n, float sqrt_alpha_t, float sqrt_beta_t,
+                                    float sqrt_alpha_prev, float sqrt_beta_prev, int32_t prediction_type,
+                                    float clip_sample_range, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(m_u && x && x_prev && n > 0, "ddim_step_ex: bad arguments");
+  B200_CHECK_ARG(prediction_type >= 0 && prediction_type <= 2, "ddim_step_ex: prediction_type must be 0 (epsilon), 1 "
+                 "(sample) or 2 (v_prediction)");
+  ddim_step_ex_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(m_u, m_c, m_fp32, guidance, x, x_prev, n, sqrt_alpha_t,
+                                                              sqrt_beta_t, sqrt_alpha_prev, sqrt_beta_prev,
+                                                              prediction_type, clip_sample_range);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_lcm_step(const void* m_u, const void* m_c, int32_t m_fp32, float guidance, const float* x,
+                                const float* noise, float* x_prev, float* denoised, int64_t n, float sqrt_alpha_t,
+                                float sqrt_beta_t, float c_skip, float c_out, float sqrt_alpha_prev, float sqrt_beta_prev,
+                                int32_t prediction_type, float clip_sample_range, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(m_u && x && x_prev && n > 0, "lcm_step: bad arguments");
+  B200_CHECK_ARG(prediction_type >= 0 && prediction_type <= 2, "lcm_step: prediction_type must be 0, 1 or 2");
+  lcm_step_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(m_u, m_c, m_fp32, guidance, x, noise, x_prev, denoised, n,
+                                                          sqrt_alpha_t, sqrt_beta_t, c_skip, c_out, sqrt_alpha_prev,
+                                                          sqrt_beta_prev, prediction_type, clip_sample_range);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_cfg_rescale_ratio(const void* eps_u, const void* eps_c, int32_t eps_fp32, float guidance,
+                                         float* ratio, int64_t B, int64_t n_per_sample, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(eps_u && eps_c && ratio && B > 0 && n_per_sample > 1, "cfg_rescale_ratio: bad arguments");
+  cfg_rescale_ratio_kernel<<<(unsigned)B, 256, 0, ST(stream)>>>(eps_u, eps_c, eps_fp32, guidance, ratio, n_per_sample);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_cfg_combine(const void* eps_u, const void* eps_c, int32_t eps_fp32, float guidance,
+                                   const float* ratio, float guidance_rescale, int64_t n_per_sample, float* out, int64_t n,
+                                   void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(eps_u && eps_c && out && n > 0 && n_per_sample > 0, "cfg_combine: bad arguments");
+  cfg_combine_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(eps_u, eps_c, eps_fp32, guidance, ratio, guidance_rescale,
+                                                             n_per_sample, out, n);
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -393,6 +393,58 @@ def ddim_step(eps_u, eps_c, guidance, x, sa_t, sb_t, sa_p, sb_p, out=None):
     return out
 
 
+PRED_TYPES = {"epsilon": 0, "sample": 1, "v_prediction": 2}
+
+
+def ddim_step_ex(m_u, m_c, guidance, x, sa_t, sb_t, sa_p, sb_p, prediction_type="epsilon", clip_sample_range=0.0, out=None):
+    """DDIM step for any prediction_type, optional x0 clipping (clip_sample_range > 0), fused CFG combine."""
+    _req(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.b200mix_ddim_step_ex(_p(m_u), _p(m_c), 1 if m_u.dtype == torch.float32 else 0, float(guidance), _p(x), _p(out),
+                                   x.numel(), float(sa_t), float(sb_t), float(sa_p), float(sb_p),
+                                   PRED_TYPES[prediction_type], float(clip_sample_range), _stream()), "b200mix_ddim_step_ex")
+    _count()
+    return out
+
+
+def lcm_step(m_u, m_c, guidance, x, noise, sa_t, sb_t, c_skip, c_out, sa_p, sb_p, prediction_type="epsilon",
+             clip_sample_range=0.0, out=None, denoised=None):
+    """LCMScheduler.step; noise None = final step (x_prev = denoised)."""
+    _req(x, torch.float32, "x")
+    if noise is not None:
+        _req(noise, torch.float32, "noise")
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.b200mix_lcm_step(_p(m_u), _p(m_c), 1 if m_u.dtype == torch.float32 else 0, float(guidance), _p(x), _p(noise),
+                               _p(out), _p(denoised), x.numel(), float(sa_t), float(sb_t), float(c_skip), float(c_out),
+                               float(sa_p), float(sb_p), PRED_TYPES[prediction_type], float(clip_sample_range), _stream()),
+          "b200mix_lcm_step")
+    _count()
+    return out
+
+
+def cfg_combine(eps_u, eps_c, guidance, guidance_rescale=0.0, out=None):
+    """noise_pred_uncond + g * (noise_pred_text - noise_pred_uncond), then rescale_noise_cfg when guidance_rescale > 0
+    (pipeline_stable_diffusion.py:69-80, :882-888). eps_*: [B, ...] bf16 / fp32 contiguous. Returns fp32."""
+    assert eps_u.shape == eps_c.shape and eps_u.dtype == eps_c.dtype and eps_u.is_contiguous() and eps_c.is_contiguous()
+    B = eps_u.shape[0]
+    nps = eps_u.numel() // B
+    fp32 = 1 if eps_u.dtype == torch.float32 else 0
+    if out is None:
+        out = torch.empty(eps_u.shape, device=eps_u.device, dtype=torch.float32)
+    ratio = None
+    if guidance_rescale > 0.0:
+        ratio = torch.empty(B, device=eps_u.device, dtype=torch.float32)
+        check(lib.b200mix_cfg_rescale_ratio(_p(eps_u), _p(eps_c), fp32, float(guidance), _p(ratio), B, nps, _stream()),
+              "b200mix_cfg_rescale_ratio")
+        _count()
+    check(lib.b200mix_cfg_combine(_p(eps_u), _p(eps_c), fp32, float(guidance), _p(ratio), float(guidance_rescale), nps,
+                                  _p(out), eps_u.numel(), _stream()), "b200mix_cfg_combine")
+    _count()
+    return out
+
+
 def euler_step(v_u, v_c, guidance, x, sigma, dt, out=None):
     _req(x, torch.float32, "x")
     if out is None:

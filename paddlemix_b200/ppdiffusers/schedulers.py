@@ -28,7 +28,14 @@ class DDIMScheduler:
 
     def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.0001, beta_end: float = 0.02,
                  beta_schedule: str = "linear", clip_sample: bool = True, set_alpha_to_one: bool = True,
-                 steps_offset: int = 0, prediction_type: str = "epsilon", timestep_spacing: str = "leading"):
+                 steps_offset: int = 0, prediction_type: str = "epsilon", timestep_spacing: str = "leading",
+                 clip_sample_range: float = 1.0, thresholding: bool = False):
+        if thresholding:
+            raise NotImplementedError("dynamic thresholding (pixel-space models) is outside the latent-diffusion hot path")
+        if prediction_type not in ("epsilon", "sample", "v_prediction"):
+            raise ValueError(f"prediction_type given as {prediction_type} must be one of `epsilon`, `sample`, or"
+                             " `v_prediction`")
+        self.clip_sample_range = clip_sample_range
         if beta_schedule == "linear":
             self.betas = _linspace_f32(beta_start, beta_end, num_train_timesteps)
         elif beta_schedule == "scaled_linear":
@@ -98,12 +105,145 @@ class DDIMScheduler:
              out=None):
         """sample, result: fp32 CUDA tensors; model_output: bf16/fp32 CUDA tensor of the same numel (any layout that
         matches `sample` elementwise). With model_output_cond the CFG combine is fused into the same kernel."""
-        if eta != 0.0 or self.prediction_type != "epsilon" or self.clip_sample:
-            raise NotImplementedError("b200mix DDIM step covers eta=0, epsilon prediction, clip_sample=False "
-                                      "(the Stable Diffusion sampling configuration)")
+        if eta != 0.0:
+            raise NotImplementedError("b200mix DDIM step covers eta = 0 (the deterministic sampler the pipelines use)")
         from .. import ops
         sa_t, sb_t, sa_p, sb_p = self.step_scalars(timestep)
-        return ops.ddim_step(model_output, model_output_cond, guidance_scale, sample, sa_t, sb_t, sa_p, sb_p, out=out)
+        if self.prediction_type == "epsilon" and not self.clip_sample:  # the Stable Diffusion configuration
+            return ops.ddim_step(model_output, model_output_cond, guidance_scale, sample, sa_t, sb_t, sa_p, sb_p, out=out)
+        # v_prediction (SD 2.x), sample prediction, clip_sample (scheduling_ddim.py:424-452)
+        return ops.ddim_step_ex(model_output, model_output_cond, guidance_scale, sample, sa_t, sb_t, sa_p, sb_p,
+                                self.prediction_type, self.clip_sample_range if self.clip_sample else 0.0, out=out)
+
+
+class LCMScheduler:
+    """ppdiffusers.LCMScheduler (scheduling_lcm.py:133-560) for latent consistency models: host-side fp32 scalars
+    (numpy, bit-identical to the reference's 0-d fp32 tensors), one fused device kernel per step
+    (b200mix_lcm_step: CFG combine, x0, clip, boundary-condition blend, noise injection)."""
+
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012,
+                 beta_schedule: str = "scaled_linear", original_inference_steps: int = 50, clip_sample: bool = False,
+                 clip_sample_range: float = 1.0, set_alpha_to_one: bool = True, steps_offset: int = 0,
+                 prediction_type: str = "epsilon", thresholding: bool = False, timestep_spacing: str = "leading",
+                 timestep_scaling: float = 10.0, rescale_betas_zero_snr: bool = False):
+        if thresholding or rescale_betas_zero_snr:
+            raise NotImplementedError("LCMScheduler(b200): thresholding / rescale_betas_zero_snr are outside the hot path")
+        if prediction_type not in ("epsilon", "sample", "v_prediction"):
+            raise ValueError(f"prediction_type given as {prediction_type} must be one of `epsilon`, `sample` or"
+                             " `v_prediction` for `LCMScheduler`.")
+        if beta_schedule == "linear":
+            self.betas = _linspace_f32(beta_start, beta_end, num_train_timesteps)
+        elif beta_schedule == "scaled_linear":
+            self.betas = _linspace_f32(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps) ** 2
+        elif beta_schedule == "squaredcos_cap_v2":
+            self.betas = _betas_for_alpha_bar(num_train_timesteps)
+        else:
+            raise NotImplementedError(f"{beta_schedule} does is not implemented for {self.__class__}")
+        self.alphas = (f32(1.0) - self.betas).astype(f32)
+        self.alphas_cumprod = _cumprod_f32(self.alphas)
+        self.final_alpha_cumprod = f32(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.num_train_timesteps, self.original_inference_steps = num_train_timesteps, original_inference_steps
+        self.clip_sample, self.clip_sample_range = clip_sample, clip_sample_range
+        self.prediction_type, self.timestep_scaling = prediction_type, timestep_scaling
+        self.num_inference_steps: Optional[int] = None
+        self.timesteps = np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64)
+        self._step_index = None
+
+    @property
+    def step_index(self):
+        return self._step_index
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def set_timesteps(self, num_inference_steps: Optional[int] = None, original_inference_steps: Optional[int] = None,
+                      timesteps=None, strength: float = 1.0):
+        if num_inference_steps is None and timesteps is None:
+            raise ValueError("Must pass exactly one of `num_inference_steps` or `custom_timesteps`.")
+        if num_inference_steps is not None and timesteps is not None:
+            raise ValueError("Can only pass one of `num_inference_steps` or `custom_timesteps`.")
+        original_steps = original_inference_steps if original_inference_steps is not None else self.original_inference_steps
+        if original_steps > self.num_train_timesteps:
+            raise ValueError(f"`original_steps`: {original_steps} cannot be larger than `self.config.train_timesteps`:"
+                             f" {self.num_train_timesteps} as the unet model trained with this scheduler can only handle"
+                             f" maximal {self.num_train_timesteps} timesteps.")
+        k = self.num_train_timesteps // original_steps
+        origin = np.asarray(list(range(1, int(original_steps * strength) + 1))) * k - 1
+        if timesteps is not None:
+            for i in range(1, len(timesteps)):
+                if timesteps[i] >= timesteps[i - 1]:
+                    raise ValueError("`custom_timesteps` must be in descending order.")
+            if timesteps[0] >= self.num_train_timesteps:
+                raise ValueError(f"`timesteps` must start before `self.config.train_timesteps`: {self.num_train_timesteps}.")
+            ts = np.array(timesteps, dtype=np.int64)
+            self.num_inference_steps = len(ts)
+            init_timestep = min(int(self.num_inference_steps * strength), self.num_inference_steps)
+            ts = ts[max(self.num_inference_steps - init_timestep, 0) * self.order:]
+        else:
+            if num_inference_steps > self.num_train_timesteps:
+                raise ValueError(f"`num_inference_steps`: {num_inference_steps} cannot be larger than "
+                                 f"`self.config.train_timesteps`: {self.num_train_timesteps}")
+            if len(origin) // num_inference_steps < 1:
+                raise ValueError(f"The combination of `original_steps x strength`: {original_steps} x {strength} is smaller "
+                                 f"than `num_inference_steps`: {num_inference_steps}.")
+            if num_inference_steps > original_steps:
+                raise ValueError(f"`num_inference_steps`: {num_inference_steps} cannot be larger than "
+                                 f"`original_inference_steps`: {original_steps}")
+            self.num_inference_steps = num_inference_steps
+            origin = origin[::-1].copy()
+            idx = np.floor(np.linspace(0, len(origin), num=num_inference_steps, endpoint=False)).astype(np.int64)
+            ts = origin[idx]
+        self.timesteps = ts.astype(np.int64)
+        self._step_index = None
+
+    def _init_step_index(self, timestep):
+        cand = np.nonzero(self.timesteps == int(timestep))[0]
+        self._step_index = int(cand[1] if len(cand) > 1 else cand[0])
+
+    def get_scalings_for_boundary_condition_discrete(self, timestep):
+        """scheduling_lcm.py:453-459 in fp32 (an int64 0-d tensor times a Python float is an fp32 tensor in Paddle)."""
+        sd2 = f32(0.5 ** 2)
+        st = f32(f32(int(timestep)) * f32(self.timestep_scaling))
+        den = f32(f32(st * st) + sd2)
+        return f32(sd2 / den), f32(st / np.sqrt(den, dtype=f32))
+
+    def step_scalars(self, timestep):
+        """(sqrt(a_t), sqrt(1-a_t), c_skip, c_out, sqrt(a_prev), sqrt(1-a_prev), is_last_step) as fp32 values."""
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the "
+                             "scheduler")
+        timestep = int(timestep)
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        nxt = self._step_index + 1
+        prev_timestep = int(self.timesteps[nxt]) if nxt < len(self.timesteps) else timestep
+        a_t = self.alphas_cumprod[timestep]
+        a_p = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        c_skip, c_out = self.get_scalings_for_boundary_condition_discrete(timestep)
+        return (float(np.sqrt(a_t, dtype=f32)), float(np.sqrt(f32(f32(1) - a_t), dtype=f32)), float(c_skip), float(c_out),
+                float(np.sqrt(a_p, dtype=f32)), float(np.sqrt(f32(f32(1) - a_p), dtype=f32)),
+                self._step_index == self.num_inference_steps - 1)
+
+    def step(self, model_output, timestep, sample, generator=None, model_output_cond=None, guidance_scale=0.0,
+             noise=None, out=None, return_denoised=False):
+        """sample / result: fp32 CUDA tensors. Multi-step sampling injects z ~ N(0, I) (scheduling_lcm.py:538-545): pass
+        `noise` (fp32 CUDA tensor) or a torch `generator` (a CUDA generator of the sample's device); the final step is
+        deterministic. With return_denoised also returns LCMSchedulerOutput.denoised."""
+        import torch
+
+        from .. import ops
+        sa_t, sb_t, c_skip, c_out, sa_p, sb_p, last = self.step_scalars(timestep)
+        if not last and noise is None:
+            noise = torch.randn(sample.shape, device=sample.device, dtype=torch.float32, generator=generator)
+        den = torch.empty_like(sample) if return_denoised else None
+        res = ops.lcm_step(model_output, model_output_cond, guidance_scale, sample, None if last else noise, sa_t, sb_t,
+                           c_skip, c_out, sa_p, sb_p, self.prediction_type,
+                           self.clip_sample_range if self.clip_sample else 0.0, out=out, denoised=den)
+        self._step_index += 1
+        return (res, den) if return_denoised else res
 
 
 def _linspace_f32(start, end, n):

@@ -53,6 +53,14 @@ dpm = {  # ppdiffusers/tests/schedulers/test_scheduler_dpm_multi.py:33-52 (confi
     "full_loop_with_noise": {"t_start": 5, "sum": 318.4111, "mean": 0.4146},
     "sum_atol": 1e-2, "mean_atol": 1e-3,
 }
+lcm = {  # ppdiffusers/tests/schedulers/test_scheduler_lcm.py:28-38 (config), :239-247 (one-step full loop, RNG-free)
+    "config": {"num_train_timesteps": 1000, "beta_start": 0.00085, "beta_end": 0.012, "beta_schedule": "scaled_linear",
+               "prediction_type": "epsilon"},
+    "one_step": {"sum": 18.7097, "mean": 0.0244}, "atol": 1e-3,
+    "one_step_timesteps": [999],  # scheduling_lcm.py:430-437 with original_inference_steps = 50
+    "ten_step_timesteps": [999, 899, 799, 699, 599, 499, 399, 299, 199, 99],
+}
+json.dump(lcm, open(os.path.join(HERE, "lcm_goldens.json"), "w"), indent=1)
 json.dump(dpm, open(os.path.join(HERE, "dpm_multistep_goldens.json"), "w"), indent=1)
 json.dump(euler, open(os.path.join(HERE, "euler_goldens.json"), "w"), indent=1)
 json.dump(ddim, open(os.path.join(HERE, "ddim_goldens.json"), "w"), indent=1)

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import torch
 
-from oracle.schedulers import DDIMScheduler, DPMSolverMultistepScheduler, EulerDiscreteScheduler
+from oracle.schedulers import DDIMScheduler, DPMSolverMultistepScheduler, EulerDiscreteScheduler, LCMScheduler
 from oracle.unet import get_timestep_embedding
 
 
@@ -154,3 +154,20 @@ def test_sinusoid_hardcoded_goldens():  # :90-115
     for case in SIN_GOLD["cases"]:
         t = get_timestep_embedding(ts, SIN_GOLD["embedding_dim"], **case["kwargs"])
         assert torch.allclose(t[r0:r1, c0:c1].flatten(), torch.tensor(case["values"]), atol=SIN_GOLD["atol"])
+
+
+def test_lcm_one_step_full_loop_golden():
+    """test_scheduler_lcm.py:222-247: the one-step loop draws no noise (the final step is deterministic), so its golden
+    (sum 18.7097, mean 0.0244) is RNG-free and pins the oracle's LCMScheduler; the 10-step golden (:249-257) depends on
+    Paddle's generator stream and cannot be reproduced."""
+    gold = json.load(open(os.path.join(GOLD, "lcm_goldens.json")))
+    sch = LCMScheduler(**gold["config"])
+    sch.set_timesteps(1)
+    assert sch.timesteps.tolist() == gold["one_step_timesteps"]
+    sample = dummy_sample_deter()
+    for t in sch.timesteps:
+        sample, _ = sch.step(dummy_model(sample, t), t, sample)
+    assert abs(sample.abs().sum().item() - gold["one_step"]["sum"]) < gold["atol"]
+    assert abs(sample.abs().mean().item() - gold["one_step"]["mean"]) < gold["atol"]
+    sch.set_timesteps(10)
+    assert sch.timesteps.tolist() == gold["ten_step_timesteps"]

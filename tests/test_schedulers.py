@@ -140,3 +140,48 @@ def test_dpm_solver_rejects_what_has_no_device_path():
                 dict(thresholding=True)):
         with pytest.raises(NotImplementedError):
             S.DPMSolverMultistepScheduler(**bad)
+
+
+LCM = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", prediction_type="epsilon")
+
+
+@pytest.mark.parametrize("kw", [LCM, dict(LCM, prediction_type="v_prediction", clip_sample=True), dict(LCM, set_alpha_to_one=False)])
+@pytest.mark.parametrize("n", [1, 4, 10, 50])
+def test_lcm_bit_exact(kw, n):
+    """Host LCMScheduler (numpy fp32) vs the oracle restatement of scheduling_lcm.py: timesteps and per-step scalars."""
+    o, s = O.LCMScheduler(**kw), S.LCMScheduler(**kw)
+    assert np.array_equal(o.alphas_cumprod.numpy(), s.alphas_cumprod)
+    o.set_timesteps(n), s.set_timesteps(n)
+    assert o.timesteps.tolist() == s.timesteps.tolist()
+    for i, t in enumerate(s.timesteps):
+        o._step_index = s._step_index = i
+        assert o.step_scalars(int(t)) == s.step_scalars(int(t)), (kw, int(t))
+
+
+def test_lcm_scalars_reproduce_step():
+    o = O.LCMScheduler(**LCM)
+    o.set_timesteps(4)
+    g = torch.Generator().manual_seed(0)
+    x, e, z = (torch.randn(2, 4, 16, 16, generator=g) for _ in range(3))
+    for t in o.timesteps:
+        sa_t, sb_t, c_skip, c_out, sa_p, sb_p, last = o.step_scalars(int(t))
+        f = lambda v: torch.tensor(v, dtype=torch.float32)  # noqa: E731
+        den = f(c_out) * ((x - f(sb_t) * e) / f(sa_t)) + f(c_skip) * x
+        mine = den if last else f(sa_p) * den + f(sb_p) * z
+        ref, den_ref = o.step(e, t, x, noise=z)
+        assert torch.equal(mine, ref) and torch.equal(den, den_ref)
+        x = ref
+
+
+def test_lcm_errors_mirror_reference():
+    s = S.LCMScheduler(**LCM)
+    with pytest.raises(ValueError, match="exactly one"):
+        s.set_timesteps()
+    with pytest.raises(ValueError, match="Can only pass one"):
+        s.set_timesteps(num_inference_steps=2, timesteps=[999, 499])
+    with pytest.raises(ValueError, match="descending"):
+        s.set_timesteps(timesteps=[499, 999])
+    s.set_timesteps(timesteps=[999, 759, 499, 259])
+    assert s.timesteps.tolist() == [999, 759, 499, 259] and s.num_inference_steps == 4
+    with pytest.raises(ValueError):
+        S.DDIMScheduler(prediction_type="nope")
