@@ -345,6 +345,23 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return r;
 }
 
+// One lane of a CONVERGED warp (all 32 lanes must reach this point). The single-thread roles (TMA producer, MMA issuer)
+// run their loops with the whole warp and put only the issuing instructions under `if (elect_one_sync())`: under an
+// `if (lane == 0)` branch the compiler treats the code as thread-divergent and wraps every tcgen05.mma / TMA instruction
+// in an election loop (ELECT + 5-7 R2UR.BROADCAST + BRA.U.ANY, ~80 cycles per instruction) because their operands must
+// live in uniform registers; with a converged warp the descriptors are computed on the uniform datapath and the
+// instructions issue back to back. Measured (ATTN_PROF build): the attention issuer spent 82 % of a key block issuing
+// 24 MMAs; see DESIGN.md.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

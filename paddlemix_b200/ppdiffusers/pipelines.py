@@ -100,7 +100,7 @@ class StableDiffusionPipeline:
                  negative_prompt_embeds: Optional[torch.Tensor] = None, output_type: str = "latent",
                  added_cond_kwargs: Optional[Dict[str, torch.Tensor]] = None,
                  negative_added_cond_kwargs: Optional[Dict[str, torch.Tensor]] = None, callback_on_step_end=None,
-                 generator: Optional[torch.Generator] = None):
+                 generator: Optional[torch.Generator] = None, guidance_rescale: float = 0.0):
         if prompt is not None or negative_prompt is not None:
             raise NotImplementedError("text encoders are outside the hot path: pass prompt_embeds / negative_prompt_embeds")
         if prompt_embeds is None:
@@ -156,7 +156,12 @@ class StableDiffusionPipeline:
             else:
                 eps = self.unet.forward(model_in, float(t), ctx, added_cond_kwargs=added, return_dict=False)[0]
             first = False
-            if do_cfg:  # noise_pred_uncond + g*(noise_pred_text - noise_pred_uncond) (:882-884), fused with the step
+            if do_cfg and guidance_rescale > 0.0:
+                # rescale_noise_cfg (pipeline_stable_diffusion.py:69-80, :886-888; SDXL :1061-1067): the guided
+                # prediction is rescaled to the text branch's per-sample std before the scheduler step
+                guided = ops.cfg_combine(eps[:B], eps[B:], guidance_scale, guidance_rescale)
+                self.scheduler.step(guided, t, latents, out=nxt)
+            elif do_cfg:  # noise_pred_uncond + g*(noise_pred_text - noise_pred_uncond) (:882-884), fused with the step
                 self.scheduler.step(eps[:B], t, latents, model_output_cond=eps[B:], guidance_scale=guidance_scale, out=nxt)
             else:
                 self.scheduler.step(eps, t, latents, out=nxt)
