@@ -821,7 +821,13 @@ __device__ unsigned long long g_attn_prof[148 * 32];
 // 1/N of the exponentials off the quarter-rate MUFU pipe that bounds the D = 64 kernel (packed FADD2 / FFMA2 keep the
 // extra issue slots at 4 per element). Inputs are clamped to >= -125 (masked scores are -inf).
 #ifndef ATTN_POLY_EVERY
-#define ATTN_POLY_EVERY 0
+#define ATTN_POLY_EVERY 8  // measured (tools/attn_probe.py, S = 4096): 0 -> 808, 8 -> 830, 4 -> 804, 3 -> 770 TFLOP/s
+#endif
+#ifndef ATTN_EXP_TURNS
+#define ATTN_EXP_TURNS 0
+#endif
+#ifndef ATTN_QK_FIRST
+#define ATTN_QK_FIRST 0
 #endif
 __device__ __forceinline__ void poly_exp2_x2(uint64_t t2, float& e0, float& e1) {
   float t0, t1;
@@ -836,8 +842,8 @@ __device__ __forceinline__ void poly_exp2_x2(uint64_t t2, float& e0, float& e1) 
   float r0, r1, p0, p1;
   unpack_f32x2(r2, r0, r1);
   unpack_f32x2(p2, p0, p1);
-  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(r0) << 23));
-  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
+  e0 = t0 < -125.0f ? 0.0f : __uint_as_float(__float_as_uint(p0) + (__float_as_uint(r0) << 23));
+  e1 = t1 < -125.0f ? 0.0f : __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
 }
 
 template <int KS>
@@ -871,7 +877,8 @@ __global__ void __launch_bounds__(384, 1)
   uint64_t* k_empty = k_full + KS;
   uint64_t* v_full = k_empty + KS;
   uint64_t* v_empty = v_full + KS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + KS);
+  uint64_t* exp_turn = v_empty + KS;   // 2, 128 arrivals: whose turn it is to use the MUFU pipe (ATTN_EXP_TURNS)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(exp_turn + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -879,6 +886,7 @@ __global__ void __launch_bounds__(384, 1)
       mbar_init(&q_full[i], 1), mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1), mbar_init(&s_empty[i], 128);
       mbar_init(&p_full[i], 128), mbar_init(&pv_done[i], 1);
+      mbar_init(&exp_turn[i], 128);
     }
     for (int i = 0; i < KS; ++i) {
       mbar_init(&k_full[i], 1), mbar_init(&k_empty[i], 1);
@@ -1000,9 +1008,8 @@ __global__ void __launch_bounds__(384, 1)
             mbar_wait(&k_full[kst], kph);
             PROF_END(0);
           }
-          // both QK^T of the next block first (S must be back long before a warpgroup finishes its exponentials), then
-          // both PV of this block: with the per-tile order QK0 PV0 QK1 PV1 the in-order issuer sat in the wait for P0
-          // while S1 had long been drained, and the warpgroups waited ~190 cycles per block for S (ATTN_PROF build)
+#if ATTN_QK_FIRST
+          // variant: both QK^T of the next block first, then both PV of this block
           if (has_next) {
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
@@ -1039,6 +1046,51 @@ __global__ void __launch_bounds__(384, 1)
             __syncwarp();
           }
           if (++vst == KS) vst = 0, vph ^= 1;
+#else
+          // Order per block: QK0(s+1) PV0(s) QK1(s+1) PV1(s). The in-order issuer thereby releases S1(s+1) only after
+          // warpgroup 0 has finished the exponentials of block s (and S0(s+2) after warpgroup 1's), which keeps the two
+          // warpgroups STAGGERED: one drains S / takes its row max while the other feeds the MUFU pipe. Issuing both
+          // QK^T first (ATTN_QK_FIRST) lets the warpgroups drift into phase - both exponentiate, then both leave the
+          // MUFU pipe idle - and costs 15 % (808 -> 684 TFLOP/s at S = 4096), as does a strict alternation of the
+          // exponential phases (ATTN_EXP_TURNS: one warp per sub-partition cannot saturate the MUFU pipe alone).
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (has_next) {
+              PROF_BEGIN();
+              mbar_wait(&s_empty[t], sidx & 1);  // softmax warpgroup t has S_t(s) in registers
+              PROF_END(1 + t);
+              tc_fence_after();
+              if (elect_one_sync()) {
+                issue_qk(t, n2 & 1, kst);
+                umma_commit(&s_full[t]);
+                if (t == 1) {
+                  umma_commit(&k_empty[kst]);
+                  if (last_qk_of_item) umma_commit(&q_empty[n2 & 1]);
+                }
+              }
+              __syncwarp();
+              if (t == 1) {
+                if (++kst == KS) kst = 0, kph ^= 1;
+              }
+            }
+            PROF_BEGIN();
+            mbar_wait(&p_full[t], sidx & 1);  // P_t(s) is in TMEM (and the warpgroup is done with O_t)
+            PROF_END(3 + t);
+            PROF_BEGIN();
+            if (t == 0) mbar_wait(&v_full[vst], vph);
+            PROF_END(5);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              issue_pv(t, vst, j != 0);
+              umma_commit(&pv_done[t]);
+              if (t == 1) umma_commit(&v_empty[vst]);
+            }
+            __syncwarp();
+            if (t == 1) {
+              if (++vst == KS) vst = 0, vph ^= 1;
+            }
+          }
+#endif
         }
         nb = nb_next;
       }
@@ -1058,6 +1110,9 @@ __global__ void __launch_bounds__(384, 1)
     const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
     uint32_t sidx = 0;
     PROF_DECL;
+#if ATTN_EXP_TURNS
+    if (t == 1) mbar_arrive(&exp_turn[0]);  // the first turn belongs to warpgroup 0
+#endif
 #if ATTN_PROF
     const unsigned long long prof_start = clock64();
 #endif
@@ -1133,6 +1188,12 @@ __global__ void __launch_bounds__(384, 1)
         }
         // exponentials: (s * scale_log2 - m_scaled) two at a time (FFMA2), ex2 on the MUFU pipe, packed row sum
         // (FADD2), bf16 pairs straight back to TMEM as the A operand of the PV MMA
+#if ATTN_EXP_TURNS
+        // The two warpgroups take strict turns on the exponentials: one warp per sub-partition then has the MUFU pipe
+        // to itself (1024 cycles per block) while the other warpgroup drains S / takes its row max / waits for its MMAs.
+        // Left to themselves the warpgroups drift into phase (both exponentiate, then both idle the MUFU pipe).
+        mbar_wait(&exp_turn[t], sidx & 1);
+#endif
         PROF_BEGIN();
         const uint64_t nm2 = pack_f32x2(-m_scaled, -m_scaled);
         uint64_t sum2[2] = {0ull, 0ull};
@@ -1159,6 +1220,9 @@ __global__ void __launch_bounds__(384, 1)
         unpack_f32x2(sum2[0], a0, a1);
         unpack_f32x2(sum2[1], b0, b1);
         l += (a0 + a1) + (b0 + b1);
+#if ATTN_EXP_TURNS
+        mbar_arrive(&exp_turn[t ^ 1]);
+#endif
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&p_full[t]);
