@@ -121,8 +121,10 @@ int b200mix_sdpa(const void* q, const void* k, const void* v, void* o, int64_t B
 /* GroupNorm (+ optional SiLU) over NHWC bf16; the input may be the channel-concatenation [x1 | x2] of two tensors
  * (skip connections, unet_2d_blocks.py:2353-2356) which is thereby never materialised. x2 may be NULL (C2 = 0).
  * Replaces nn.GroupNorm + nonlinearity (resnet.py:667-692,760-786; transformer_2d.py:161; unet_2d_condition.py:1193).
- * y bf16 [B,H,W,C1+C2]. Two launches: per-CTA partial statistics (double, fixed reduction
- * order: bit-reproducible), then apply. `stats` = scratch of at least (4*num_sms + B) * groups * 16 bytes. */
+ * y bf16 [B,H,W,C1+C2]. Two launches: per-CTA partial statistics in double, reduced in a fixed order by the last
+ * CTA of each batch element (bit-reproducible), then apply. `stats` = scratch of at least
+ * (4*num_sms + 2*B) * groups * 16 + 4*B bytes that the caller ZERO-FILLS ONCE at allocation (it holds the arrival
+ * counters, which every call leaves at zero); one scratch per concurrently used stream. */
 int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2, int64_t C2, const float* gamma,
                            const float* beta, void* y, void* stats, int64_t stats_bytes, int64_t B, int64_t HW,
                            int32_t groups, float eps, int32_t silu, void* stream);
@@ -135,6 +137,12 @@ int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2, int64_t C
 int b200mix_layernorm(const void* x, const void* delta, const float* gate, void* resid_out, void* y,
                       const float* weight, const float* bias, const float* scale, const float* shift, int64_t ld_mod,
                       int64_t rows_per_group, int64_t M, int64_t N, float eps, int32_t rms, void* stream);
+
+/* Row softmax y[m, :] = softmax(x[m, :] * scale): fp32 scores [M, ldx] -> bf16 probabilities [M, ldy], N <= 51200.
+ * The attention of the VAE decoder's mid block (one 512-wide head over H*W tokens, ppdiffusers/models/vae.py:232-241;
+ * AttnProcessor, attention_processor.py:673-735) = score GEMM (fp32 out) -> this kernel -> PV GEMM. */
+int b200mix_softmax_rows(const float* x, void* y, int64_t M, int64_t N, int64_t ldx, int64_t ldy, float scale,
+                         void* stream);
 
 /* ---- small elementwise kernels ------------------------------------------------------------------------------ */
 

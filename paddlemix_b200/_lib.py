@@ -58,6 +58,7 @@ SIGNATURES = {
                                c_int64, c_int64, c_int32, c_float, c_int32, c_void_p],
     "b200mix_layernorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                           c_int64, c_int64, c_int64, c_int64, c_float, c_int32, c_void_p],
+    "b200mix_softmax_rows": [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p],
     "b200mix_timestep_embedding": [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_int32, c_float,
                                    c_float, c_float, c_void_p],
     "b200mix_activation": [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p],

@@ -641,11 +641,13 @@ static int g_gemm_pair = GEMM_PAIR_DEFAULT;
 
 static int pick_bn(long long tiles_m, long long N, int glu) {
   // cost = waves x time per tile; time per tile ~ BN / rate(BN). Rates are the measured mainloop rates of each tile
-  // width relative to BN=256 in CTA-pair mode (tools/bn_sweep.py, 16384x8192x2048: 1541 / 1448 / 1331 / 1202 / 1032 /
-  // 530 / 270 TFLOP/s): the per-SM operand fill (A tile + B half per k-chunk, ~60 B/clk) does not shrink with BN as
-  // fast as the MMA time does, so narrower tiles are only chosen when they avoid wave / N-padding waste.
+  // width relative to BN=256 in CTA-pair mode (tools/bn_sweep.py, 16384x8192x2048): the per-SM operand fill (A tile +
+  // B half per k-chunk, ~60 B/clk) does not shrink with BN as fast as the MMA time does, so narrower tiles are only
+  // chosen when they avoid wave / N-padding waste. (Round 1's table, 1541 / 1448 / 1331 / 1202 / 1032 / 530 / 270, was
+  // dominated by the ~80-cycle election loop the compiler put around every MMA issued from an `if (lane == 0)` region.)
   const int cands[7] = {256, 224, 192, 160, 128, 64, 32};
-  const double eff[7] = {1.00, 0.94, 0.87, 0.79, 0.68, 0.35, 0.18};
+  // round 2 (converged-warp MMA / TMA issue): 1617 / 1595 / 1559 / 1443 / 1337 / 780 / 405 TFLOP/s (profiles/r02_bn_sweep.txt)
+  const double eff[7] = {1.00, 0.985, 0.96, 0.89, 0.825, 0.48, 0.25};
   double best = 1e30;
   int best_bn = 256;
   const int clusters = num_sms() / 2;

@@ -6,6 +6,8 @@
 // nn.LayerNorm in BasicTransformerBlock (attention.py:307-350); the Triton ops fused_adaLN_scale_residual /
 // adaptive_layer_norm / rms_norm (paddlemix/triton_ops/triton_ops.py:702-755, 981-1027, 1198-1232) and
 // Qwen2RMSNorm (paddlemix/models/qwen2_vl/modeling_qwen2_vl.py:467-478).
+#include <algorithm>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -19,7 +21,16 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
                     pack_bf16x2(f[6], f[7]));
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// SiLU as x * sigmoid(x) = h + h * tanh(h), h = x / 2: ONE MUFU op (tanh.approx, relative error ~2^-11, below the
+// bf16 rounding of the output) and two FMA-pipe ops. The round-1 form x / (1 + __expf(-x)) compiled to two MUFU ops plus
+// an IEEE division (~10 instructions) and made gn_apply issue-bound (72 registers, 45 % issue-active, 38 us for a 42 MB
+// tensor against 15 us for the statistics pass over the same bytes).
+__device__ __forceinline__ float silu_f(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // GroupNorm statistics: per (batch, CTA, group) partial sum / sum of squares in double, reduced in a fixed order
@@ -27,9 +38,11 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)
 // vector, so every row is read with fully coalesced 16-byte loads.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2,
-                                int C2, double* __restrict__ partial, long long HW, int groups, int PPB,
-                                int pix_per_cta) {
+                                int C2, double* __restrict__ partial, float* __restrict__ mr,
+                                unsigned int* __restrict__ counters, long long HW, int groups, int PPB, int pix_per_cta,
+                                double n_per_group, float eps) {
   extern __shared__ float sm[];  // [PPB][2][C]
+  __shared__ bool is_last;
   pdl_wait();
   pdl_launch_dependents();
   const int C = C1 + C2;
@@ -53,12 +66,12 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = 0.0f, q[i] = 0.0f;
     long long pix = p_begin + pl;
-    for (; pix + 3LL * PPB < p_end; pix += 4LL * PPB) {  // 4 independent 16-byte loads in flight per thread
-      uint4 w[4];
+    for (; pix + 7LL * PPB < p_end; pix += 8LL * PPB) {  // 8 independent 16-byte loads in flight per thread
+      uint4 w[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) w[u] = __ldg(reinterpret_cast<const uint4*>(src + (pix + (long long)u * PPB) * ld + cc));
+      for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const uint4*>(src + (pix + (long long)u * PPB) * ld + cc));
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         float f[8];
         unpack8(w[u], f);
 #pragma unroll
@@ -87,36 +100,42 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
     double* o = partial + ((static_cast<long long>(b) * gridDim.x + blockIdx.x) * groups + g) * 2;
     o[0] = ss, o[1] = qq;
   }
-}
-
-// One block per batch element: (sum, sumsq) partials of all CTAs -> (mean, rstd) per group, fixed summation order.
-__global__ void gn_finalize_kernel(const double* __restrict__ partial, float* __restrict__ mr, int gx, int groups,
-                                   double n, float eps) {
-  __shared__ double sh[256][2];
-  pdl_wait();
-  pdl_launch_dependents();
-  const int b = blockIdx.x;
+  // ---- the last CTA of this batch element reduces the per-CTA partials in a FIXED order (bit-reproducible whichever
+  // CTA happens to be last) and writes (mean, rstd) per group: no separate finalize launch. The counter is reset for
+  // the next call (graph replays reuse the scratch).
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(&counters[b], 1u);
+    is_last = (done == gridDim.x - 1);
+    if (is_last) counters[b] = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double* red = reinterpret_cast<double*>(sm);  // [threads][2] (dynamic smem is at least 256 * 16 bytes: host guarantees)
+  const int gx = gridDim.x;
   const int per = blockDim.x / groups;  // threads cooperating on one group (host guarantees >= 1)
   const int g = threadIdx.x / per, j = threadIdx.x % per;
   double su = 0.0, sq = 0.0;
   if (g < groups) {
-    const double* src = partial + (static_cast<long long>(b) * gx * groups + g) * 2;
-    for (int i = j; i < gx; i += per) su += src[static_cast<size_t>(i) * groups * 2], sq += src[static_cast<size_t>(i) * groups * 2 + 1];
+    const volatile double* srcp = partial + (static_cast<long long>(b) * gx * groups + g) * 2;
+    for (int i = j; i < gx; i += per) su += srcp[static_cast<size_t>(i) * groups * 2], sq += srcp[static_cast<size_t>(i) * groups * 2 + 1];
   }
-  sh[threadIdx.x][0] = su, sh[threadIdx.x][1] = sq;
+  red[2 * threadIdx.x] = su, red[2 * threadIdx.x + 1] = sq;
   __syncthreads();
   if (g < groups && j == 0) {
     double a = 0.0, c = 0.0;
-    for (int t = 0; t < per; ++t) a += sh[threadIdx.x + t][0], c += sh[threadIdx.x + t][1];
-    const double mean = a / n;
-    double var = c / n - mean * mean;
+    for (int t = 0; t < per; ++t) a += red[2 * (threadIdx.x + t)], c += red[2 * (threadIdx.x + t) + 1];
+    const double mean = a / n_per_group;
+    double var = c / n_per_group - mean * mean;
     if (var < 0.0) var = 0.0;
     mr[(b * groups + g) * 2 + 0] = static_cast<float>(mean);
     mr[(b * groups + g) * 2 + 1] = rsqrtf(static_cast<float>(var) + eps);
   }
 }
 
-__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2,
+__global__ void __launch_bounds__(1024) gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2,
                                 int C2, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 __nv_bfloat16* __restrict__ y, const float* __restrict__ mr, long long HW,
                                 int groups, int silu, int PPB, int pix_per_cta) {
@@ -368,23 +387,92 @@ extern "C" int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2
   if (pix_per_cta < PPB) pix_per_cta = PPB;
   const unsigned gx = (unsigned)((HW + pix_per_cta - 1) / pix_per_cta);
   double* dstats = reinterpret_cast<double*>(stats);
-  B200_CHECK_ARG((long long)gx * B * groups * 2 * 8 + (long long)B * groups * 2 * 4 <= stats_bytes,
-                 "groupnorm: stats scratch too small (%lld bytes needed)", (long long)gx * B * groups * 16 + B * groups * 8);
-  B200_CHECK_ARG(groups <= 256, "groupnorm: at most 256 groups");
+  // scratch layout: [gx*B*groups*2] double partials | [B*groups*2] float (mean, rstd) | [B] uint32 arrival counters.
+  // The counters must be ZERO before the first call and are left at zero by every call (the caller zero-fills the
+  // scratch once when it allocates it).
+  const long long need = (long long)gx * B * groups * 16 + (long long)B * groups * 8 + (long long)B * 4;
+  B200_CHECK_ARG(need <= stats_bytes, "groupnorm: stats scratch too small (%lld bytes needed)", need);
+  B200_CHECK_ARG(groups <= 256 && groups <= threads, "groupnorm: at most min(256, block size) groups");
   float* mr = reinterpret_cast<float*>(dstats + (long long)gx * B * groups * 2);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(mr + (long long)B * groups * 2);
   dim3 grid(gx, (unsigned)B);
-  B200_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(threads), (size_t)PPB * 2 * C * sizeof(float), st, 1,
-                       reinterpret_cast<const __nv_bfloat16*>(x1), (int)C1, reinterpret_cast<const __nv_bfloat16*>(x2),
-                       (int)C2, dstats, (long long)HW, (int)groups, PPB, (int)pix_per_cta));
-  {
-    int fthreads = 256 / groups * groups;  // a whole number of threads per group
-    B200_CUDA(launch_pdl(gn_finalize_kernel, dim3((unsigned)B), dim3(fthreads), 0, st, 1, (const double*)dstats, mr,
-                         (int)gx, (int)groups, static_cast<double>(HW) * (double)(C / groups), eps));
-  }
+  const size_t smem = std::max((size_t)PPB * 2 * C * sizeof(float), (size_t)threads * 2 * sizeof(double));
+  B200_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(threads), smem, st, 1, reinterpret_cast<const __nv_bfloat16*>(x1),
+                       (int)C1, reinterpret_cast<const __nv_bfloat16*>(x2), (int)C2, dstats, mr, counters, (long long)HW,
+                       (int)groups, PPB, (int)pix_per_cta, static_cast<double>(HW) * (double)(C / groups), eps));
   B200_CUDA(launch_pdl(gn_apply_kernel, grid, dim3(threads), 0, st, 1, reinterpret_cast<const __nv_bfloat16*>(x1),
                        (int)C1, reinterpret_cast<const __nv_bfloat16*>(x2), (int)C2, gamma, beta,
                        reinterpret_cast<__nv_bfloat16*>(y), (const float*)mr, (long long)HW, (int)groups, (int)silu, PPB,
                        (int)pix_per_cta));
+  return 0;
+}
+
+// Row softmax y = softmax(x * scale) for fp32 scores [M, N] -> bf16 probabilities: the attention of the VAE decoder's
+// mid block (ONE 512-wide head over H*W tokens, ppdiffusers/models/vae.py:232-241, attention_processor.py:673-735 with
+// upcast_softmax) runs as two GEMMs around this kernel because a 512-wide head does not fit the flash kernels' TMEM /
+// shared-memory budget. One CTA per row; the row is staged in shared memory (read once), fp32 math, exp2.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                          long long N, long long ldx, long long ldy, float scale_log2) {
+  extern __shared__ float srow[];
+  __shared__ float red[8];
+  const float* xr = x + static_cast<long long>(blockIdx.x) * ldx;
+  __nv_bfloat16* yr = y + static_cast<long long>(blockIdx.x) * ldy;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+  for (long long i = threadIdx.x * 4; i < N; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + i);
+    *reinterpret_cast<float4*>(srow + i) = v;
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  const float ms = (mx == -INFINITY) ? 0.0f : mx * scale_log2;
+  float sum = 0.0f;
+  for (long long i = threadIdx.x * 4; i < N; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(srow + i);
+    v.x = exp2f(fmaf(v.x, scale_log2, -ms)), v.y = exp2f(fmaf(v.y, scale_log2, -ms));
+    v.z = exp2f(fmaf(v.z, scale_log2, -ms)), v.w = exp2f(fmaf(v.w, scale_log2, -ms));
+    sum += (v.x + v.y) + (v.z + v.w);
+    *reinterpret_cast<float4*>(srow + i) = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.0f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += red[w];  // fixed order: bit-reproducible
+  const float inv = 1.0f / sum;
+  for (long long i = threadIdx.x * 4; i < N; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(srow + i);
+    uint2 o;
+    o.x = pack_bf16x2(v.x * inv, v.y * inv), o.y = pack_bf16x2(v.z * inv, v.w * inv);
+    *reinterpret_cast<uint2*>(yr + i) = o;
+  }
+}
+
+extern "C" int b200mix_softmax_rows(const float* x, void* y, int64_t M, int64_t N, int64_t ldx, int64_t ldy, float scale,
+                                    void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(x && y && M > 0 && N > 0, "softmax_rows: bad arguments");
+  B200_CHECK_ARG(N % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && N * 4 <= 200 * 1024,
+                 "softmax_rows: N, ldx, ldy must be multiples of 4 and N <= 51200");
+  B200_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 8 == 0,
+                 "softmax_rows: pointers must be 16- / 8-byte aligned");
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  softmax_rows_kernel<<<(unsigned)M, 256, (size_t)N * 4, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(y), N, ldx, ldy, scale * 1.4426950408889634f);
+  B200_LAUNCH_CHECK();
   return 0;
 }
 

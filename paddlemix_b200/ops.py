@@ -268,12 +268,13 @@ def groupnorm_nhwc(x1: torch.Tensor, gamma, beta, *, x2=None, groups=32, eps=1e-
     key = (x1.device, torch.cuda.current_stream().cuda_stream, B, groups)
     st = _gn_scratch.get(key)
     if st is None:
-        st = torch.empty((1024 + B) * groups * 2, device=x1.device, dtype=torch.float64)
+        # zero-filled once: the tail holds the per-batch arrival counters, which every call leaves at zero
+        st = torch.zeros((1024 + 2 * B) * groups * 2 + B, device=x1.device, dtype=torch.float64)
         _gn_scratch[key] = st
     with _Timed("groupnorm", 2.0 * 2 * B * HW * (C1 + C2), "byte", lambda: f"gn {B}x{HW}x{C1 + C2}"):  # algorithmic: read once + write once (bf16)
         check(lib.b200mix_groupnorm_nhwc(_p(x1), C1, _p(x2), C2, _p(gamma), _p(beta), _p(out), _p(st), st.numel() * 8, B,
                                          HW, groups, float(eps), 1 if silu else 0, _stream()), "b200mix_groupnorm_nhwc")
-    _count(3)
+    _count(2)
     return out
 
 
@@ -299,6 +300,20 @@ def layernorm(x: torch.Tensor, weight=None, bias=None, *, eps=1e-5, rms=False, d
     _count()
     if want_resid:
         return (resid if resid is not None else x), out
+    return out
+
+
+def softmax_rows(x: torch.Tensor, scale: float = 1.0, out=None) -> torch.Tensor:
+    """x: fp32 [M, N] (row stride arbitrary multiple of 4) -> bf16 softmax(x * scale) [M, N]."""
+    _req(x, torch.float32, "x")
+    M, N = x.shape
+    assert x.stride(1) == 1
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=bf16)
+    with _Timed("softmax", 4.0 * M * N + 2.0 * M * N, "byte", lambda: f"softmax {M}x{N}"):
+        check(lib.b200mix_softmax_rows(_p(x), _p(out), M, N, x.stride(0), out.stride(0), float(scale), _stream()),
+              "b200mix_softmax_rows")
+    _count()
     return out
 
 

@@ -79,9 +79,19 @@ class GraphedUNet:
 class StableDiffusionPipeline:
     """Loop-only mirror of ppdiffusers.StableDiffusionPipeline / StableDiffusionXLPipeline.__call__."""
 
-    def __init__(self, unet: UNet2DConditionModel, scheduler: DDIMScheduler, use_cuda_graph: bool = True):
-        self.unet, self.scheduler, self.use_cuda_graph = unet, scheduler, use_cuda_graph
+    def __init__(self, unet: UNet2DConditionModel, scheduler: DDIMScheduler, use_cuda_graph: bool = True, vae=None):
+        self.unet, self.scheduler, self.use_cuda_graph, self.vae = unet, scheduler, use_cuda_graph, vae
         self._graphed = {}
+
+    def decode_latents(self, latents):
+        """pipeline_stable_diffusion.py:910-917 + VaeImageProcessor.postprocess(output_type="pt"): image =
+        vae.decode(latents / scaling_factor).sample, denormalised to [0, 1]. Returns fp32 [B, 3, H, W] on the device."""
+        from .. import ops
+        if self.vae is None:
+            raise ValueError("output_type='pt' needs a VAE: StableDiffusionPipeline(unet, scheduler, vae=AutoencoderKL(...))")
+        z = ops.scale_model_input(latents.contiguous(), float(self.vae.config.scaling_factor))  # IEEE fp32 division
+        image = self.vae.decode(z, return_dict=False)[0]
+        return (image / 2 + 0.5).clamp(0, 1)  # image_processor.py denormalize: host-side post-processing of the result
 
     def _denoiser(self, sample_shape, ctx_shape, added):
         if not self.use_cuda_graph:
@@ -105,8 +115,8 @@ class StableDiffusionPipeline:
             raise NotImplementedError("text encoders are outside the hot path: pass prompt_embeds / negative_prompt_embeds")
         if prompt_embeds is None:
             raise ValueError("Provide either `prompt` or `prompt_embeds`. Cannot leave both `prompt` and `prompt_embeds` undefined.")
-        if output_type != "latent":
-            raise NotImplementedError("the VAE decoder is outside the hot path: use output_type='latent'")
+        if output_type not in ("latent", "pt"):
+            raise NotImplementedError("output_type must be 'latent' or 'pt' (PIL / numpy conversion is the caller's)")
         if eta != 0.0:
             raise NotImplementedError("eta > 0 (stochastic DDIM) is outside the hot path")
         from .. import ops
@@ -168,7 +178,7 @@ class StableDiffusionPipeline:
             latents, nxt = nxt, latents
             if callback_on_step_end is not None:
                 callback_on_step_end(self, i, t, {"latents": latents})
-        return latents
+        return latents if output_type == "latent" else self.decode_latents(latents)
 
 
 class StableDiffusion3Pipeline:
