@@ -185,6 +185,8 @@ class Ctx:
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
+            from paddlemix_b200 import distributed as bdist
+            bdist.init_comm(self.local)  # the path's collective goes through the C ABI (b200mix_allgather_latents)
         self.dist = dist
 
     def sync_all(self):

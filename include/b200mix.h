@@ -68,6 +68,22 @@ const char* b200mix_version(void);
 int b200mix_init(int device);
 int b200mix_num_sms(void);
 
+/* ---- the path's only collective -------------------------------------------------------------
+ * Images are sharded over ranks (one process per GPU, weights replicated, no per-step communication); the finished
+ * latents are gathered once over NCCL. For contrast, the reference's on-path collective site does 4 scatters + 1
+ * all_gather per step (pipelines/stable_diffusion_3/pipeline_stable_diffusion_3.py:803-839).
+ *   b200mix_nccl_load(path)      dlopen the NCCL the caller names ("" / NULL: "libnccl.so.2" on the loader path)
+ *   b200mix_nccl_unique_id(id)   rank 0: 128-byte ncclUniqueId, handed to the other ranks by the caller's launcher
+ *   b200mix_comm_init(&comm, world, rank, id)   after b200mix_init(device); ncclCommInitRank
+ *   b200mix_allgather_latents(comm, send, recv, bytes_per_rank, stream)   recv = [world * bytes_per_rank], rank order
+ *   b200mix_comm_destroy(comm) */
+int b200mix_nccl_load(const char* libnccl_path);
+int b200mix_nccl_version(void);
+int b200mix_nccl_unique_id(void* id128);
+int b200mix_comm_init(void** comm, int32_t world_size, int32_t rank, const void* id128);
+int b200mix_allgather_latents(void* comm, const void* send, void* recv, int64_t bytes_per_rank, void* stream);
+int b200mix_comm_destroy(void* comm);
+
 /* ---- dense contractions on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> fused epilogue) ------- */
 
 /* C[M, N(/2 if glu)] = epilogue(A[M,K] @ W[N,K]^T). Replaces F.linear (ppdiffusers/models/lora.py:453-459) and

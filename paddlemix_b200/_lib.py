@@ -42,6 +42,12 @@ GLU_NONE, GLU_GEGLU, GLU_SWIGLU = 0, 1, 2
 SIGNATURES = {
     "b200mix_init": [c_int],
     "b200mix_num_sms": [],
+    "b200mix_nccl_load": [c_char_p],
+    "b200mix_nccl_version": [],
+    "b200mix_nccl_unique_id": [c_void_p],
+    "b200mix_comm_init": [POINTER(c_void_p), c_int32, c_int32, c_void_p],
+    "b200mix_allgather_latents": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
+    "b200mix_comm_destroy": [c_void_p],
     "b200mix_linear": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
                        POINTER(Epilogue), c_void_p],
     "b200mix_linear_batched": [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,

@@ -246,10 +246,16 @@ class StableDiffusion3Pipeline:
 
 
 def all_gather_latents(latents: torch.Tensor) -> torch.Tensor:
-    """The single collective of the data-parallel path: finished latents of every rank -> [world*B_local, ...]."""
+    """The single collective of the data-parallel path: finished latents of every rank -> [world*B_local, ...].
+    With a communicator created by paddlemix_b200.distributed.init_comm() the gather is the C-ABI call
+    b200mix_allgather_latents (NCCL on libb200mix's own communicator); otherwise torch.distributed's NCCL all_gather."""
     import torch.distributed as dist
+
+    from .. import distributed as bdist
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         return latents
+    if bdist.comm_ready():
+        return bdist.all_gather_latents(latents)
     out = [torch.empty_like(latents) for _ in range(dist.get_world_size())]
     dist.all_gather(out, latents.contiguous())
     return torch.cat(out, 0)
