@@ -139,8 +139,8 @@ int b200mix_sdpa(const void* q, const void* k, const void* v, void* o, int64_t B
  * Replaces nn.GroupNorm + nonlinearity (resnet.py:667-692,760-786; transformer_2d.py:161; unet_2d_condition.py:1193).
  * y bf16 [B,H,W,C1+C2]. Two launches: per-CTA partial statistics in double, reduced in a fixed order by the last
  * CTA of each batch element (bit-reproducible), then apply. `stats` = scratch of at least
- * (4*num_sms + 2*B) * groups * 16 + 4*B bytes that the caller ZERO-FILLS ONCE at allocation (it holds the arrival
- * counters, which every call leaves at zero); one scratch per concurrently used stream. */
+ * 4096 + (4*num_sms + 2*B) * groups * 16 bytes that the caller ZERO-FILLS ONCE at allocation (its first 4 KB hold the
+ * arrival counters, which every call leaves at zero); one scratch per concurrently used stream. */
 int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2, int64_t C2, const float* gamma,
                            const float* beta, void* y, void* stats, int64_t stats_bytes, int64_t B, int64_t HW,
                            int32_t groups, float eps, int32_t silu, void* stream);

@@ -386,15 +386,17 @@ extern "C" int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2
   pix_per_cta = ((pix_per_cta + PPB - 1) / PPB) * PPB;
   if (pix_per_cta < PPB) pix_per_cta = PPB;
   const unsigned gx = (unsigned)((HW + pix_per_cta - 1) / pix_per_cta);
-  double* dstats = reinterpret_cast<double*>(stats);
-  // scratch layout: [gx*B*groups*2] double partials | [B*groups*2] float (mean, rstd) | [B] uint32 arrival counters.
-  // The counters must be ZERO before the first call and are left at zero by every call (the caller zero-fills the
-  // scratch once when it allocates it).
-  const long long need = (long long)gx * B * groups * 16 + (long long)B * groups * 8 + (long long)B * 4;
+  // scratch layout: [1024] uint32 arrival counters at a FIXED offset | [gx*B*groups*2] double partials | [B*groups*2]
+  // float (mean, rstd). The counters must be ZERO before the first call and are left at zero by every call (the caller
+  // zero-fills the scratch once when it allocates it); they sit in front because gx - and with it the size of the
+  // partial region - changes from call to call.
+  B200_CHECK_ARG(B <= 1024, "groupnorm: at most 1024 batch elements");
+  unsigned int* counters = reinterpret_cast<unsigned int*>(stats);
+  double* dstats = reinterpret_cast<double*>(reinterpret_cast<char*>(stats) + 4096);
+  const long long need = 4096 + (long long)gx * B * groups * 16 + (long long)B * groups * 8;
   B200_CHECK_ARG(need <= stats_bytes, "groupnorm: stats scratch too small (%lld bytes needed)", need);
   B200_CHECK_ARG(groups <= 256 && groups <= threads, "groupnorm: at most min(256, block size) groups");
   float* mr = reinterpret_cast<float*>(dstats + (long long)gx * B * groups * 2);
-  unsigned int* counters = reinterpret_cast<unsigned int*>(mr + (long long)B * groups * 2);
   dim3 grid(gx, (unsigned)B);
   const size_t smem = std::max((size_t)PPB * 2 * C * sizeof(float), (size_t)threads * 2 * sizeof(double));
   B200_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(threads), smem, st, 1, reinterpret_cast<const __nv_bfloat16*>(x1),

@@ -268,8 +268,8 @@ def groupnorm_nhwc(x1: torch.Tensor, gamma, beta, *, x2=None, groups=32, eps=1e-
     key = (x1.device, torch.cuda.current_stream().cuda_stream, B, groups)
     st = _gn_scratch.get(key)
     if st is None:
-        # zero-filled once: the tail holds the per-batch arrival counters, which every call leaves at zero
-        st = torch.zeros((1024 + 2 * B) * groups * 2 + B, device=x1.device, dtype=torch.float64)
+        # zero-filled once: the first 4 KB hold the per-batch arrival counters, which every call leaves at zero
+        st = torch.zeros(512 + (1024 + 2 * B) * groups * 2, device=x1.device, dtype=torch.float64)
         _gn_scratch[key] = st
     with _Timed("groupnorm", 2.0 * 2 * B * HW * (C1 + C2), "byte", lambda: f"gn {B}x{HW}x{C1 + C2}"):  # algorithmic: read once + write once (bf16)
         check(lib.b200mix_groupnorm_nhwc(_p(x1), C1, _p(x2), C2, _p(gamma), _p(beta), _p(out), _p(st), st.numel() * 8, B,
