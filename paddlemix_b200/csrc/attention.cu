@@ -678,19 +678,25 @@ __global__ void __launch_bounds__(192, 2)
           if (c < nch) add_mask_chunk(sv[c], p, mask_row, c * 32);
       }
 
-      float mx = -INFINITY;
+      // only the chunk that holds the boundary needs per-column masking; row max with 3-input max on four chains, the
+      // scale-subtract and the row sum on packed fp32 pairs (FFMA2 / FADD2): the kernel is issue-bound, not MUFU-bound
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         if (c < nch) {
+          if (kv_len < (c + 1) * 32) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float sc = (c * 32 + j < kv_len) ? __uint_as_float(sv[c][j]) : -INFINITY;
-            sv[c][j] = __float_as_uint(sc);
-            mx = fmaxf(mx, sc);
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j >= kv_len) sv[c][j] = 0xff800000u;  // -inf
           }
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            mx4[j & 3] = fmax3(mx4[j & 3], __uint_as_float(sv[c][2 * j]), __uint_as_float(sv[c][2 * j + 1]));
         }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_scaled = (mx == -INFINITY) ? 0.0f : mx * p.scale_log2;
-      float sum = 0.0f;
+      const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(-m_scaled, -m_scaled);
+      uint64_t sum2[2] = {0ull, 0ull};
 #pragma unroll
       for (int g8 = 0; g8 < 16; ++g8) {
         if ((g8 >> 2) < nch) {
@@ -698,15 +704,21 @@ __global__ void __launch_bounds__(192, 2)
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int col = g8 * 8 + t * 2;
-            const float e0 = fast_exp2(fmaf(__uint_as_float(sv[col >> 5][col & 31]), p.scale_log2, -m_scaled));
-            const float e1 = fast_exp2(fmaf(__uint_as_float(sv[col >> 5][(col & 31) + 1]), p.scale_log2, -m_scaled));
-            sum += e0 + e1;
+            float t0, t1;
+            unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(sv[col >> 5][col & 31]), __uint_as_float(sv[col >> 5][(col & 31) + 1])),
+                               sc2, nm2), t0, t1);
+            const float e0 = fast_exp2(t0), e1 = fast_exp2(t1);
+            sum2[t & 1] = fadd2(sum2[t & 1], pack_f32x2(e0, e1));
             w[t] = pack_bf16x2(e0, e1);
           }
           const int chunk = g8 >> 3, u = g8 & 7;
           *reinterpret_cast<uint4*>(p_row + chunk * 16384 + ((u ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
+      float sa0, sa1, sb0, sb1;
+      unpack_f32x2(sum2[0], sa0, sa1);
+      unpack_f32x2(sum2[1], sb0, sb1);
+      const float sum = (sa0 + sa1) + (sb0 + sb1);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);

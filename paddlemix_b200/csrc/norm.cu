@@ -201,7 +201,85 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const __nv_bfloat16* __r
 
 // ------------------------------------------------------------------------------------------------------------
 // Row-wise LayerNorm / RMSNorm: one warp per row, the row lives in registers (two-pass mean / variance).
+// The arithmetic runs on PACKED fp32 pairs (FADD2 / FMUL2 / FFMA2: two lanes per instruction): the round-1 kernels were
+// issue-bound (ncu: 57 % issue-active, ~20 instructions per element, DRAM at 21 %), not memory-bound. Both LayerNorm
+// kernels share these helpers, so they accumulate in the same order and stay bit-identical to each other.
 // ------------------------------------------------------------------------------------------------------------
+struct P8 {
+  uint64_t p[4];  // 8 fp32 values as 4 (even, odd) pairs
+};
+__device__ __forceinline__ P8 unpack8p(const uint4& w) {
+  P8 r;
+  r.p[0] = pack_f32x2(bf16_lo(w.x), bf16_hi(w.x)), r.p[1] = pack_f32x2(bf16_lo(w.y), bf16_hi(w.y));
+  r.p[2] = pack_f32x2(bf16_lo(w.z), bf16_hi(w.z)), r.p[3] = pack_f32x2(bf16_lo(w.w), bf16_hi(w.w));
+  return r;
+}
+__device__ __forceinline__ uint4 pack8p(const P8& v) {
+  float a, b;
+  uint4 w;
+  unpack_f32x2(v.p[0], a, b), w.x = pack_bf16x2(a, b);
+  unpack_f32x2(v.p[1], a, b), w.y = pack_bf16x2(a, b);
+  unpack_f32x2(v.p[2], a, b), w.z = pack_bf16x2(a, b);
+  unpack_f32x2(v.p[3], a, b), w.w = pack_bf16x2(a, b);
+  return w;
+}
+__device__ __forceinline__ float pair_sum(uint64_t v) {
+  float a, b;
+  unpack_f32x2(v, a, b);
+  return a + b;
+}
+// acc += the 8 values of w (as two interleaved partial sums)
+__device__ __forceinline__ void ln_acc_sum(uint64_t& acc, const uint4& w) {
+  const P8 v = unpack8p(w);
+  acc = fadd2(fadd2(acc, v.p[0]), fadd2(v.p[1], fadd2(v.p[2], v.p[3])));
+}
+// acc += (v - mean)^2 over the 8 values of w
+__device__ __forceinline__ void ln_acc_sq(uint64_t& acc, const uint4& w, uint64_t nmean2) {
+  const P8 v = unpack8p(w);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t d = fadd2(v.p[k], nmean2);
+    acc = ffma2(d, d, acc);
+  }
+}
+__device__ __forceinline__ P8 load8f(const float* ptr) {  // 8 consecutive fp32 (32-byte aligned) as pairs
+  const float4 a = __ldg(reinterpret_cast<const float4*>(ptr)), b = __ldg(reinterpret_cast<const float4*>(ptr) + 1);
+  P8 r;
+  r.p[0] = pack_f32x2(a.x, a.y), r.p[1] = pack_f32x2(a.z, a.w), r.p[2] = pack_f32x2(b.x, b.y), r.p[3] = pack_f32x2(b.z, b.w);
+  return r;
+}
+// Output stage for 8 channels of one row: ((x - mean) * rstd) [*w] [+b] [*(1 + scale) + shift] -> bf16. RMSNorm with a
+// weight keeps Qwen2RMSNorm's cast order (normalised value rounded to the activation dtype, THEN multiplied).
+__device__ __forceinline__ uint4 ln_output8(const uint4& raw, uint64_t nmean2, uint64_t rstd2, bool rms, const P8* wv,
+                                            const P8* bv, const float* scale, const float* shift) {
+  P8 o = unpack8p(raw);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o.p[k] = fmul2(fadd2(o.p[k], nmean2), rstd2);
+  if (rms && wv) {
+    o = unpack8p(pack8p(o));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.p[k] = fmul2(o.p[k], wv->p[k]);
+  } else if (wv) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.p[k] = fmul2(o.p[k], wv->p[k]);
+  }
+  if (bv) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.p[k] = fadd2(o.p[k], bv->p[k]);
+  }
+  if (scale) {
+    const P8 sc = load8f(scale);
+    const uint64_t one2 = pack_f32x2(1.0f, 1.0f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.p[k] = fmul2(o.p[k], fadd2(sc.p[k], one2));
+  }
+  if (shift) {
+    const P8 sh = load8f(shift);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.p[k] = fadd2(o.p[k], sh.p[k]);
+  }
+  return pack8p(o);
+}
 struct LNParams {
   const __nv_bfloat16* x;
   const __nv_bfloat16* delta;
@@ -274,14 +352,10 @@ __global__ void __launch_bounds__(256, (VPL * ROWS > 16) ? 1 : 2) layernorm_kern
   for (int r = 0; r < ROWS; ++r) {
     mean[r] = 0.0f;
     if (!p.rms) {
-      float s = 0.0f;
+      uint64_t acc = 0ull;
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        float v[8];
-        unpack8(raw[r][i], v);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s += v[k];
-      }
+      for (int i = 0; i < VPL; ++i) ln_acc_sum(acc, raw[r][i]);  // lanes past the row hold zeros
+      float s = pair_sum(acc);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       mean[r] = s / p.N;
@@ -289,20 +363,14 @@ __global__ void __launch_bounds__(256, (VPL * ROWS > 16) ? 1 : 2) layernorm_kern
   }
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
-    float sq = 0.0f;
+    const uint64_t nmean2 = pack_f32x2(-mean[r], -mean[r]);
+    uint64_t acc = 0ull;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = lane + 32 * i;
-      if (vi < NV) {
-        float v[8];
-        unpack8(raw[r][i], v);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float d = v[k] - mean[r];
-          sq += d * d;
-        }
-      }
+      if (vi < NV) ln_acc_sq(acc, raw[r][i], nmean2);
     }
+    float sq = pair_sum(acc);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     rstd[r] = rsqrtf(sq / p.N + p.eps);
@@ -313,52 +381,23 @@ __global__ void __launch_bounds__(256, (VPL * ROWS > 16) ? 1 : 2) layernorm_kern
   for (int i = 0; i < VPL; ++i) {
     const int vi = lane + 32 * i;
     if (vi >= NV) continue;
-    float wv[8], bv[8];
-    if (p.weight) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(p.weight) + 2 * vi);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.weight) + 2 * vi + 1);
-      wv[0] = a.x, wv[1] = a.y, wv[2] = a.z, wv[3] = a.w, wv[4] = b.x, wv[5] = b.y, wv[6] = b.z, wv[7] = b.w;
-    }
-    if (p.bias) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(p.bias) + 2 * vi);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + 2 * vi + 1);
-      bv[0] = a.x, bv[1] = a.y, bv[2] = a.z, bv[3] = a.w, bv[4] = b.x, bv[5] = b.y, bv[6] = b.z, bv[7] = b.w;
-    }
+    P8 wv, bv;
+    if (p.weight) wv = load8f(p.weight + 8 * vi);
+    if (p.bias) bv = load8f(p.bias + 8 * vi);
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const long long row = row0 + r;
       if (row >= p.M) continue;
-      float o[8];
-      unpack8(raw[r][i], o);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = (o[k] - mean[r]) * rstd[r];
-      if (p.rms && p.weight) {
-        // Qwen2RMSNorm: normalised value is cast to the activation dtype first, then multiplied by the weight
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = __bfloat162float(__float2bfloat16(o[k])) * wv[k];
-      } else if (p.weight) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] *= wv[k];
-      }
-      if (p.bias) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] += bv[k];
-      }
+      const float* sc = nullptr;
+      const float* sh = nullptr;
       if (p.scale || p.shift) {
         const long long g = static_cast<long long>(static_cast<unsigned>(row) / static_cast<unsigned>(p.rows_per_group));
-        if (p.scale) {
-          const float4* sp = reinterpret_cast<const float4*>(p.scale + g * p.ld_mod) + 2 * vi;
-          const float4 a = __ldg(sp), b = __ldg(sp + 1);
-          o[0] *= 1.0f + a.x, o[1] *= 1.0f + a.y, o[2] *= 1.0f + a.z, o[3] *= 1.0f + a.w;
-          o[4] *= 1.0f + b.x, o[5] *= 1.0f + b.y, o[6] *= 1.0f + b.z, o[7] *= 1.0f + b.w;
-        }
-        if (p.shift) {
-          const float4* sp = reinterpret_cast<const float4*>(p.shift + g * p.ld_mod) + 2 * vi;
-          const float4 a = __ldg(sp), b = __ldg(sp + 1);
-          o[0] += a.x, o[1] += a.y, o[2] += a.z, o[3] += a.w, o[4] += b.x, o[5] += b.y, o[6] += b.z, o[7] += b.w;
-        }
+        if (p.scale) sc = p.scale + g * p.ld_mod + 8 * vi;
+        if (p.shift) sh = p.shift + g * p.ld_mod + 8 * vi;
       }
-      *(reinterpret_cast<uint4*>(p.y + row * p.N) + vi) = pack8(o);
+      *(reinterpret_cast<uint4*>(p.y + row * p.N) + vi) =
+          ln_output8(raw[r][i], pack_f32x2(-mean[r], -mean[r]), pack_f32x2(rstd[r], rstd[r]), p.rms != 0,
+                     p.weight ? &wv : nullptr, p.bias ? &bv : nullptr, sc, sh);
     }
   }
 }
@@ -543,77 +582,39 @@ __global__ void __launch_bounds__(512, 2) layernorm_block_kernel(const LNParams 
         }
       }
       if (!p.rms) {
-        float s = 0.0f;
-        for (int vi = lane; vi < NV; vi += 32) {
-          float v[8];
-          unpack8(srow[rr][vi], v);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) s += v[k];
-        }
+        uint64_t acc = 0ull;
+        for (int vi = lane; vi < NV; vi += 32) ln_acc_sum(acc, srow[rr][vi]);
+        float s = pair_sum(acc);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         mean[rr] = s / p.N;
       }
-      float sq = 0.0f;
-      for (int vi = lane; vi < NV; vi += 32) {
-        float v[8];
-        unpack8(srow[rr][vi], v);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float d = v[k] - mean[rr];
-          sq += d * d;
-        }
-      }
+      const uint64_t nmean2 = pack_f32x2(-mean[rr], -mean[rr]);
+      uint64_t acc = 0ull;
+      for (int vi = lane; vi < NV; vi += 32) ln_acc_sq(acc, srow[rr][vi], nmean2);
+      float sq = pair_sum(acc);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
       rstd[rr] = rsqrtf(sq / p.N + p.eps);
     }
     for (int vi = lane; vi < NV; vi += 32) {
-      float wv[8], bv[8];
-      if (p.weight) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p.weight) + 2 * vi);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.weight) + 2 * vi + 1);
-        wv[0] = a.x, wv[1] = a.y, wv[2] = a.z, wv[3] = a.w, wv[4] = b.x, wv[5] = b.y, wv[6] = b.z, wv[7] = b.w;
-      }
-      if (p.bias) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p.bias) + 2 * vi);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + 2 * vi + 1);
-        bv[0] = a.x, bv[1] = a.y, bv[2] = a.z, bv[3] = a.w, bv[4] = b.x, bv[5] = b.y, bv[6] = b.z, bv[7] = b.w;
-      }
+      P8 wv, bv;
+      if (p.weight) wv = load8f(p.weight + 8 * vi);
+      if (p.bias) bv = load8f(p.bias + 8 * vi);
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         if (rr >= nr) break;
         const long long row = r0 + r + rr;
-        float o[8];
-        unpack8(srow[rr][vi], o);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = (o[k] - mean[rr]) * rstd[rr];
-        if (p.rms && p.weight) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] = __bfloat162float(__float2bfloat16(o[k])) * wv[k];
-        } else if (p.weight) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] *= wv[k];
-        }
-        if (p.bias) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] += bv[k];
-        }
+        const float* sc = nullptr;
+        const float* sh = nullptr;
         if (p.scale || p.shift) {
           const long long g = static_cast<long long>(static_cast<unsigned>(row) / static_cast<unsigned>(p.rows_per_group));
-          if (p.scale) {
-            const float4* sp = reinterpret_cast<const float4*>(p.scale + g * p.ld_mod) + 2 * vi;
-            const float4 a = __ldg(sp), b = __ldg(sp + 1);
-            o[0] *= 1.0f + a.x, o[1] *= 1.0f + a.y, o[2] *= 1.0f + a.z, o[3] *= 1.0f + a.w;
-            o[4] *= 1.0f + b.x, o[5] *= 1.0f + b.y, o[6] *= 1.0f + b.z, o[7] *= 1.0f + b.w;
-          }
-          if (p.shift) {
-            const float4* sp = reinterpret_cast<const float4*>(p.shift + g * p.ld_mod) + 2 * vi;
-            const float4 a = __ldg(sp), b = __ldg(sp + 1);
-            o[0] += a.x, o[1] += a.y, o[2] += a.z, o[3] += a.w, o[4] += b.x, o[5] += b.y, o[6] += b.z, o[7] += b.w;
-          }
+          if (p.scale) sc = p.scale + g * p.ld_mod + 8 * vi;
+          if (p.shift) sh = p.shift + g * p.ld_mod + 8 * vi;
         }
-        *(reinterpret_cast<uint4*>(p.y + row * p.N) + vi) = pack8(o);
+        *(reinterpret_cast<uint4*>(p.y + row * p.N) + vi) =
+            ln_output8(srow[rr][vi], pack_f32x2(-mean[rr], -mean[rr]), pack_f32x2(rstd[rr], rstd[rr]), p.rms != 0,
+                       p.weight ? &wv : nullptr, p.bias ? &bv : nullptr, sc, sh);
       }
     }
   }
