@@ -610,6 +610,127 @@ __global__ void __launch_bounds__(320, 1)
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Skinny-M Linear (M <= 8 activation rows: single-token decode steps, the UNet's time / text-time embedding MLPs):
+// the work is streaming W once from HBM, so this is a CUDA-core weight-streaming kernel, not a tensor-core tile (a
+// 256-row MMA tile would spend 97 % of its rows on zeros: round 1 measured 1.2 TB/s of weight reads through igemm).
+// One warp owns TWO consecutive output rows n0, n0 + 1 (a GLU pair when the rows are interleaved value / gate): every
+// lane streams 16-byte pieces of both weight rows (coalesced 512 B per warp and row), the activations of the current
+// K chunk sit in shared memory as fp32, products accumulate on packed fp32 pairs (FFMA2), one butterfly reduction
+// per row at the end. Bound: HBM (N * K * 2 bytes of weights); epilogue = bias / activation / GLU / residual.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SK_KC = 2048;  // K chunk staged in shared memory (M * 8 KB)
+
+__device__ __forceinline__ void sk_unpack8(const uint4& w, uint64_t (&p)[4]) {
+  p[0] = pack_f32x2(bf16_lo(w.x), bf16_hi(w.x)), p[1] = pack_f32x2(bf16_lo(w.y), bf16_hi(w.y));
+  p[2] = pack_f32x2(bf16_lo(w.z), bf16_hi(w.z)), p[3] = pack_f32x2(bf16_lo(w.w), bf16_hi(w.w));
+}
+
+template <int M>
+__global__ void __launch_bounds__(256)
+    skinny_linear_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __nv_bfloat16* __restrict__ W,
+                         long long ldw, void* __restrict__ C, long long ldc, int N, int K, const float* __restrict__ bias,
+                         const __nv_bfloat16* __restrict__ residual, long long ldr, int act, int glu, int out_fp32,
+                         int rows) {  // rows <= M: the template rounds the row count up (zero rows are staged for the rest)
+  extern __shared__ __align__(16) float sA[];  // [M][SK_KC]
+  pdl_wait();
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x * 8 + warp) * 2;
+  const bool have0 = n0 < N, have1 = n0 + 1 < N;
+  const __nv_bfloat16* w0 = W + static_cast<long long>(have0 ? n0 : 0) * ldw;
+  const __nv_bfloat16* w1 = W + static_cast<long long>(have1 ? n0 + 1 : 0) * ldw;
+  uint64_t acc[M][2];
+#pragma unroll
+  for (int m = 0; m < M; ++m) acc[m][0] = acc[m][1] = 0ull;
+  for (int k0 = 0; k0 < K; k0 += SK_KC) {
+    const int kc = min(SK_KC, K - k0);
+    __syncthreads();
+    for (int i = threadIdx.x * 8; i < M * kc; i += 256 * 8) {  // stage A[:, k0 : k0 + kc] as fp32 (kc % 8 == 0)
+      const int m = i / kc, k = i - m * kc;
+      const uint4 v = m < rows ? __ldg(reinterpret_cast<const uint4*>(A + m * lda + k0 + k)) : make_uint4(0u, 0u, 0u, 0u);
+      float* d = sA + m * SK_KC + k;
+      d[0] = bf16_lo(v.x), d[1] = bf16_hi(v.x), d[2] = bf16_lo(v.y), d[3] = bf16_hi(v.y);
+      d[4] = bf16_lo(v.z), d[5] = bf16_hi(v.z), d[6] = bf16_lo(v.w), d[7] = bf16_hi(v.w);
+    }
+    __syncthreads();
+    if (!have0) continue;
+#pragma unroll 2
+    for (int kk = lane * 8; kk < kc; kk += 256) {
+      const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(w0 + k0 + kk));
+      const uint4 r1 = have1 ? __ldg(reinterpret_cast<const uint4*>(w1 + k0 + kk)) : make_uint4(0u, 0u, 0u, 0u);
+      uint64_t p0[4], p1[4];
+      sk_unpack8(r0, p0);
+      sk_unpack8(r1, p1);
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const float4 a = *reinterpret_cast<const float4*>(sA + m * SK_KC + kk);
+        const float4 b = *reinterpret_cast<const float4*>(sA + m * SK_KC + kk + 4);
+        const uint64_t pa[4] = {pack_f32x2(a.x, a.y), pack_f32x2(a.z, a.w), pack_f32x2(b.x, b.y), pack_f32x2(b.z, b.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[m][0] = ffma2(p0[j], pa[j], acc[m][0]);
+          acc[m][1] = ffma2(p1[j], pa[j], acc[m][1]);
+        }
+      }
+    }
+  }
+  if (!have0) return;
+  const ActCoef ac = act_coef(act, glu);
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    float v0, v1, t;
+    unpack_f32x2(acc[m][0], v0, t), v0 += t;
+    unpack_f32x2(acc[m][1], v1, t), v1 += t;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+    }
+    if (lane != 0 || m >= rows) continue;
+    if (bias) v0 += bias[n0], v1 += have1 ? bias[n0 + 1] : 0.0f;
+    if (glu) {  // interleaved rows: 2j = value, 2j + 1 = gate
+      const float o = v0 * act_eval(v1, ac);
+      if (out_fp32) reinterpret_cast<float*>(C)[m * ldc + (n0 >> 1)] = o;
+      else reinterpret_cast<__nv_bfloat16*>(C)[m * ldc + (n0 >> 1)] = __float2bfloat16(o);
+      continue;
+    }
+    if (act != B200MIX_ACT_NONE) v0 = act_eval(v0, ac), v1 = act_eval(v1, ac);
+    if (residual) {
+      v0 += __bfloat162float(residual[m * ldr + n0]);
+      if (have1) v1 += __bfloat162float(residual[m * ldr + n0 + 1]);
+    }
+    if (out_fp32) {
+      float* c = reinterpret_cast<float*>(C) + m * ldc + n0;
+      c[0] = v0;
+      if (have1) c[1] = v1;
+    } else {
+      __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(C) + m * ldc + n0;
+      c[0] = __float2bfloat16(v0);
+      if (have1) c[1] = __float2bfloat16(v1);
+    }
+  }
+}
+
+static int g_skinny = 1;  // test hook: 0 = M <= 8 problems go through the tensor-core kernel again
+
+template <int M>
+static int launch_skinny(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int rows, int N,
+                         int K, const b200mix_epilogue* e, cudaStream_t stream) {
+  const size_t smem = (size_t)M * SK_KC * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(skinny_linear_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const unsigned grid = (unsigned)((N + 15) / 16);
+  B200_CUDA(launch_pdl(skinny_linear_kernel<M>, dim3(grid), dim3(256), smem, stream, 1,
+                       reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(W), ldw, C, ldc, N,
+                       K, e ? e->bias : nullptr, e ? reinterpret_cast<const __nv_bfloat16*>(e->residual) : nullptr,
+                       e ? (long long)e->ldr : 0ll, e ? e->act : 0, e ? e->glu : 0, e ? e->out_fp32 : 0, rows));
+  return 0;
+}
+
 static int g_max_clusters = 0;  // measurement hook: cap the persistent grid (0 = all SMs)
 
 template <int BN, int STAGES, bool PAIR>
@@ -739,6 +860,7 @@ static int g_force_bn = 0;
 extern "C" void b200mix_debug_force_bn(int bn) { g_force_bn = bn; }
 extern "C" void b200mix_debug_gemm_pair(int on) { b200::g_gemm_pair = on; }
 extern "C" void b200mix_debug_max_clusters(int n) { b200::g_max_clusters = n; }
+extern "C" void b200mix_debug_skinny(int on) { b200::g_skinny = on; }
 
 extern "C" int b200mix_linear(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M,
                               int64_t N, int64_t K, const b200mix_epilogue* epi, void* stream) {
@@ -749,6 +871,20 @@ extern "C" int b200mix_linear(const void* A, int64_t lda, const void* W, int64_t
   B200_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0, "linear: lda/ldw must be multiples of 8 elements (16 B TMA strides)");
   B200_CHECK_ARG(lda >= K && ldw >= K, "linear: leading dimensions smaller than K");
   B200_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31), "linear: M/N too large");
+
+  // M <= 8: weight-streaming kernel (decode steps, embedding MLPs) unless the epilogue needs per-group vectors
+  if (g_skinny && M <= 8 && K % 8 == 0 && K < (1ll << 31) &&
+      (!epi || (!epi->row_add && !epi->row_gate && epi->residual_row_mod == 0 &&
+                (epi->out_scale == 0.0f || epi->out_scale == 1.0f) && !(epi->glu && (N & 1)) &&
+                !(epi->glu && (epi->residual || epi->act))))) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch ((int)M) {
+      case 1: return launch_skinny<1>(A, lda, W, ldw, C, ldc, 1, (int)N, (int)K, epi, st);
+      case 2: return launch_skinny<2>(A, lda, W, ldw, C, ldc, 2, (int)N, (int)K, epi, st);
+      case 3: case 4: return launch_skinny<4>(A, lda, W, ldw, C, ldc, (int)M, (int)N, (int)K, epi, st);
+      default: return launch_skinny<8>(A, lda, W, ldw, C, ldc, (int)M, (int)N, (int)K, epi, st);
+    }
+  }
 
   IGemmParams p = {};
   p.N = (int)N;

@@ -67,6 +67,68 @@ class KVCache:
         return self.length
 
 
+class GraphedDecodeStep:
+    """One decode step of Qwen2-VL as a CUDA graph (weak point of round 1: 11.7 ms per step, eager launches, host syncs).
+    Static device state: newest token ids, the cache row to write and the key count per sequence (both advance INSIDE the
+    graph), the 1-D rotary position per sequence (after the prompt all three M-RoPE axes carry the same position,
+    cache_position + rope_delta, modeling_qwen2_vl.py:1413-1441) with cos / sin gathered from device tables.
+    step(ids) = one small H2D copy (or none, with device ids) + one graph replay; logits stay on the device."""
+
+    def __init__(self, model, cache: KVCache, rope_deltas, warmup: int = 2):
+        from .. import ops
+        self.model, self.cache = model, cache
+        dev, B, hd = model.device, cache.batch, model.head_dim
+        c = model.config
+        P = cache.length
+        deltas = torch.zeros(B, dtype=torch.long) if rope_deltas is None else rope_deltas.reshape(B).cpu().long()
+        n_pos = cache.max_len + int(deltas.max().clamp(min=0)) + 2
+        inv_freq = 1.0 / (c.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
+        fr = torch.arange(n_pos, dtype=torch.float32)[:, None] * inv_freq[None]
+        emb = torch.cat([fr, fr], -1)
+        self.cos_table, self.sin_table = emb.cos().contiguous().to(dev), emb.sin().contiguous().to(dev)
+        self.ids = torch.zeros(B, dtype=torch.long, device=dev)
+        self.pos = (P + deltas).clamp(min=0).to(dev)
+        self.rows = (torch.arange(B) * cache.max_len + P).to(dev)
+        self.kv_lens = torch.full((B,), P + 1, dtype=torch.int32, device=dev)
+        self.cos, self.sin = torch.empty(B, hd, device=dev), torch.empty(B, hd, device=dev)
+        self._state0 = (self.pos.clone(), self.rows.clone(), self.kv_lens.clone())
+
+        def body():
+            torch.index_select(self.cos_table, 0, self.pos, out=self.cos)  # row gathers (no arithmetic on activations)
+            torch.index_select(self.sin_table, 0, self.pos, out=self.sin)
+            logits = model.decode_body_static(self.ids, self.cos, self.sin, cache, self.rows, self.kv_lens)
+            self.pos.add_(1), self.rows.add_(1), self.kv_lens.add_(1)  # index bookkeeping advances on the device
+            return logits
+
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        for t, t0 in zip((self.pos, self.rows, self.kv_lens), self._state0):  # undo the warm-up steps' advance
+            t.copy_(t0)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.launches()
+        with torch.cuda.graph(self.graph):
+            self.logits = body()
+        self.launches_per_step = ops.launches() - n0
+        for t, t0 in zip((self.pos, self.rows, self.kv_lens), self._state0):
+            t.copy_(t0)
+
+    def step(self, ids):
+        """ids: int64 [B] (host or device) newest token of each sequence -> fp32 logits [B, vocab] (device, reused)."""
+        from .. import ops
+        if self.cache.length + 1 > self.cache.max_len:
+            raise ValueError(f"KV cache is full ({self.cache.max_len} positions)")
+        self.ids.copy_(ids.reshape(-1), non_blocking=True)
+        self.graph.replay()
+        ops._count(self.launches_per_step)
+        self.cache.length += 1
+        return self.logits
+
+
 def _pad_rows(w, heads, d, dp):  # [heads*d, in] -> [heads*dp, in]
     if d == dp:
         return w
@@ -447,6 +509,38 @@ class Qwen2VLForConditionalGeneration:
         hN = ops.layernorm(x, self.norm_w, None, eps=c.rms_norm_eps, rms=True)
         return ops.linear(hN, self.lm_head, out_fp32=True)
 
+    def decode_body_static(self, ids_dev, cos, sin, cache: KVCache, rows, kv_lens):
+        """decode_device with every position-dependent quantity on the DEVICE (CUDA-graph capturable): `rows` int64 [B] =
+        b * max_len + position of the new token (row of the flattened cache to write), `kv_lens` int32 [B] = keys to attend
+        to (position + 1). The G = heads / kv_heads query heads that share a KV head are presented to the attention kernel
+        as G query rows of ONE head (Sq = G, Hq = Hkv): one K / V stream per KV head instead of one per query head."""
+        from .. import ops
+        from .._lib import GLU_SWIGLU
+        c, hd = self.config, self.head_dim
+        nh, nkv = c.num_attention_heads, c.num_key_value_heads
+        G = nh // nkv
+        B = ids_dev.shape[0]
+        x = ops.gather_rows(self.embed, ids_dev)
+        qd, kvd = nh * hd, nkv * hd
+        for li, L in enumerate(self.layers):
+            h1 = ops.layernorm(x, L["ln1"], None, eps=c.rms_norm_eps, rms=True)
+            qkv = ops.linear(h1, *L["qkv"])
+            q = qkv[:, :qd].unflatten(-1, (nh, hd))
+            k = qkv[:, qd:qd + kvd].unflatten(-1, (nkv, hd))
+            ops.rope_inplace(q, cos, sin)
+            ops.rope_inplace(k, cos, sin)
+            ops.scatter_rows(qkv[:, qd:qd + kvd].contiguous(), rows, cache.k[li].view(-1, kvd))
+            ops.scatter_rows(qkv[:, qd + kvd:].contiguous(), rows, cache.v[li].view(-1, kvd))
+            a = torch.empty(B, qd, device=x.device, dtype=bf16)
+            qg = qkv.as_strided((B, G, nkv, hd), (qkv.stride(0), hd, G * hd, 1), qkv.storage_offset())
+            ag = a.as_strided((B, G, nkv, hd), (qd, hd, G * hd, 1))
+            ops.sdpa(qg, cache.k[li], cache.v[li], scale=hd ** -0.5, kv_lens=kv_lens, out=ag)
+            x = ops.linear(a, L["o"], residual=x)
+            h2 = ops.layernorm(x, L["ln2"], None, eps=c.rms_norm_eps, rms=True)
+            x = ops.linear(ops.linear(h2, L["gu"], glu=GLU_SWIGLU), L["down"], residual=x)
+        hN = ops.layernorm(x, self.norm_w, None, eps=c.rms_norm_eps, rms=True)
+        return ops.linear(hN, self.lm_head, out_fp32=True)
+
     @torch.no_grad()
     def generate(self, input_ids, pixel_values=None, image_grid_thw=None, max_new_tokens: int = 16, eos_token_id=None):
         """Greedy decoding (generation_utils' default `do_sample=False`): prefill with use_cache, then one decode step per
@@ -458,11 +552,17 @@ class Qwen2VLForConditionalGeneration:
         nxt = out.logits[:, -1].argmax(-1)
         seq = [input_ids.cpu(), nxt.cpu().unsqueeze(1)]
         done = torch.zeros(B, dtype=torch.bool)
+        if eos_token_id is None:
+            # no early stop: the whole continuation stays on the device (graph replays, device argmax, ONE final D2H)
+            stepper = GraphedDecodeStep(self, cache, deltas)
+            toks = [nxt]
+            for _ in range(max_new_tokens - 1):
+                toks.append(stepper.step(toks[-1]).argmax(-1))
+            return torch.cat([input_ids.cpu(), torch.stack(toks, 1).cpu()], 1)
         for _ in range(max_new_tokens - 1):
-            if eos_token_id is not None:
-                done |= seq[-1].squeeze(1) == eos_token_id
-                if bool(done.all()):
-                    break
+            done |= seq[-1].squeeze(1) == eos_token_id
+            if bool(done.all()):
+                break
             out = self.forward(input_ids=seq[-1], past_key_values=cache, rope_deltas=deltas, use_cache=True)
             seq.append(out.logits[:, -1].argmax(-1).cpu().unsqueeze(1))
         return torch.cat(seq, 1)

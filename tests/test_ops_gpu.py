@@ -557,3 +557,40 @@ def test_llama_decoder_layer_from_ops(ops):
     r2 = rms(yf, n2)
     ref = yf + (torch.nn.functional.silu(r2 @ wg.float().t()) * (r2 @ wu.float().t())) @ wd.float().t()
     close(out, ref, 6e-2, 3e-2, "llama decoder layer")
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 8])
+@pytest.mark.parametrize("N,K", [(37, 64), (4608, 3584), (10, 18944), (1280, 2816)])
+@pytest.mark.parametrize("epi", ["plain", "bias+silu", "bias+res", "f32", "swiglu", "geglu"])
+def test_linear_skinny_m(ops, M, N, K, epi):
+    """M <= 8 rows take the weight-streaming kernel (decode steps, embedding MLPs); it must agree with the fp32
+    reference and with the tensor-core kernel on every epilogue it accepts."""
+    from paddlemix_b200._lib import lib
+    lib.b200mix_debug_skinny.argtypes, lib.b200mix_debug_skinny.restype = [__import__("ctypes").c_int], None
+    if epi in ("swiglu", "geglu") and N % 2:
+        N += 1
+    a, w = rnd(M, K, seed=110), rnd(N, K, seed=111, scale=K ** -0.5)
+    bias = rnd(N, seed=112, dtype=torch.float32)
+    acc = a.float() @ w.float().t()
+    kw = {}
+    if epi == "plain":
+        ref, b = acc, None
+    elif epi == "bias+silu":
+        ref, b, kw = F.silu(acc + bias), bias, dict(act=1)
+    elif epi == "bias+res":
+        res = rnd(M, N, seed=113)
+        ref, b, kw = acc + bias + res.float(), bias, dict(residual=res)
+    elif epi == "f32":
+        ref, b, kw = acc + bias, bias, dict(out_fp32=True)
+    else:
+        z = acc + bias
+        ref, b = z[:, 0::2] * (F.silu(z[:, 1::2]) if epi == "swiglu" else F.gelu(z[:, 1::2])), bias
+        kw = dict(glu=2 if epi == "swiglu" else 1)
+    out = ops.linear(a, w, b, **kw)
+    close(out, ref, GEMM_ATOL, GEMM_RTOL, f"skinny M{M} {N}x{K} {epi}")
+    lib.b200mix_debug_skinny(0)
+    try:
+        tc = ops.linear(a, w, b, **kw)
+    finally:
+        lib.b200mix_debug_skinny(1)
+    close(out, tc.float(), GEMM_ATOL, GEMM_RTOL, f"skinny vs tensor-core M{M} {N}x{K} {epi}")

@@ -84,3 +84,37 @@ def test_qwen2vl_kv_cache_decode_matches_full_recompute():
     assert torch.equal(gen[:, S], first)
     with pytest.raises(NotImplementedError):
         model(input_ids=input_ids[:, :2], past_key_values=cache, rope_deltas=deltas)  # decode takes one token per sequence
+
+
+def test_graphed_decode_step_matches_eager_and_oracle():
+    """GraphedDecodeStep (CUDA graph, device-side cache positions, GQA rows folded into one attention tile, skinny-M
+    weight-streaming GEMMs) must reproduce the eager decode steps and the oracle's full recompute."""
+    from paddlemix_b200.qwen2_vl import GraphedDecodeStep, Qwen2VLForConditionalGeneration
+    cfg = O.QWEN2VL_CONFIGS["tiny"]
+    P = O.init_qwen2vl_params(cfg, seed=6)
+    model = Qwen2VLForConditionalGeneration(cfg).load_state_dict(P, device=0)
+    grid = [[1, 8, 8], [1, 8, 8], [1, 8, 8]]
+    input_ids, pv = _inputs(cfg, grid, [10, 10, 10], seed=7)
+    B, S = input_ids.shape
+    model.cache_headroom = 16
+    out_a = model(input_ids=input_ids, pixel_values=pv.cuda(), image_grid_thw=torch.tensor(grid), use_cache=True)
+    out_b = model(input_ids=input_ids, pixel_values=pv.cuda(), image_grid_thw=torch.tensor(grid), use_cache=True)
+    stepper = GraphedDecodeStep(model, out_b.past_key_values, out_b.rope_deltas)
+    g = torch.Generator().manual_seed(8)
+    ids = input_ids
+    for step in range(5):
+        new = torch.randint(0, 1000, (B, 1), generator=g)
+        ids = torch.cat([ids, new], 1)
+        eager = model(input_ids=new, past_key_values=out_a.past_key_values, rope_deltas=out_a.rope_deltas, use_cache=True).logits[:, 0]
+        graphed = stepper.step(new.reshape(-1)).clone()
+        assert out_b.past_key_values.get_seq_length() == S + step + 1
+        scale = eager.abs().max().item()
+        assert (graphed - eager).abs().max().item() <= 2e-2 * scale, (step, (graphed - eager).abs().max().item(), scale)
+        ref = O.qwen2vl_prefill(cfg, P, ids, pv, grid)[:, -1]
+        o = graphed.cpu()
+        cos = torch.nn.functional.cosine_similarity(o.flatten(), ref.flatten(), dim=0).item()
+        assert cos >= 0.999 and (o - ref).abs().max().item() <= 0.04 * ref.abs().max().item(), (step, cos)
+    # greedy generate (no eos): the graphed continuation equals the eager one token for token
+    gen = model.generate(input_ids, pixel_values=pv.cuda(), image_grid_thw=torch.tensor(grid), max_new_tokens=6)
+    gen_e = model.generate(input_ids, pixel_values=pv.cuda(), image_grid_thw=torch.tensor(grid), max_new_tokens=6, eos_token_id=-1)
+    assert gen.shape == (B, S + 6) and torch.equal(gen, gen_e)

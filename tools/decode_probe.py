@@ -47,3 +47,20 @@ for _ in range(8):
 e1.record()
 torch.cuda.synchronize()
 print(f"decode_device back-to-back: {e0.elapsed_time(e1) / 8:.2f} ms/step (weights 15.2 GB bf16 -> {15.2 / (e0.elapsed_time(e1) / 8):.2f} TB/s if weight-bound)")
+# the CUDA-graph step (device-side positions, skinny-M weight-streaming GEMMs, GQA rows folded into one attention tile)
+from paddlemix_b200.qwen2_vl import GraphedDecodeStep  # noqa: E402
+stepper = GraphedDecodeStep(model, cache, deltas)
+tok = nxt.cuda().reshape(-1)
+for _ in range(3):
+    tok = stepper.step(tok).argmax(-1)
+torch.cuda.synchronize()
+e0.record()
+t0 = time.perf_counter()
+N = 32
+for _ in range(N):
+    tok = stepper.step(tok).argmax(-1)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / N
+print(f"graphed decode step B={B} past~{cache.length}: {ms:.3f} ms/step device, {(time.perf_counter() - t0) * 1e3 / N:.3f} ms/step wall, "
+      f"{B / ms * 1e3:.0f} tokens/s, {stepper.launches_per_step} launches/step, weights 15.2 GB bf16 -> {15.2 / ms:.2f} TB/s of weight reads")
