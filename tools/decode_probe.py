@@ -64,3 +64,21 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / N
 print(f"graphed decode step B={B} past~{cache.length}: {ms:.3f} ms/step device, {(time.perf_counter() - t0) * 1e3 / N:.3f} ms/step wall, "
       f"{B / ms * 1e3:.0f} tokens/s, {stepper.launches_per_step} launches/step, weights 15.2 GB bf16 -> {15.2 / ms:.2f} TB/s of weight reads")
+# per-call CUDA-event profile of one eager decode step (which kernels the 8 ms go to)
+ops.profile_begin()
+model.decode_body_static(stepper.ids, stepper.cos, stepper.sin, cache, stepper.rows - 1, stepper.kv_lens - 1)
+prof = ops.profile_end(by_tag=True)
+tot = sum(v["ms"] for v in prof.values())
+print(f"# eager decode step, per-call events: {tot:.3f} ms in timed ops.* calls")
+for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:14]:
+    rate = v["work"] / (v["ms"] * 1e-3) / (1e12 if v["unit"] == "flop" else 1e9)
+    print(f"  {k:44s} n={v['calls']:4d} {v['ms']:8.3f} ms  {rate:9.1f} {'TFLOP/s' if v['unit'] == 'flop' else 'GB/s'}")
+# isolated skinny GEMMs (graph-timed): GB/s of weight streaming
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from gemm_bench import timeit  # noqa: E402
+for name, N, K, glu in [("qkv", 4608, 3584, 0), ("o_proj", 3584, 3584, 0), ("gate_up swiglu", 37888, 3584, 2), ("down", 3584, 18944, 0),
+                        ("lm_head f32", 152064, 3584, 0)]:
+    a = (torch.randn(4, K, device="cuda") * 0.05).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.02).to(torch.bfloat16)
+    ms = timeit(lambda: ops.linear(a, w, glu=glu, out_fp32=(name.startswith("lm_head"))), iters=10)
+    print(f"  skinny {name:16s} N={N:6d} K={K:6d}: {ms * 1e3:8.1f} us  {N * K * 2 / ms / 1e6:8.1f} GB/s")
