@@ -120,7 +120,9 @@ int b200mix_conv3x3_small_cin(const void* x, int32_t x_fp32, const void* w, cons
  * cu_seqlens (int32 device [nseq+1], may be NULL) switches on the varlen block-diagonal mode of the Qwen2-VL ViT
  * (modeling_qwen2_vl.py:354-381): then B must be 1 and both q and k are packed along seq. kv_lens (int32 device [B],
  * may be NULL) gives the number of valid keys per batch element (the block-diagonal text mask of STDiT2's
- * MultiHeadCrossAttention, Open-Sora layers/blocks.py:275-331); a batch element with 0 valid keys gets zeros.
+ * MultiHeadCrossAttention, Open-Sora layers/blocks.py:275-331); a batch element with 0 valid keys gets zeros. The K / V
+ * rows between kv_lens[b] and Sk are still read (they take probability 0): they must hold FINITE values (a preallocated
+ * KV cache is zero-filled once).
  * attn_mask (may be NULL): additive bias on the scaled scores, bf16 or fp32 (mask_fp32), element (b, h, q, k) at
  * attn_mask + b*m_sb + h*m_sh + q*m_sq + k (key stride 1; a stride of 0 broadcasts that dimension, so the
  * [B,1,1,Sk] key-padding bias (1 - m) * -10000 of unet_2d_condition.py:916-927 and the full [B,H,Sq,Sk] mask of
@@ -293,6 +295,15 @@ int b200mix_cast(const void* x, void* y, int64_t n, int32_t x_fp32, int32_t y_fp
  * host side by the shim exactly as apply_multimodal_rotary_pos_emb :179-224 does). */
 int b200mix_rope_inplace(void* x, int64_t T, int64_t H, int64_t D, int64_t ld_tok, int64_t ld_head, const float* cos,
                          const float* sin, void* stream);
+
+/* Single-token decode step, one launch per layer for what Qwen2VLAttention.forward does between the qkv projection and
+ * the attention (modeling_qwen2_vl.py:573-596: apply_multimodal_rotary_pos_emb on q and k, then the cache append):
+ * qkv bf16 [B, (heads + 2 * kv_heads) * D] (row stride ld_row): the q heads are rotated in place, the k heads are rotated
+ * into row rows[b] of cache_k, the v heads are copied into row rows[b] of cache_v (caches bf16 [*, kv_heads * D];
+ * rows int64 [B] on the device, so the step is CUDA-graph capturable); cos / sin fp32 [B, D]. */
+int b200mix_decode_rope_cache(void* qkv, int64_t ld_row, int64_t B, int64_t heads, int64_t kv_heads, int64_t D,
+                              const float* cos, const float* sin, const int64_t* rows, void* cache_k, void* cache_v,
+                              void* stream);
 
 #ifdef __cplusplus
 }

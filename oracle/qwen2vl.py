@@ -211,14 +211,26 @@ def rms_norm(x, w, eps):  # Qwen2RMSNorm :467-478
     return (torch.rsqrt(var + eps) * x) * w
 
 
-def decoder_forward(cfg, P: Params, inputs_embeds, position_ids):
-    """Qwen2VLModel.forward (:1037-1130) with a full causal mask (attention_mask all ones), eager attention."""
+def causal_padding_mask(attention_mask, S):
+    """_prepare_4d_causal_attention_mask_with_cache_position (:403-444) for a prefill (cache_position = arange(S)):
+    additive [B, 1, S, S] fp32, finfo.min above the diagonal and on padded keys (attention_mask [B, S], 1 = token)."""
+    mn = torch.finfo(torch.float32).min
+    m = torch.full((S, S), mn).triu(1)[None, None].expand(attention_mask.shape[0], 1, -1, -1).clone()
+    pad = (m + attention_mask[:, None, None, :].to(torch.float32)) == 0  # unmasked by causality but a padded key
+    return m.masked_fill(pad, mn)
+
+
+def decoder_forward(cfg, P: Params, inputs_embeds, position_ids, attention_mask=None):
+    """Qwen2VLModel.forward (:1037-1130), eager attention (:604-607): causal mask, plus the key-padding mask of a padded
+    batch when attention_mask [B, S] has zeros."""
     B, S, H = inputs_embeds.shape
     nh, nkv = cfg["num_attention_heads"], cfg["num_key_value_heads"]
     hd = H // nh
     cos, sin = mrope_cos_sin(cfg, position_ids)
     cos, sin = cos.unsqueeze(1), sin.unsqueeze(1)
     causal = torch.full((S, S), float("-inf")).triu(1)
+    if attention_mask is not None:
+        causal = causal_padding_mask(attention_mask, S)
     x = inputs_embeds
     for i in range(cfg["num_hidden_layers"]):
         b = f"model.layers.{i}"
@@ -236,16 +248,17 @@ def decoder_forward(cfg, P: Params, inputs_embeds, position_ids):
     return rms_norm(x, P["model.norm.weight"], cfg["rms_norm_eps"])
 
 
-def qwen2vl_prefill(cfg, P: Params, input_ids, pixel_values, image_grid_thw, position_ids=None):
-    """Qwen2VLForConditionalGeneration.forward :1382-1503 (prefill, no cache): logits fp32 [B, S, vocab]."""
+def qwen2vl_prefill(cfg, P: Params, input_ids, pixel_values, image_grid_thw, position_ids=None, attention_mask=None):
+    """Qwen2VLForConditionalGeneration.forward :1382-1503 (prefill, no cache): logits fp32 [B, S, vocab]. With a padded
+    batch (attention_mask [B, S] with zeros) only the rows of real tokens are meaningful."""
     embeds = P["model.embed_tokens.weight"][input_ids]
     if pixel_values is not None:
         image_embeds = vision_forward(cfg, P, pixel_values, image_grid_thw)
         embeds = embeds.clone()
         embeds[input_ids == cfg["image_token_id"]] = image_embeds
     if position_ids is None:
-        position_ids, _ = get_rope_index(cfg, input_ids, image_grid_thw)
-    hidden = decoder_forward(cfg, P, embeds, position_ids)
+        position_ids, _ = get_rope_index(cfg, input_ids, image_grid_thw, attention_mask)
+    hidden = decoder_forward(cfg, P, embeds, position_ids, attention_mask)
     return linear(hidden, P, "lm_head").float()
 
 

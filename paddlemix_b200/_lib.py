@@ -97,6 +97,8 @@ SIGNATURES = {
     "b200mix_unpatchify3d": [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p],
     "b200mix_cast": [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p],
     "b200mix_rope_inplace": [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p],
+    "b200mix_decode_rope_cache": [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p],
 }
 STRING_GETTERS = ("b200mix_last_error", "b200mix_version")
 

@@ -424,6 +424,32 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ x, long long T, int H, i
   }
 }
 
+// Decode-step glue in one launch (was: RoPE(q), RoPE(k), two staging copies, two cache scatters): for every sequence b of
+// a single-token step, rotate the q heads of the fused qkv row in place, rotate the k heads INTO the cache row rows[b],
+// copy the v heads into the cache row. grid (heads + 2 * kv_heads, B); same fp32 expression as rope_kernel.
+__global__ void decode_rope_cache_kernel(__nv_bfloat16* __restrict__ qkv, long long ld_row, int nh, int nkv, int D,
+                                         const float* __restrict__ cs, const float* __restrict__ sn,
+                                         const long long* __restrict__ rows, __nv_bfloat16* __restrict__ cache_k,
+                                         __nv_bfloat16* __restrict__ cache_v) {
+  const int b = blockIdx.y, hh = blockIdx.x, half = D >> 1;
+  const long long kvd = (long long)nkv * D;
+  __nv_bfloat16* src = qkv + b * ld_row + (long long)hh * D;  // q heads, then k heads, then v heads, all D wide
+  if (hh >= nh + nkv) {
+    __nv_bfloat16* dst = cache_v + rows[b] * kvd + (long long)(hh - nh - nkv) * D;
+    for (int i = threadIdx.x; i < D / 8; i += blockDim.x)
+      reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    return;
+  }
+  __nv_bfloat16* dst = hh < nh ? src : cache_k + rows[b] * kvd + (long long)(hh - nh) * D;
+  const float* c = cs + (long long)b * D;
+  const float* s = sn + (long long)b * D;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float x1 = __bfloat162float(src[i]), x2 = __bfloat162float(src[i + half]);
+    dst[i] = __float2bfloat16(x1 * c[i] - x2 * s[i]);
+    dst[i + half] = __float2bfloat16(x2 * c[i + half] + x1 * s[i + half]);
+  }
+}
+
 __global__ void patchify_kernel(const void* __restrict__ x, int x_fp32, __nv_bfloat16* __restrict__ y, int B, int C,
                                 int H, int W, int p) {
   const int h = H / p, w = W / p, K = C * p * p;
@@ -777,6 +803,22 @@ extern "C" int b200mix_rope_inplace(void* x, int64_t T, int64_t H, int64_t D, in
   B200_CHECK_ARG(x && cos && sin && D % 2 == 0, "rope: bad arguments");
   rope_kernel<<<ew_grid(T * H * (D / 2), 256), 256, 0, ST(stream)>>>(reinterpret_cast<__nv_bfloat16*>(x), T, (int)H,
                                                                      (int)D, ld_tok, ld_head, cos, sin);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200mix_decode_rope_cache(void* qkv, int64_t ld_row, int64_t B, int64_t heads, int64_t kv_heads, int64_t D,
+                                         const float* cos, const float* sin, const int64_t* rows, void* cache_k,
+                                         void* cache_v, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(qkv && cos && sin && rows && cache_k && cache_v, "decode_rope_cache: null pointer");
+  B200_CHECK_ARG(B > 0 && heads > 0 && kv_heads > 0 && D % 8 == 0 && ld_row % 8 == 0 && B < 65536,
+                 "decode_rope_cache: bad shape (head_dim and the row stride must be multiples of 8)");
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+  decode_rope_cache_kernel<<<dim3((unsigned)(heads + 2 * kv_heads), (unsigned)B), 64, 0, ST(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(qkv), ld_row, (int)heads, (int)kv_heads, (int)D, cos, sin,
+      reinterpret_cast<const long long*>(rows), reinterpret_cast<__nv_bfloat16*>(cache_k),
+      reinterpret_cast<__nv_bfloat16*>(cache_v));
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -614,120 +614,215 @@ __global__ void __launch_bounds__(320, 1)
 // Skinny-M Linear (M <= 8 activation rows: single-token decode steps, the UNet's time / text-time embedding MLPs):
 // the work is streaming W once from HBM, so this is a CUDA-core weight-streaming kernel, not a tensor-core tile (a
 // 256-row MMA tile would spend 97 % of its rows on zeros: round 1 measured 1.2 TB/s of weight reads through igemm).
-// One warp owns TWO consecutive output rows n0, n0 + 1 (a GLU pair when the rows are interleaved value / gate): every
-// lane streams 16-byte pieces of both weight rows (coalesced 512 B per warp and row), the activations of the current
-// K chunk sit in shared memory as fp32, products accumulate on packed fp32 pairs (FFMA2), one butterfly reduction
-// per row at the end. Bound: HBM (N * K * 2 bytes of weights); epilogue = bias / activation / GLU / residual.
+//   * one warp owns SK_R = 4 consecutive output rows (two GLU pairs when the rows are interleaved value / gate); every
+//     lane streams 16-byte pieces of the four weight rows (512 coalesced bytes per warp and row, the next k-step's
+//     loads are issued before the current one is consumed: 8 x 16 B in flight per lane);
+//   * the CTA's K range of the activations is staged ONCE in shared memory as fp32, laid out so that a warp's
+//     LDS.128 is conflict-free ([k-step][half][lane][4]); one shared-memory read feeds four weight rows;
+//   * K is split over the CTAs of a thread-block cluster (1-8) when the N direction alone cannot fill the machine or
+//     the K range does not fit shared memory; the partial sums travel to the cluster's first CTA through distributed
+//     shared memory and are added in rank order (deterministic, no workspace, no atomics);
+//   * products accumulate on packed fp32 pairs (FFMA2), one butterfly reduction per (row, activation row) at the end.
+// Bound: HBM (N * K * 2 bytes of weights); epilogue = bias / activation / GLU / residual / fp32 output.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int SK_KC = 2048;  // K chunk staged in shared memory (M * 8 KB)
+constexpr int SK_R = 4;                 // output rows per warp
+constexpr int SK_ROWS_PER_CTA = 8 * SK_R;
+constexpr int SK_SMEM_FLOATS = 24576;   // 96 KB of staged activations per CTA (two CTAs per SM)
+constexpr int SK_MAX_SPLITS = 8;
 
 __device__ __forceinline__ void sk_unpack8(const uint4& w, uint64_t (&p)[4]) {
   p[0] = pack_f32x2(bf16_lo(w.x), bf16_hi(w.x)), p[1] = pack_f32x2(bf16_lo(w.y), bf16_hi(w.y));
   p[2] = pack_f32x2(bf16_lo(w.z), bf16_hi(w.z)), p[3] = pack_f32x2(bf16_lo(w.w), bf16_hi(w.w));
 }
+#ifndef SK_PREFETCH
+#define SK_PREFETCH 4  // k-steps (of 256 elements per row) the L2 prefetch window runs ahead of the register loads
+#endif
+// weights are read exactly once: no L1 allocation
+__device__ __forceinline__ uint4 ldg_stream(const __nv_bfloat16* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void st_shared_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
 
 template <int M>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, M <= 4 ? 2 : 1)
     skinny_linear_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __nv_bfloat16* __restrict__ W,
                          long long ldw, void* __restrict__ C, long long ldc, int N, int K, const float* __restrict__ bias,
                          const __nv_bfloat16* __restrict__ residual, long long ldr, int act, int glu, int out_fp32,
-                         int rows) {  // rows <= M: the template rounds the row count up (zero rows are staged for the rest)
-  extern __shared__ __align__(16) float sA[];  // [M][SK_KC]
+                         int rows,     // rows <= M: the template rounds the row count up (zero rows are staged for the rest)
+                         int splits,   // cluster size = number of K ranges
+                         int kpart,    // K elements per cluster rank (multiple of 256)
+                         int ksm) {    // K elements staged per pass (multiple of 256, <= SK_SMEM_FLOATS / M)
+  extern __shared__ __align__(16) float sA[];  // [M][ksm], element (step, lane, j) at step * 256 + (j / 4) * 128 + lane * 4 + j % 4
+  __shared__ float red[SK_MAX_SPLITS][8][M * SK_R];
   pdl_wait();
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = (blockIdx.x * 8 + warp) * 2;
-  const bool have0 = n0 < N, have1 = n0 + 1 < N;
-  const __nv_bfloat16* w0 = W + static_cast<long long>(have0 ? n0 : 0) * ldw;
-  const __nv_bfloat16* w1 = W + static_cast<long long>(have1 ? n0 + 1 : 0) * ldw;
-  uint64_t acc[M][2];
+  const int rank = splits > 1 ? (int)cluster_ctarank() : 0;
+  const int n0 = ((int)(blockIdx.x / splits) * 8 + warp) * SK_R;
+  const __nv_bfloat16* w[SK_R];
 #pragma unroll
-  for (int m = 0; m < M; ++m) acc[m][0] = acc[m][1] = 0ull;
-  for (int k0 = 0; k0 < K; k0 += SK_KC) {
-    const int kc = min(SK_KC, K - k0);
+  for (int r = 0; r < SK_R; ++r) w[r] = W + static_cast<long long>(min(n0 + r, N - 1)) * ldw;  // clamped: results of rows >= N are dropped
+  uint64_t acc[M][SK_R];
+#pragma unroll
+  for (int m = 0; m < M; ++m)
+#pragma unroll
+    for (int r = 0; r < SK_R; ++r) acc[m][r] = 0ull;
+  const int kend = min(K, (rank + 1) * kpart);
+  for (int k0 = rank * kpart; k0 < kend; k0 += ksm) {
+    const int kc = min(ksm, kend - k0);
+    // the weight stream does not depend on the staged activations: first loads and the L2 prefetch window go out first
+    int kk = lane * 8;
+    uint4 cur[SK_R];
+    if (kk < kc) {
+#pragma unroll
+      for (int r = 0; r < SK_R; ++r) cur[r] = ldg_stream(w[r] + k0 + kk);
+    }
+#pragma unroll
+    for (int d = 1; d <= SK_PREFETCH; ++d)
+      if (kk + 256 * d < kc) {
+#pragma unroll
+        for (int r = 0; r < SK_R; ++r) prefetch_l2(w[r] + k0 + kk + 256 * d);
+      }
     __syncthreads();
     for (int i = threadIdx.x * 8; i < M * kc; i += 256 * 8) {  // stage A[:, k0 : k0 + kc] as fp32 (kc % 8 == 0)
       const int m = i / kc, k = i - m * kc;
       const uint4 v = m < rows ? __ldg(reinterpret_cast<const uint4*>(A + m * lda + k0 + k)) : make_uint4(0u, 0u, 0u, 0u);
-      float* d = sA + m * SK_KC + k;
-      d[0] = bf16_lo(v.x), d[1] = bf16_hi(v.x), d[2] = bf16_lo(v.y), d[3] = bf16_hi(v.y);
-      d[4] = bf16_lo(v.z), d[5] = bf16_hi(v.z), d[6] = bf16_lo(v.w), d[7] = bf16_hi(v.w);
+      float* d = sA + m * ksm + (k >> 8) * 256 + ((k & 255) >> 3) * 4;
+      *reinterpret_cast<float4*>(d) = make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+      *reinterpret_cast<float4*>(d + 128) = make_float4(bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w));
     }
     __syncthreads();
-    if (!have0) continue;
-#pragma unroll 2
-    for (int kk = lane * 8; kk < kc; kk += 256) {
-      const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(w0 + k0 + kk));
-      const uint4 r1 = have1 ? __ldg(reinterpret_cast<const uint4*>(w1 + k0 + kk)) : make_uint4(0u, 0u, 0u, 0u);
-      uint64_t p0[4], p1[4];
-      sk_unpack8(r0, p0);
-      sk_unpack8(r1, p1);
+    for (; kk < kc; kk += 256) {
+      uint4 nxt[SK_R];
+      if (kk + 256 < kc) {
+#pragma unroll
+        for (int r = 0; r < SK_R; ++r) nxt[r] = ldg_stream(w[r] + k0 + kk + 256);
+      }
+      if (kk + 256 * (SK_PREFETCH + 1) < kc) {
+#pragma unroll
+        for (int r = 0; r < SK_R; ++r) prefetch_l2(w[r] + k0 + kk + 256 * (SK_PREFETCH + 1));
+      }
+#ifdef SK_NO_MATH  // diagnostic build: the weight stream alone (loads kept alive by an integer fold), no products
+#pragma unroll
+      for (int r = 0; r < SK_R; ++r) acc[0][r] ^= (uint64_t)(cur[r].x ^ cur[r].y ^ cur[r].z ^ cur[r].w);
+      if (false) {
+#else
+      {
+#endif
+      uint64_t p[SK_R][4];
+#pragma unroll
+      for (int r = 0; r < SK_R; ++r) sk_unpack8(cur[r], p[r]);
+      const float* sa = sA + (kk - lane * 8) + lane * 4;
 #pragma unroll
       for (int m = 0; m < M; ++m) {
-        const float4 a = *reinterpret_cast<const float4*>(sA + m * SK_KC + kk);
-        const float4 b = *reinterpret_cast<const float4*>(sA + m * SK_KC + kk + 4);
+        const float4 a = *reinterpret_cast<const float4*>(sa + m * ksm);
+        const float4 b = *reinterpret_cast<const float4*>(sa + m * ksm + 128);
         const uint64_t pa[4] = {pack_f32x2(a.x, a.y), pack_f32x2(a.z, a.w), pack_f32x2(b.x, b.y), pack_f32x2(b.z, b.w)};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[m][0] = ffma2(p0[j], pa[j], acc[m][0]);
-          acc[m][1] = ffma2(p1[j], pa[j], acc[m][1]);
-        }
+        for (int r = 0; r < SK_R; ++r)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[m][r] = ffma2(p[r][j], pa[j], acc[m][r]);
       }
+      }
+#pragma unroll
+      for (int r = 0; r < SK_R; ++r) cur[r] = nxt[r];
     }
   }
-  if (!have0) return;
+  // warp totals -> red[rank][warp][m * SK_R + r] of the cluster's first CTA (lane m * SK_R + r stores its own entry)
+  const uint32_t red_dst = splits > 1 ? mapa_smem(&red[rank][warp][0], 0) : smem_u32(&red[0][warp][0]);
+#pragma unroll
+  for (int m = 0; m < M; ++m)
+#pragma unroll
+    for (int r = 0; r < SK_R; ++r) {
+      float v, t;
+      unpack_f32x2(acc[m][r], v, t), v += t;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == m * SK_R + r) {
+        if (splits > 1) st_shared_cluster_f32(red_dst + 4u * (m * SK_R + r), v);
+        else red[0][warp][m * SK_R + r] = v;
+      }
+    }
+  if (splits > 1) cluster_sync_all();  // every thread of every CTA of the cluster gets here (no early exits above)
+  else __syncwarp();
+  if (rank != 0) return;
+  const int m = lane / (SK_R / 2), n = n0 + 2 * (lane % (SK_R / 2));
+  if (lane >= M * (SK_R / 2) || m >= rows || n >= N) return;
+  const bool have1 = n + 1 < N;
+  float v0 = 0.0f, v1 = 0.0f;
+  for (int s = 0; s < splits; ++s) {  // fixed order: bit-reproducible
+    v0 += red[s][warp][m * SK_R + (n - n0)];
+    v1 += red[s][warp][m * SK_R + (n - n0) + 1];
+  }
   const ActCoef ac = act_coef(act, glu);
-#pragma unroll
-  for (int m = 0; m < M; ++m) {
-    float v0, v1, t;
-    unpack_f32x2(acc[m][0], v0, t), v0 += t;
-    unpack_f32x2(acc[m][1], v1, t), v1 += t;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-    }
-    if (lane != 0 || m >= rows) continue;
-    if (bias) v0 += bias[n0], v1 += have1 ? bias[n0 + 1] : 0.0f;
-    if (glu) {  // interleaved rows: 2j = value, 2j + 1 = gate
-      const float o = v0 * act_eval(v1, ac);
-      if (out_fp32) reinterpret_cast<float*>(C)[m * ldc + (n0 >> 1)] = o;
-      else reinterpret_cast<__nv_bfloat16*>(C)[m * ldc + (n0 >> 1)] = __float2bfloat16(o);
-      continue;
-    }
-    if (act != B200MIX_ACT_NONE) v0 = act_eval(v0, ac), v1 = act_eval(v1, ac);
-    if (residual) {
-      v0 += __bfloat162float(residual[m * ldr + n0]);
-      if (have1) v1 += __bfloat162float(residual[m * ldr + n0 + 1]);
-    }
-    if (out_fp32) {
-      float* c = reinterpret_cast<float*>(C) + m * ldc + n0;
-      c[0] = v0;
-      if (have1) c[1] = v1;
-    } else {
-      __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(C) + m * ldc + n0;
-      c[0] = __float2bfloat16(v0);
-      if (have1) c[1] = __float2bfloat16(v1);
-    }
+  if (bias) v0 += bias[n], v1 += have1 ? bias[n + 1] : 0.0f;
+  if (glu) {  // interleaved rows: 2j = value, 2j + 1 = gate
+    const float o = v0 * act_eval(v1, ac);
+    if (out_fp32) reinterpret_cast<float*>(C)[m * ldc + (n >> 1)] = o;
+    else reinterpret_cast<__nv_bfloat16*>(C)[m * ldc + (n >> 1)] = __float2bfloat16(o);
+    return;
+  }
+  if (act != B200MIX_ACT_NONE) v0 = act_eval(v0, ac), v1 = act_eval(v1, ac);
+  if (residual) {
+    v0 += __bfloat162float(residual[m * ldr + n]);
+    if (have1) v1 += __bfloat162float(residual[m * ldr + n + 1]);
+  }
+  if (out_fp32) {
+    float* c = reinterpret_cast<float*>(C) + m * ldc + n;
+    c[0] = v0;
+    if (have1) c[1] = v1;
+  } else {
+    __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(C) + m * ldc + n;
+    c[0] = __float2bfloat16(v0);
+    if (have1) c[1] = __float2bfloat16(v1);
   }
 }
 
 static int g_skinny = 1;  // test hook: 0 = M <= 8 problems go through the tensor-core kernel again
+static int g_skinny_splits = 0;  // test hook: force the K split (0 = automatic)
 
 template <int M>
 static int launch_skinny(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int rows, int N,
                          int K, const b200mix_epilogue* e, cudaStream_t stream) {
-  const size_t smem = (size_t)M * SK_KC * sizeof(float);
+  constexpr int kcap = SK_SMEM_FLOATS / M / 256 * 256;  // K elements one CTA can stage
+  const int ctas_n = (N + SK_ROWS_PER_CTA - 1) / SK_ROWS_PER_CTA;
+  // K ranges (= cluster size): every candidate that lets a CTA stage its range in one pass is costed as
+  // rounds-over-the-machine x (K elements per CTA + a fixed per-CTA cost in the same unit); ranges are at least 512 long.
+  const int slots = (M <= 4 ? 2 : 1) * num_sms();
+  const int s_min = std::min(SK_MAX_SPLITS, (K + kcap - 1) / kcap);
+  int splits = s_min, kpart = 0;
+  long long best = -1;
+  for (int s = s_min; s <= SK_MAX_SPLITS && (s == s_min || K / s >= 512); ++s) {
+    const int kp = ((K + s - 1) / s + 255) / 256 * 256;
+    const int parts = (K + kp - 1) / kp;  // empty ranges dropped
+    const long long rounds = ((long long)ctas_n * parts + slots - 1) / slots;
+    const long long cost = rounds * (std::min(kp, K) + 768ll);
+    if (best < 0 || cost < best) best = cost, splits = parts, kpart = kp;
+  }
+  if (g_skinny_splits > 0) {
+    splits = std::min(g_skinny_splits, SK_MAX_SPLITS);
+    kpart = ((K + splits - 1) / splits + 255) / 256 * 256;
+    splits = (K + kpart - 1) / kpart;
+  }
+  const int ksm = std::min(kpart, kcap);
+  const size_t smem = (size_t)M * ksm * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(skinny_linear_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(skinny_linear_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(SK_SMEM_FLOATS * sizeof(float))));
     configured = true;
   }
-  const unsigned grid = (unsigned)((N + 15) / 16);
-  B200_CUDA(launch_pdl(skinny_linear_kernel<M>, dim3(grid), dim3(256), smem, stream, 1,
+  B200_CUDA(launch_pdl(skinny_linear_kernel<M>, dim3((unsigned)(ctas_n * splits)), dim3(256), smem, stream, splits,
                        reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(W), ldw, C, ldc, N,
                        K, e ? e->bias : nullptr, e ? reinterpret_cast<const __nv_bfloat16*>(e->residual) : nullptr,
-                       e ? (long long)e->ldr : 0ll, e ? e->act : 0, e ? e->glu : 0, e ? e->out_fp32 : 0, rows));
+                       e ? (long long)e->ldr : 0ll, e ? e->act : 0, e ? e->glu : 0, e ? e->out_fp32 : 0, rows, splits, kpart,
+                       ksm));
   return 0;
 }
 
@@ -861,6 +956,7 @@ extern "C" void b200mix_debug_force_bn(int bn) { g_force_bn = bn; }
 extern "C" void b200mix_debug_gemm_pair(int on) { b200::g_gemm_pair = on; }
 extern "C" void b200mix_debug_max_clusters(int n) { b200::g_max_clusters = n; }
 extern "C" void b200mix_debug_skinny(int on) { b200::g_skinny = on; }
+extern "C" void b200mix_debug_skinny_splits(int splits) { b200::g_skinny_splits = splits; }
 
 extern "C" int b200mix_linear(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M,
                               int64_t N, int64_t K, const b200mix_epilogue* epi, void* stream) {

@@ -512,6 +512,18 @@ def rope_inplace(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, rot_dim:
     return x
 
 
+def decode_rope_cache(qkv: torch.Tensor, heads: int, kv_heads: int, head_dim: int, cos: torch.Tensor, sin: torch.Tensor,
+                      rows: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor):
+    """qkv bf16 [B, (heads + 2*kv_heads) * head_dim] of a single-token step: RoPE on the q heads in place, RoPE'd k heads and
+    the v heads written into row rows[b] (int64, device) of the flattened caches [*, kv_heads * head_dim]."""
+    _req(qkv, bf16, "qkv"), _req(rows, torch.int64, "rows"), _req(cache_k, bf16, "cache_k"), _req(cache_v, bf16, "cache_v")
+    assert qkv.stride(1) == 1 and qkv.shape[1] == (heads + 2 * kv_heads) * head_dim
+    assert cache_k.is_contiguous() and cache_v.is_contiguous() and cos.is_contiguous() and sin.is_contiguous()
+    check(lib.b200mix_decode_rope_cache(_p(qkv), qkv.stride(0), qkv.shape[0], heads, kv_heads, head_dim, _p(cos), _p(sin),
+                                        _p(rows), _p(cache_k), _p(cache_v), _stream()), "b200mix_decode_rope_cache")
+    _count()
+
+
 def gather_rows(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
     """table bf16 [V, D], ids int64 [n] (device) -> bf16 [n, D]."""
     _req(table, bf16, "table"), _req(ids, torch.int64, "ids")

@@ -56,12 +56,17 @@ class Qwen2VLCausalLMOutputWithPast:
 class KVCache:
     """past_key_values of the LLM (modeling_qwen2_vl.py:591-596 appends along the sequence axis): one preallocated
     [B, max_len, kv_heads, head_dim] bf16 buffer per layer for K (after RoPE) and V, plus the number of valid positions
-    (all sequences of a batch have the same length: padded batches are outside this path)."""
+    (the same for every sequence of the batch). A padded prompt batch keeps its padding inside the cache: `key_bias`
+    (fp32 [B, max_len], 0 on real tokens and on the positions still to be generated, -inf on the prompt's padding) is the
+    additive key mask every later decode step applies."""
 
     def __init__(self, n_layers, B, max_len, n_kv, head_dim, device):
-        self.k = [torch.empty(B, max_len, n_kv, head_dim, device=device, dtype=bf16) for _ in range(n_layers)]
-        self.v = [torch.empty(B, max_len, n_kv, head_dim, device=device, dtype=bf16) for _ in range(n_layers)]
+        # zero-filled: with kv_lens the kernel multiplies the not-yet-written rows of the last key block by probability 0,
+        # which is only 0 when those rows are finite (recycled allocator memory may hold inf / nan bit patterns)
+        self.k = [torch.zeros(B, max_len, n_kv, head_dim, device=device, dtype=bf16) for _ in range(n_layers)]
+        self.v = [torch.zeros(B, max_len, n_kv, head_dim, device=device, dtype=bf16) for _ in range(n_layers)]
         self.length, self.max_len, self.batch = 0, max_len, B
+        self.key_bias = None
 
     def get_seq_length(self):
         return self.length
@@ -394,7 +399,10 @@ class Qwen2VLForConditionalGeneration:
                 rope_deltas=None):
         """Same signature as the reference (:1382-1399). Prefill (optionally filling a KV cache: use_cache=True) and
         single-token decode (past_key_values = the KVCache a previous call returned; position = past length +
-        rope_deltas, :1413-1441). attention_mask must be all ones."""
+        rope_deltas, :1413-1441). A padded batch (attention_mask [B, S] with zeros, either side) runs with the reference's
+        causal + key-padding mask (:403-444, applied at :604-607) and its mask-aware M-RoPE positions; the rows of padding
+        tokens carry no meaning (as in the reference). During decode the padding recorded in the cache is used; a mask
+        passed then only has to be consistent in shape."""
         if self.device is None:
             raise RuntimeError("load_state_dict() must be called before forward()")
         for name, val in (("labels", labels), ("pixel_values_videos", pixel_values_videos),
@@ -403,8 +411,6 @@ class Qwen2VLForConditionalGeneration:
                 raise NotImplementedError(f"Qwen2VL(b200).forward: `{name}` is outside the inference hot path")
         if output_attentions or output_hidden_states:
             raise NotImplementedError("output_attentions / output_hidden_states are outside the inference hot path")
-        if attention_mask is not None and not bool((attention_mask == 1).all()):
-            raise NotImplementedError("padded batches are outside the hot path (attention_mask must be all ones)")
         c, dev = self.config, self.device
         ids_host = input_ids.cpu()
         B, S = ids_host.shape
@@ -433,14 +439,27 @@ class Qwen2VLForConditionalGeneration:
         if use_cache:
             cache = past_key_values if past_key_values is not None else KVCache(
                 c.num_hidden_layers, B, S + int(getattr(self, "cache_headroom", 256)), c.num_key_value_heads, self.head_dim, dev)
-        logits = self.prefill_device(ids_dev, B, S, cos, sin, pixel_values, image_grid_thw, image_idx, cache=cache)
+        attn_bias = None
+        if attention_mask is not None and not bool((attention_mask == 1).all()):
+            if tuple(attention_mask.shape) != (B, S):
+                raise ValueError(f"attention_mask {tuple(attention_mask.shape)} does not match input_ids {(B, S)}")
+            key_ok = attention_mask.to(dev) == 1
+            allowed = torch.ones(S, S, dtype=torch.bool, device=dev).tril()[None] & key_ok[:, None, :]
+            attn_bias = torch.zeros(B, 1, S, S, device=dev, dtype=bf16).masked_fill_(~allowed[:, None], float("-inf"))
+            if cache is not None:
+                cache.key_bias = torch.zeros(B, cache.max_len, device=dev, dtype=torch.float32)
+                cache.key_bias[:, :S].masked_fill_(~key_ok, float("-inf"))
+        logits = self.prefill_device(ids_dev, B, S, cos, sin, pixel_values, image_grid_thw, image_idx, cache=cache,
+                                     attn_bias=attn_bias)
         if return_dict is False:
             return (logits,) if cache is None else (logits, cache)
         return Qwen2VLCausalLMOutputWithPast(logits=logits, past_key_values=cache, rope_deltas=rope_deltas)
 
-    def prefill_device(self, ids_dev, B, S, cos, sin, pixel_values=None, image_grid_thw=None, image_idx=None, cache=None):
+    def prefill_device(self, ids_dev, B, S, cos, sin, pixel_values=None, image_grid_thw=None, image_idx=None, cache=None,
+                       attn_bias=None):
         """The device part of forward(): everything below is kernel launches on the current stream (no host sync).
-        ids_dev int64 [B*S]; cos/sin fp32 [B*S, head_dim] (M-RoPE tables); image_idx int64 [n_image_tokens]."""
+        ids_dev int64 [B*S]; cos/sin fp32 [B*S, head_dim] (M-RoPE tables); image_idx int64 [n_image_tokens]; attn_bias =
+        additive [B, 1, S, S] mask of a padded batch (causality included) or None for the plain causal mask."""
         from .. import ops
         from .._lib import GLU_SWIGLU
         c, hd = self.config, self.head_dim
@@ -468,7 +487,8 @@ class Qwen2VLForConditionalGeneration:
             if cache is not None:  # key_states / value_states after RoPE are what the reference caches (:591-596)
                 cache.k[li][:, :S].copy_(k.unflatten(0, (B, S)))
                 cache.v[li][:, :S].copy_(vv.unflatten(0, (B, S)))
-            a = ops.sdpa(q.unflatten(0, (B, S)), k.unflatten(0, (B, S)), vv.unflatten(0, (B, S)), scale=hd ** -0.5, causal=True)
+            a = ops.sdpa(q.unflatten(0, (B, S)), k.unflatten(0, (B, S)), vv.unflatten(0, (B, S)), scale=hd ** -0.5,
+                         causal=attn_bias is None, attn_mask=attn_bias)
             x = ops.linear(a.reshape(B * S, qd), L["o"], residual=x)
             h2 = ops.layernorm(x, L["ln2"], None, eps=c.rms_norm_eps, rms=True)
             g = ops.linear(h2, L["gu"], glu=GLU_SWIGLU)  # silu(gate) * up
@@ -500,7 +520,8 @@ class Qwen2VLForConditionalGeneration:
             ops.rope_inplace(k, cos, sin)
             cache.k[li][:, P].copy_(k)
             cache.v[li][:, P].copy_(vv)
-            a = ops.sdpa(q.unsqueeze(1), cache.k[li][:, :P + 1], cache.v[li][:, :P + 1], scale=hd ** -0.5)  # [B,1,nh,hd]
+            kb = None if cache.key_bias is None else cache.key_bias[:, None, None, :P + 1]
+            a = ops.sdpa(q.unsqueeze(1), cache.k[li][:, :P + 1], cache.v[li][:, :P + 1], scale=hd ** -0.5, attn_mask=kb)  # [B,1,nh,hd]
             x = ops.linear(a.reshape(B, qd), L["o"], residual=x)
             h2 = ops.layernorm(x, L["ln2"], None, eps=c.rms_norm_eps, rms=True)
             g = ops.linear(h2, L["gu"], glu=GLU_SWIGLU)
@@ -525,16 +546,12 @@ class Qwen2VLForConditionalGeneration:
         for li, L in enumerate(self.layers):
             h1 = ops.layernorm(x, L["ln1"], None, eps=c.rms_norm_eps, rms=True)
             qkv = ops.linear(h1, *L["qkv"])
-            q = qkv[:, :qd].unflatten(-1, (nh, hd))
-            k = qkv[:, qd:qd + kvd].unflatten(-1, (nkv, hd))
-            ops.rope_inplace(q, cos, sin)
-            ops.rope_inplace(k, cos, sin)
-            ops.scatter_rows(qkv[:, qd:qd + kvd].contiguous(), rows, cache.k[li].view(-1, kvd))
-            ops.scatter_rows(qkv[:, qd + kvd:].contiguous(), rows, cache.v[li].view(-1, kvd))
+            ops.decode_rope_cache(qkv, nh, nkv, hd, cos, sin, rows, cache.k[li].view(-1, kvd), cache.v[li].view(-1, kvd))
             a = torch.empty(B, qd, device=x.device, dtype=bf16)
             qg = qkv.as_strided((B, G, nkv, hd), (qkv.stride(0), hd, G * hd, 1), qkv.storage_offset())
             ag = a.as_strided((B, G, nkv, hd), (qd, hd, G * hd, 1))
-            ops.sdpa(qg, cache.k[li], cache.v[li], scale=hd ** -0.5, kv_lens=kv_lens, out=ag)
+            kb = None if cache.key_bias is None else cache.key_bias[:, None, None, :]
+            ops.sdpa(qg, cache.k[li], cache.v[li], scale=hd ** -0.5, kv_lens=kv_lens, attn_mask=kb, out=ag)
             x = ops.linear(a, L["o"], residual=x)
             h2 = ops.layernorm(x, L["ln2"], None, eps=c.rms_norm_eps, rms=True)
             x = ops.linear(ops.linear(h2, L["gu"], glu=GLU_SWIGLU), L["down"], residual=x)
@@ -542,12 +559,17 @@ class Qwen2VLForConditionalGeneration:
         return ops.linear(hN, self.lm_head, out_fp32=True)
 
     @torch.no_grad()
-    def generate(self, input_ids, pixel_values=None, image_grid_thw=None, max_new_tokens: int = 16, eos_token_id=None):
+    def generate(self, input_ids, pixel_values=None, image_grid_thw=None, max_new_tokens: int = 16, eos_token_id=None,
+                 attention_mask=None):
         """Greedy decoding (generation_utils' default `do_sample=False`): prefill with use_cache, then one decode step per
-        token; returns [B, S + n_new] token ids (generation stops early when every sequence has produced EOS)."""
+        token; returns [B, S + n_new] token ids (generation stops early when every sequence has produced EOS). Prompts of
+        different lengths are LEFT-padded (attention_mask zeros in front), so that every prompt ends at column S - 1."""
         B, S = input_ids.shape
+        if attention_mask is not None and not bool((attention_mask[:, -1] == 1).all()):
+            raise ValueError("generate(): pad on the left (the last column of attention_mask must be all ones)")
         self.cache_headroom = max_new_tokens
-        out = self.forward(input_ids=input_ids, pixel_values=pixel_values, image_grid_thw=image_grid_thw, use_cache=True)
+        out = self.forward(input_ids=input_ids, attention_mask=attention_mask, pixel_values=pixel_values,
+                           image_grid_thw=image_grid_thw, use_cache=True)
         cache, deltas = out.past_key_values, out.rope_deltas
         nxt = out.logits[:, -1].argmax(-1)
         seq = [input_ids.cpu(), nxt.cpu().unsqueeze(1)]

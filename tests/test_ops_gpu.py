@@ -594,3 +594,24 @@ def test_linear_skinny_m(ops, M, N, K, epi):
     finally:
         lib.b200mix_debug_skinny(1)
     close(out, tc.float(), GEMM_ATOL, GEMM_RTOL, f"skinny vs tensor-core M{M} {N}x{K} {epi}")
+
+
+@pytest.mark.parametrize("splits", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("M,N,K", [(4, 3584, 18944), (4, 38, 3584), (8, 130, 1096), (1, 1000, 4096), (7, 66, 520)])
+def test_linear_skinny_cluster_split_k(ops, M, N, K, splits):
+    """The K split of the skinny kernel (partials travel through distributed shared memory to the cluster's first CTA and
+    are added in rank order): every forced split factor gives the fp32 reference and is bit-identical run to run."""
+    import ctypes
+    from paddlemix_b200._lib import lib
+    lib.b200mix_debug_skinny_splits.argtypes, lib.b200mix_debug_skinny_splits.restype = [ctypes.c_int], None
+    a, w = rnd(M, K, seed=120), rnd(N, K, seed=121, scale=K ** -0.5)
+    bias, res = rnd(N, seed=122, dtype=torch.float32), rnd(M, N, seed=123)
+    ref = a.float() @ w.float().t() + bias + res.float()
+    lib.b200mix_debug_skinny_splits(splits)
+    try:
+        out = ops.linear(a, w, bias, residual=res)
+        again = ops.linear(a, w, bias, residual=res)
+    finally:
+        lib.b200mix_debug_skinny_splits(0)
+    close(out, ref, GEMM_ATOL, GEMM_RTOL, f"skinny split{splits} M{M} {N}x{K}")
+    assert torch.equal(out, again)

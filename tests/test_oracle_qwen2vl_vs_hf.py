@@ -70,3 +70,42 @@ def test_oracle_matches_hf_qwen2vl():
     assert (ours - ref).abs().max().item() < tol, (ours - ref).abs().max().item()
     if ref_auto is not None:
         assert (ours - ref_auto).abs().max().item() < tol, "M-RoPE position ids differ from transformers'"
+
+
+@pytest.mark.parametrize("side", ["left", "right"])
+def test_oracle_matches_hf_qwen2vl_padded_batch(side):
+    """Padded batches (attention_mask with zeros): causal + key-padding mask and the mask-aware M-RoPE positions against
+    transformers, compared on the rows of real tokens."""
+    cfg = Q.QWEN2VL_CONFIGS["tiny"]
+    P = Q.init_qwen2vl_params(cfg, seed=4)
+    m = _hf_model(cfg)
+    new = {}
+    for k, t in m.state_dict().items():
+        name = k.replace("model.visual.", "visual.").replace("model.language_model.", "model.")
+        if name not in P:
+            pytest.skip(f"unexpected HF parameter name {k}")
+        w = P[name]
+        if w.ndim == 2 and "embed_tokens" not in name:
+            w = w.t()
+        new[k] = w.contiguous()
+    m.load_state_dict(new)
+    g = torch.Generator().manual_seed(1)
+    grid = [[1, 8, 8], [1, 4, 8]]
+    pv = torch.randn(64 + 32, 3 * 2 * 14 * 14, generator=g)
+    seqs = [[cfg["vision_start_token_id"]] + [cfg["image_token_id"]] * n_img + [cfg["vision_end_token_id"]] +
+            torch.randint(0, 1000, (n_txt,), generator=g).tolist() for n_img, n_txt in ((16, 20), (8, 11))]
+    S = max(len(x) for x in seqs)
+    pad = 0
+    ids = torch.full((2, S), pad, dtype=torch.long)
+    am = torch.zeros(2, S, dtype=torch.long)
+    for i, x in enumerate(seqs):
+        sl = slice(S - len(x), S) if side == "left" else slice(0, len(x))
+        ids[i, sl] = torch.tensor(x)
+        am[i, sl] = 1
+    ours = Q.qwen2vl_prefill(cfg, P, ids, pv, grid, attention_mask=am)
+    pos, _ = Q.get_rope_index(cfg, ids, grid, am)
+    with torch.no_grad():
+        ref = m(input_ids=ids, pixel_values=pv, image_grid_thw=torch.tensor(grid), attention_mask=am, position_ids=pos).logits
+    keep = am.bool()
+    tol = 2e-4 * max(1.0, ref[keep].abs().max().item())
+    assert (ours[keep] - ref[keep]).abs().max().item() < tol, (ours[keep] - ref[keep]).abs().max().item()

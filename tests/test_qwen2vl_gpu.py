@@ -118,3 +118,82 @@ def test_graphed_decode_step_matches_eager_and_oracle():
     gen = model.generate(input_ids, pixel_values=pv.cuda(), image_grid_thw=torch.tensor(grid), max_new_tokens=6)
     gen_e = model.generate(input_ids, pixel_values=pv.cuda(), image_grid_thw=torch.tensor(grid), max_new_tokens=6, eos_token_id=-1)
     assert gen.shape == (B, S + 6) and torch.equal(gen, gen_e)
+
+
+def _padded(cfg, grid, n_text, side, seed=7):
+    """Sequences of different lengths padded to one length: ids [B, S], attention_mask [B, S], pixel values."""
+    g = torch.Generator().manual_seed(seed)
+    m2 = cfg["vision"]["spatial_merge_size"] ** 2
+    T = sum(t * h * w for t, h, w in grid)
+    pv = torch.randn(T, 3 * 2 * 14 * 14, generator=g)
+    seqs = [[cfg["vision_start_token_id"]] + [cfg["image_token_id"]] * (t * h * w // m2) + [cfg["vision_end_token_id"]] +
+            torch.randint(0, 1000, (nt,), generator=g).tolist() for (t, h, w), nt in zip(grid, n_text)]
+    S = max(len(x) for x in seqs)
+    ids, am = torch.zeros(len(seqs), S, dtype=torch.long), torch.zeros(len(seqs), S, dtype=torch.long)
+    for i, x in enumerate(seqs):
+        sl = slice(S - len(x), S) if side == "left" else slice(0, len(x))
+        ids[i, sl], am[i, sl] = torch.tensor(x), 1
+    return ids, am, pv
+
+
+@pytest.mark.parametrize("side", ["left", "right"])
+def test_qwen2vl_padded_batch_prefill_parity(side):
+    """attention_mask with zeros (modeling_qwen2_vl.py:403-444,604-607): causal + key-padding additive mask through
+    b200mix_sdpa and mask-aware M-RoPE indices; the rows of real tokens match the oracle (itself checked against HF
+    transformers on padded batches)."""
+    from paddlemix_b200.qwen2_vl import Qwen2VLForConditionalGeneration
+    cfg = O.QWEN2VL_CONFIGS["tiny"]
+    P = O.init_qwen2vl_params(cfg, seed=1)
+    model = Qwen2VLForConditionalGeneration(cfg).load_state_dict(P, device=0)
+    grid = [[1, 8, 8], [1, 4, 8], [1, 8, 8]]
+    ids, am, pv = _padded(cfg, grid, [40, 9, 150], side)
+    ref = O.qwen2vl_prefill(cfg, P, ids, pv, grid, attention_mask=am)
+    out = model(input_ids=ids, attention_mask=am, pixel_values=pv.cuda(), image_grid_thw=torch.tensor(grid)).logits.cpu()
+    keep = am.bool()
+    o, r = out[keep], ref[keep]
+    cos = torch.nn.functional.cosine_similarity(o.flatten(), r.flatten(), dim=0).item()
+    err = (o - r).abs().max().item() / r.abs().max().item()
+    assert cos >= 0.999 and err <= 0.04, (cos, err)
+    pos_o, d_o = O.get_rope_index(cfg, ids, grid, am)
+    pos_m, d_m = model.get_rope_index(ids, torch.tensor(grid), None, am)
+    assert torch.equal(pos_o, pos_m) and torch.equal(d_o, d_m)
+
+
+def test_qwen2vl_left_padded_decode_matches_full_recompute():
+    """Decode after a LEFT-padded prompt batch: the cache keeps the padding, every step masks it (eager step and the
+    CUDA-graph step), logits = the oracle's full recompute of the extended, still padded, batch."""
+    from paddlemix_b200.qwen2_vl import GraphedDecodeStep, Qwen2VLForConditionalGeneration
+    cfg = O.QWEN2VL_CONFIGS["tiny"]
+    P = O.init_qwen2vl_params(cfg, seed=2)
+    model = Qwen2VLForConditionalGeneration(cfg).load_state_dict(P, device=0)
+    grid = [[1, 8, 8], [1, 4, 8]]
+    ids, am, pv = _padded(cfg, grid, [30, 12], "left")
+    B, S = ids.shape
+
+    def check(o, ids_ext, am_ext, what):
+        ref = O.qwen2vl_prefill(cfg, P, ids_ext, pv, grid, attention_mask=am_ext)[:, -1]
+        cos = torch.nn.functional.cosine_similarity(o.flatten(), ref.flatten(), dim=0).item()
+        err = (o - ref).abs().max().item() / ref.abs().max().item()
+        assert cos >= 0.999 and err <= 0.04, (what, cos, err)
+
+    g = torch.Generator().manual_seed(9)
+    news = [torch.randint(0, 1000, (B, 1), generator=g) for _ in range(4)]
+    # eager steps
+    out = model(input_ids=ids, attention_mask=am, pixel_values=pv.cuda(), image_grid_thw=torch.tensor(grid), use_cache=True)
+    cache, deltas = out.past_key_values, out.rope_deltas
+    check(out.logits[:, -1].cpu(), ids, am, "prefill")
+    ids_e, am_e = ids, am
+    for i, new in enumerate(news[:2]):
+        ids_e, am_e = torch.cat([ids_e, new], 1), torch.cat([am_e, torch.ones(B, 1, dtype=torch.long)], 1)
+        o = model(input_ids=new, attention_mask=am_e, past_key_values=cache, rope_deltas=deltas, use_cache=True).logits[:, 0].cpu()
+        check(o, ids_e, am_e, f"eager step {i}")
+    # graphed steps continue from the same cache
+    stepper = GraphedDecodeStep(model, cache, deltas)
+    for i, new in enumerate(news[2:]):
+        ids_e, am_e = torch.cat([ids_e, new], 1), torch.cat([am_e, torch.ones(B, 1, dtype=torch.long)], 1)
+        o = stepper.step(new.reshape(-1)).float().cpu()
+        check(o, ids_e, am_e, f"graphed step {i}")
+    gen = model.generate(ids, pixel_values=pv.cuda(), image_grid_thw=torch.tensor(grid), max_new_tokens=3, attention_mask=am)
+    assert gen.shape == (B, S + 3) and torch.equal(gen[:, :S], ids)
+    with pytest.raises(ValueError):
+        model.generate(ids.flip(1), max_new_tokens=2, attention_mask=am.flip(1))  # right-padded prompts are refused
