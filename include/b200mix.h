@@ -106,6 +106,16 @@ int b200mix_linear_batched(const void* A, int64_t lda, int64_t a_bstride, const 
 int b200mix_conv3x3(const void* x, const void* w, void* y, int64_t B, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
                     int32_t stride, const b200mix_epilogue* epi, void* stream);
 
+/* y[B,2H,2W,Cout] = epilogue(conv3x3(nearest_upsample_2x(x[B,H,W,Cin]), padding 1)) without materialising the upsampled
+ * tensor: Upsample2D.forward (ppdiffusers/models/resnet.py:169-218: F.interpolate(scale_factor=2.0, mode="nearest") then
+ * self.conv). Each output parity (y%2, x%2) is a 2x2 conv over the low-resolution input, so w4 holds the 3x3 filter
+ * folded per parity: bf16 [Cout, 4 (py,px), 4 (a,b), Cin], tap (a,b) of parity (py,px) = sum of the taps of w[Cout,3,3,Cin]
+ * that read the same input pixel (py = 0: a=0 <- ky 0, a=1 <- ky 1+2; py = 1: a=0 <- ky 0+1, a=1 <- ky 2; same in x),
+ * summed in fp32 and rounded once. 4/9 of the plain conv's FLOPs and none of the 4x tensor's traffic. Cin % 64 == 0.
+ * epilogue: bias / row_add (rows_per_group = 4*H*W) / activation / residual[B,2H,2W,Cout] / out_scale. */
+int b200mix_conv3x3_up2x(const void* x, const void* w4, void* y, int64_t B, int64_t H, int64_t W, int64_t Cin,
+                         int64_t Cout, const b200mix_epilogue* epi, void* stream);
+
 /* conv3x3 stride 1 pad 1 for tiny Cin (UNet conv_in, unet_2d_condition.py:1064): x fp32 or bf16 NHWC [B,H,W,Cin],
  * w bf16 [Cout,3,3,Cin], bias fp32, y bf16 NHWC. CUDA-core kernel (K = 9*Cin = 36 is below one MMA k-block). */
 int b200mix_conv3x3_small_cin(const void* x, int32_t x_fp32, const void* w, const float* bias, void* y, int64_t B,

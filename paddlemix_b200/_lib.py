@@ -56,6 +56,8 @@ SIGNATURES = {
     "b200mix_unpatchify": [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p],
     "b200mix_conv3x3": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32,
                         POINTER(Epilogue), c_void_p],
+    "b200mix_conv3x3_up2x": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                             POINTER(Epilogue), c_void_p],
     "b200mix_conv3x3_small_cin": [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                                   c_int64, c_void_p],
     "b200mix_sdpa": [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 6 + [c_int64] * 12 +

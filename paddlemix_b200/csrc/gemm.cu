@@ -21,6 +21,10 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+
 namespace b200 {
 
 struct IGemmParams {
@@ -31,7 +35,11 @@ struct IGemmParams {
   int TW, TH, TB;  // tile box in (x, y, b); TW*TH*TB == 128
   int Wo, Ho, Bn;  // output extents in (x, y, b); plain GEMM: Wo = M, Ho = Bn = 1
   int tiles_x, tiles_y, tiles_b, tiles_n;
-  int tap_dc[9], tap_dx[9], tap_p[9], tap_dy[9];
+  int tap_dc[16], tap_dx[16], tap_p[16], tap_dy[16];
+  // fused nearest-2x upsample (b200mix_conv3x3_up2x): m-tiles enumerate (output parity, low-resolution tile); tile
+  // `mt` has parity mt / par_tiles and uses taps [4 * parity, 4 * parity + 4); its rows land on output pixels
+  // (2y + parity / 2, 2x + parity % 2). par_tiles = tiles per parity rounded up to even (a CTA pair shares one B tile).
+  int up, par_tiles;
   // epilogue
   const float* bias;
   const float* row_add;
@@ -48,7 +56,60 @@ struct IGemmParams {
   // residual at residual + b*r_bstride + x*ldr; plain mode (c_bstride == 0) uses the flat row index for both.
   long long c_bstride, r_bstride;
   long long res_row_mod;  // > 0: residual row = flat row % res_row_mod (a [rows, N] table shared by all groups)
+  // stream-K head (see SegIter): the first sk_tiles super-tiles are cut into equal k-block ranges, one per cluster
+  int sk_tiles;
+  float4* sk_ws;          // [cluster][cta rank][chunk][8][128 rows] fp32 partial accumulators
+  unsigned int* sk_flags; // [cluster][cta rank]: 1 = the partial of that CTA's tail piece is in sk_ws
 };
+
+// ---- work schedule -------------------------------------------------------------------------------------------------
+// A problem of T super-tiles (256 x BN) on C clusters needs ceil(T / C) rounds; SDXL's 8192 x 1280 projections have
+// T = 160 on C = 74: 2.16 rounds of work in 3 rounds of time. The schedule therefore starts with a STREAM-K head: the
+// first sk_tiles = C + (T mod C) tiles are laid end to end in units of one 64-deep k-block and cluster c takes the
+// contiguous unit range [c, c+1) * units / C (>= one whole tile, so a tile is shared by at most two clusters: its k
+// range splits into a HEAD piece = the last piece of cluster c and a TAIL piece = the first piece of cluster c + 1).
+// The tail piece's fp32 accumulators go to a per-cluster workspace slot right after that cluster's first few k-blocks;
+// the head piece's epilogue - which runs (1 + T mod C / C) tiles later - adds them to its own accumulators and finishes
+// the tile (fixed split and fixed order: results are reproducible run to run). The remaining T - sk_tiles tiles (a
+// multiple of C) follow round-robin as before. Every cluster thus gets T / C tiles' worth of k-blocks.
+constexpr int SK_WS_FLOAT4_PER_CTA = 8 * 8 * 128;  // 8 chunks x 8 float4 x 128 rows = 128 KB
+enum { SEG_FULL = 0, SEG_TAIL = 1, SEG_HEAD = 2 };
+struct SegIter {
+  int u, u1;        // stream-K unit range still to do
+  int st_rr, step, total, kblocks;
+  int st, kb0, kb1;  // current piece: super-tile and k-block range
+  __device__ __forceinline__ SegIter(int sk_tiles, int total_super, int kblocks_, int cluster_id, int num_clusters) {
+    const int units = sk_tiles * kblocks_;
+    u = static_cast<int>(static_cast<long long>(cluster_id) * units / num_clusters);
+    u1 = static_cast<int>(static_cast<long long>(cluster_id + 1) * units / num_clusters);
+    st_rr = sk_tiles + cluster_id, step = num_clusters, total = total_super, kblocks = kblocks_;
+    st = 0, kb0 = 0, kb1 = 0;
+  }
+  __device__ __forceinline__ bool next() {
+    if (u < u1) {
+      st = u / kblocks;
+      kb0 = u - st * kblocks;
+      kb1 = min(kblocks, kb0 + (u1 - u));
+      u += kb1 - kb0;
+      return true;
+    }
+    if (st_rr < total) {
+      st = st_rr, kb0 = 0, kb1 = kblocks;
+      st_rr += step;
+      return true;
+    }
+    return false;
+  }
+  __device__ __forceinline__ int mode() const { return kb0 > 0 ? SEG_TAIL : (kb1 < kblocks ? SEG_HEAD : SEG_FULL); }
+};
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // Epilogue activations. All are of the form x * sigmoid(q(x)) and cost one ex2 + one rcp on the MUFU pipe, so a
 // GEGLU / SiLU epilogue stays well inside the tensor-core time of its tile.
@@ -409,7 +470,7 @@ __global__ void __launch_bounds__(320, 1)
   const uint32_t cta_rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
-  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int tiles_m = p.up ? 4 * p.par_tiles : p.tiles_x * p.tiles_y * p.tiles_b;
   const int tiles_m2 = (tiles_m + 1) >> 1;            // pairs of m-tiles (the odd one out pairs with a phantom)
   const int total_super = tiles_m2 * p.tiles_n;
   const int kblocks = p.ntaps * p.kchunks;
@@ -419,37 +480,44 @@ __global__ void __launch_bounds__(320, 1)
       // ===== TMA producer (whole warp runs the loop, one elected lane issues: see elect_one_sync) =====
       int stage = 0;
       uint32_t phase = 0;
-      for (int st = cluster_id; st < total_super; st += num_clusters) {
+      for (SegIter seg(p.sk_tiles, total_super, kblocks, cluster_id, num_clusters); seg.next();) {
+        const int st = seg.st;
         const int mp = st / p.tiles_n, nt = st - mp * p.tiles_n;
-        const int mt = mp * 2 + (int)cta_rank;  // may be == tiles_m (phantom): its A box is out of bounds -> zeros
+        int mt = mp * 2 + (int)cta_rank;  // may be == tiles_m (phantom): its A box is out of bounds -> zeros
+        int tap_base = 0;
+        if (p.up) {  // phantom tiles of a parity (index >= tiles of the grid) get b0 >= Bn: zeros as well
+          const int par = mt / p.par_tiles;
+          mt -= par * p.par_tiles, tap_base = par * 4;
+        }
         const int tx = mt % p.tiles_x;
         const int ty = (mt / p.tiles_x) % p.tiles_y;
         const int tb = mt / (p.tiles_x * p.tiles_y);
         const int x0 = tx * p.TW, y0 = ty * p.TH, b0 = tb * p.TB, n0 = nt * BN;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int dc = p.tap_dc[tap], dx = p.tap_dx[tap], pp = p.tap_p[tap], dy = p.tap_dy[tap];
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
-            uint8_t* sB = sA + Cfg::A_BYTES;
-            if (elect_one_sync()) {
-              if (PAIR) {
-                // both CTAs' boxes complete on the LEADER's barrier (it alone issues the MMA): my A rows, my half of B
-                if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                const uint32_t lbar = mapa_smem(&full_bar[stage], 0);
-                tma_load_5d_pair(sA, &tmA, lbar, kc * 64 + dc, x0 + dx, pp, y0 + dy, b0);
-                tma_load_2d_pair(sB, &tmB, lbar, tap * p.Kc + kc * 64, n0 + (int)cta_rank * (BN / 2));
-              } else {
-                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                tma_load_5d(sA, &tmA, &full_bar[stage], kc * 64 + dc, x0 + dx, pp, y0 + dy, b0);
-                // my half of the weight tile, delivered to both CTAs of the cluster
-                tma_load_2d_mcast(sB + cta_rank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], tap * p.Kc + kc * 64,
-                                  n0 + (int)cta_rank * (BN / 2), (uint16_t)0x3);
-              }
+        int tap = seg.kb0 / p.kchunks, kc = seg.kb0 - tap * p.kchunks;
+        for (int kb = seg.kb0; kb < seg.kb1; ++kb) {
+          const int tg = tap_base + tap;
+          const int dc = p.tap_dc[tg], dx = p.tap_dx[tg], pp = p.tap_p[tg], dy = p.tap_dy[tg];
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          if (elect_one_sync()) {
+            if (PAIR) {
+              // both CTAs' boxes complete on the LEADER's barrier (it alone issues the MMA): my A rows, my half of B
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              const uint32_t lbar = mapa_smem(&full_bar[stage], 0);
+              tma_load_5d_pair(sA, &tmA, lbar, kc * 64 + dc, x0 + dx, pp, y0 + dy, b0);
+              tma_load_2d_pair(sB, &tmB, lbar, tg * p.Kc + kc * 64, n0 + (int)cta_rank * (BN / 2));
+            } else {
+              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              tma_load_5d(sA, &tmA, &full_bar[stage], kc * 64 + dc, x0 + dx, pp, y0 + dy, b0);
+              // my half of the weight tile, delivered to both CTAs of the cluster
+              tma_load_2d_mcast(sB + cta_rank * (Cfg::B_BYTES / 2), &tmB, &full_bar[stage], tg * p.Kc + kc * 64,
+                                n0 + (int)cta_rank * (BN / 2), (uint16_t)0x3);
             }
-            __syncwarp();
-            if (++stage == STAGES) stage = 0, phase ^= 1;
           }
+          __syncwarp();
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+          if (++kc == p.kchunks) kc = 0, ++tap;
         }
       }
     }
@@ -461,12 +529,13 @@ __global__ void __launch_bounds__(320, 1)
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int st = cluster_id; st < total_super; st += num_clusters) {
+      for (SegIter seg(p.sk_tiles, total_super, kblocks, cluster_id, num_clusters); seg.next();) {
         if (PAIR) mbar_wait_cluster(&tempty[as], aphase ^ 1);
         else mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int kb_first = seg.kb0, kb_last = seg.kb1 - 1;
+        for (int kb = kb_first; kb <= kb_last; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -476,13 +545,14 @@ __global__ void __launch_bounds__(320, 1)
             for (int k = 0; k < 4; ++k) {
               const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
               const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-              if (PAIR) umma_bf16_ss_pair(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-              else umma_bf16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+              const uint32_t accumulate = (kb != kb_first || k != 0) ? 1u : 0u;  // a piece starts from zero
+              if (PAIR) umma_bf16_ss_pair(d_tmem, ad, bd, idesc, accumulate);
+              else umma_bf16_ss(d_tmem, ad, bd, idesc, accumulate);
             }
             // frees this stage in both CTAs
             if (PAIR) umma_commit_pair_mcast(&empty_bar[stage], (uint16_t)0x3);
             else umma_commit_mcast(&empty_bar[stage], (uint16_t)0x3);
-            if (kb == kblocks - 1) {
+            if (kb == kb_last) {
               if (PAIR) umma_commit_pair_mcast(&tfull[as], (uint16_t)0x3);  // accumulators of both CTAs are ready
               else umma_commit(&tfull[as]);
             }
@@ -509,15 +579,26 @@ __global__ void __launch_bounds__(320, 1)
     const int tbb = row / (p.TW * p.TH);
     int as = 0;
     uint32_t aphase = 0;
-    for (int st = cluster_id; st < total_super; st += num_clusters) {
+    const int epi_tid = (warp - IG_EPI_BASE) * 32 + lane;
+    for (SegIter seg(p.sk_tiles, total_super, kblocks, cluster_id, num_clusters); seg.next();) {
+      const int st = seg.st;
+      const int seg_mode = seg.mode();
+      // stream-K pieces: the tail piece (my first) goes to MY workspace slot; the head piece (my last) is completed with
+      // the tail piece of the same tile, which the NEXT cluster produced at its very start
+      const int sk_slot = (seg_mode == SEG_TAIL ? cluster_id : cluster_id + 1) * 2 + (int)cta_rank;
+      float4* sk_ws = p.sk_ws + static_cast<size_t>(sk_slot) * SK_WS_FLOAT4_PER_CTA + (q * 32 + lane);
       const int mp = st / p.tiles_n, nt = st - mp * p.tiles_n;
-      const int mt = mp * 2 + (int)cta_rank;
+      int mt = mp * 2 + (int)cta_rank;
+      const bool in_range = mt < tiles_m;
+      int par = 0;
+      if (p.up) par = mt / p.par_tiles, mt -= par * p.par_tiles;
       const int tx = mt % p.tiles_x;
       const int ty = (mt / p.tiles_x) % p.tiles_y;
       const int tb = mt / (p.tiles_x * p.tiles_y);
       const int x = tx * p.TW + tw, y = ty * p.TH + th, b = tb * p.TB + tbb;
-      const bool valid = (mt < tiles_m) && (x < p.Wo) && (y < p.Ho) && (b < p.Bn);
-      const long long gm = (static_cast<long long>(b) * p.Ho + y) * p.Wo + x;
+      const bool valid = in_range && (x < p.Wo) && (y < p.Ho) && (b < p.Bn);
+      const long long gm = p.up ? (static_cast<long long>(b) * (2 * p.Ho) + (2 * y + (par >> 1))) * (2 * p.Wo) + (2 * x + (par & 1))
+                                : (static_cast<long long>(b) * p.Ho + y) * p.Wo + x;
       long long g, c_off, r_off;
       if (p.c_bstride) {  // batched-strided: group == batch
         g = b;
@@ -562,11 +643,41 @@ __global__ void __launch_bounds__(320, 1)
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
+      if (seg_mode == SEG_HEAD) {
+        // the partner's partial was published ~a tile ago; a bounded spin turns a scheduling accident (the partner
+        // cluster not resident) into an error instead of a hang
+        const unsigned int* flag = p.sk_flags + sk_slot;
+        const long long t_start = clock64();
+        while (ld_acquire_gpu(flag) == 0u) {
+          if (clock64() - t_start > (1ll << 32)) __trap();
+        }
+      }
 #pragma unroll 1
       for (int c = wg; c < BN / 32; c += 2) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c * 32, r);
         const int n_abs = n0 + c * 32;
+        if (seg_mode == SEG_TAIL) {  // partial accumulators -> workspace (512 contiguous bytes per warp and store)
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            __stcg(sk_ws + (c * 8 + j) * 128, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                          __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+          continue;
+        }
+        float4 part[8];
+        if (seg_mode == SEG_HEAD) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) part[j] = __ldcg(sk_ws + (c * 8 + j) * 128);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + part[j].x);
+            r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + part[j].y);
+            r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + part[j].z);
+            r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + part[j].w);
+          }
+        }
         if (st_cur) {  // warp-uniform: coalesced path through the transpose buffer
 #if EPI_PIPE
           uint4 res_next[4];
@@ -597,6 +708,16 @@ __global__ void __launch_bounds__(320, 1)
       else mbar_arrive(&tempty[as]);
       as ^= 1;
       if (as == 0) aphase ^= 1;
+      if (seg_mode != SEG_FULL) {
+        // tail: all 256 epilogue threads' partials are visible device-wide before the flag goes up;
+        // head: everybody has read the partial before the flag is lowered for the next launch
+        if (seg_mode == SEG_TAIL) __threadfence();
+        named_bar_sync(1, 256);
+        if (epi_tid == 0) {
+          if (seg_mode == SEG_TAIL) st_release_gpu(p.sk_flags + sk_slot, 1u);
+          else p.sk_flags[sk_slot] = 0u;
+        }
+      }
     }
   }
 
@@ -827,9 +948,82 @@ static int launch_skinny(const void* A, long long lda, const void* W, long long 
 }
 
 static int g_max_clusters = 0;  // measurement hook: cap the persistent grid (0 = all SMs)
+#ifndef GEMM_STREAMK_DEFAULT
+#define GEMM_STREAMK_DEFAULT 1
+#endif
+// test / measurement hook: 0 = plain round-robin tile schedule (b200mix_debug_streamk, or B200MIX_STREAMK=0 in the environment)
+static int g_streamk = [] {
+  const char* e = getenv("B200MIX_STREAMK");
+  return e ? atoi(e) : GEMM_STREAMK_DEFAULT;
+}();
+// A split tile sends its 256 KB of fp32 partials through L2 twice; a tile's own operand traffic is 32 KB per k-block.
+// Measured on the SDXL step (profiles/r02_streamk_ab.txt): 180 k-blocks (conv 8192 x 1280 x 11520) +10.6 %, 360 +11.5 %,
+// 80 (FF2, K = 5120) +2 %, 20 (the 1280-wide projections, already bound by the L2 -> SM operand fill) -20 %.
+constexpr int SK_MIN_KBLOCKS = 64;
+constexpr int SK_MAX_CLUSTERS = 74;
+
+// Stream-K workspaces: SK_POOL slots per device (19 MB of partial accumulators + 148 flags each), allocated together on
+// the first eager GEMM call (never inside a stream capture). A slot belongs to ONE stream: launches on a stream are
+// ordered (a kernel's first global access follows griddepcontrol.wait = completion of its predecessor), so they can
+// share it; kernels captured into a CUDA graph keep the slot of their capture stream. Streams beyond the pool, and
+// launches that arrive before the pool exists, keep the round-robin schedule (same results up to fp32 summation order).
+// Not covered: two graphs captured on the same stream and replayed concurrently on different streams.
+constexpr int SK_POOL = 4;
+struct SkPool {
+  float4* ws[SK_POOL] = {};
+  unsigned int* flags[SK_POOL] = {};
+  cudaStream_t owner[SK_POOL] = {};
+  int assigned = 0;
+  bool ready = false, failed = false;
+};
+static SkPool g_sk[16];
+static std::mutex g_sk_mutex;
+
+static bool sk_workspace(cudaStream_t stream, float4** ws, unsigned int** flags) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return false;
+  std::lock_guard<std::mutex> lock(g_sk_mutex);
+  SkPool& w = g_sk[dev];
+  if (w.failed) return false;
+  if (!w.ready) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return false;
+    }
+    const size_t bytes = (size_t)SK_MAX_CLUSTERS * 2 * SK_WS_FLOAT4_PER_CTA * sizeof(float4);
+    const size_t fbytes = SK_MAX_CLUSTERS * 2 * sizeof(unsigned int);
+    for (int i = 0; i < SK_POOL; ++i) {
+      void *a = nullptr, *f = nullptr;
+      if (cudaMalloc(&a, bytes) != cudaSuccess || cudaMalloc(&f, fbytes) != cudaSuccess ||
+          cudaMemset(f, 0, fbytes) != cudaSuccess) {
+        cudaGetLastError();
+        w.failed = true;
+        return false;
+      }
+      w.ws[i] = reinterpret_cast<float4*>(a), w.flags[i] = reinterpret_cast<unsigned int*>(f);
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      cudaGetLastError();
+      w.failed = true;
+      return false;
+    }
+    w.ready = true;
+  }
+  int slot = -1;
+  for (int i = 0; i < w.assigned; ++i)
+    if (w.owner[i] == stream) slot = i;
+  if (slot < 0) {
+    if (w.assigned == SK_POOL) return false;
+    slot = w.assigned++;
+    w.owner[slot] = stream;
+  }
+  *ws = w.ws[slot], *flags = w.flags[slot];
+  return true;
+}
 
 template <int BN, int STAGES, bool PAIR>
-static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IGemmParams& p, cudaStream_t stream) {
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IGemmParams p, cudaStream_t stream) {
   using Cfg = IGemmCfg<BN, PAIR>;
   constexpr int smem_bytes = STAGES * Cfg::STAGE_BYTES + 1024 + 256 + 8 * 2048 + 8 * 512;  // + epilogue transpose / bias
   static_assert(smem_bytes <= 227 * 1024, "stage count does not fit shared memory");
@@ -839,11 +1033,17 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IG
                                    smem_bytes));
     configured = true;
   }
-  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int tiles_m = p.up ? 4 * p.par_tiles : p.tiles_x * p.tiles_y * p.tiles_b;
   const int total_super = ((tiles_m + 1) / 2) * p.tiles_n;
   int clusters = num_sms() / 2;
   if (g_max_clusters > 0 && clusters > g_max_clusters) clusters = g_max_clusters;
   if (clusters > total_super) clusters = total_super;
+  // stream-K head over the partial round + one full round (see SegIter): needs more than one round of tiles
+  p.sk_tiles = 0;
+  const int rem = total_super % clusters;
+  if (g_streamk && rem != 0 && total_super > clusters && clusters <= SK_MAX_CLUSTERS &&
+      p.ntaps * p.kchunks >= SK_MIN_KBLOCKS && sk_workspace(stream, &p.sk_ws, &p.sk_flags))
+    p.sk_tiles = clusters + rem;
   B200_CUDA(launch_pdl(igemm_kernel<BN, STAGES, PAIR>, dim3(2 * clusters), dim3(320), smem_bytes, stream, 2, tmA, tmB,
                        p));
   return 0;
@@ -855,7 +1055,7 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IG
 #endif
 static int g_gemm_pair = GEMM_PAIR_DEFAULT;
 
-static int pick_bn(long long tiles_m, long long N, int glu) {
+static int pick_bn(long long tiles_m, long long N, int kblocks) {
   // cost = waves x time per tile; time per tile ~ BN / rate(BN). Rates are the measured mainloop rates of each tile
   // width relative to BN=256 in CTA-pair mode (tools/bn_sweep.py, 16384x8192x2048): the per-SM operand fill (A tile +
   // B half per k-chunk, ~60 B/clk) does not shrink with BN as fast as the MMA time does, so narrower tiles are only
@@ -870,18 +1070,21 @@ static int pick_bn(long long tiles_m, long long N, int glu) {
   for (int i = 0; i < 7; ++i) {
     const int bn = cands[i];
     const long long tn = (N + bn - 1) / bn;
-    const long long waves = (((tiles_m + 1) / 2) * tn + clusters - 1) / clusters;
-    const double cost = double(waves) * (bn / eff[i]);
+    const long long tiles = ((tiles_m + 1) / 2) * tn;
+    double waves = double((tiles + clusters - 1) / clusters);
+    // stream-K head (launch_igemm): a ragged last round costs its fraction plus about a fifth of a tile for the split
+    if (g_streamk && kblocks >= SK_MIN_KBLOCKS && tiles > clusters && tiles % clusters != 0)
+      waves = double(tiles) / clusters + 0.2;
+    const double cost = waves * (bn / eff[i]);
     if (cost < best * 0.999) best = cost, best_bn = bn;
   }
-  (void)glu;
   return best_bn;
 }
 
 static int dispatch_igemm(const CUtensorMap& tmA, const void* W, long long ldw, long long Ktot, IGemmParams& p,
                           cudaStream_t stream, int force_bn) {
-  const long long tiles_m = (long long)p.tiles_x * p.tiles_y * p.tiles_b;
-  const int bn = force_bn > 0 ? force_bn : pick_bn(tiles_m, p.N, p.glu);
+  const long long tiles_m = p.up ? 4ll * p.par_tiles : (long long)p.tiles_x * p.tiles_y * p.tiles_b;
+  const int bn = force_bn > 0 ? force_bn : pick_bn(tiles_m, p.N, p.ntaps * p.kchunks);
   p.tiles_n = (p.N + bn - 1) / bn;
   CUtensorMap tmB;
   {
@@ -956,6 +1159,7 @@ extern "C" void b200mix_debug_force_bn(int bn) { g_force_bn = bn; }
 extern "C" void b200mix_debug_gemm_pair(int on) { b200::g_gemm_pair = on; }
 extern "C" void b200mix_debug_max_clusters(int n) { b200::g_max_clusters = n; }
 extern "C" void b200mix_debug_skinny(int on) { b200::g_skinny = on; }
+extern "C" void b200mix_debug_streamk(int on) { b200::g_streamk = on; }
 extern "C" void b200mix_debug_skinny_splits(int splits) { b200::g_skinny_splits = splits; }
 
 extern "C" int b200mix_linear(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int64_t M,
@@ -1003,6 +1207,23 @@ extern "C" int b200mix_linear(const void* A, int64_t lda, const void* W, int64_t
   return dispatch_igemm(tmA, W, ldw, K, p, reinterpret_cast<cudaStream_t>(stream), g_force_bn);
 }
 
+// tile box of a conv: TW x TH x TB = 128 pixels of the [B, Ho, Wo] grid the m-tiles walk over
+static int conv_tile_box(IGemmParams& p, int64_t B, int64_t Ho, int64_t Wo) {
+  int TW = 1;
+  while (TW * 2 <= Wo && TW < 128 && Wo % (TW * 2) == 0) TW *= 2;
+  int TH = 1;
+  while (TW * TH * 2 <= 128 && TH * 2 <= Ho && Ho % (TH * 2) == 0) TH *= 2;
+  int TB = 128 / (TW * TH);
+  B200_CHECK_ARG(TW * TH * TB == 128, "conv3x3: cannot tile %lldx%lld output into 128-pixel boxes", (long long)Ho,
+                 (long long)Wo);
+  p.TW = TW, p.TH = TH, p.TB = TB;
+  p.Wo = (int)Wo, p.Ho = (int)Ho, p.Bn = (int)B;
+  p.tiles_x = (int)((Wo + TW - 1) / TW);
+  p.tiles_y = (int)((Ho + TH - 1) / TH);
+  p.tiles_b = (int)((B + TB - 1) / TB);
+  return 0;
+}
+
 extern "C" int b200mix_conv3x3(const void* x, const void* w, void* y, int64_t B, int64_t H, int64_t W, int64_t Cin,
                                int64_t Cout, int32_t stride, const b200mix_epilogue* epi, void* stream) {
   if (int rc = ensure_device()) return rc;
@@ -1018,19 +1239,7 @@ extern "C" int b200mix_conv3x3(const void* x, const void* w, void* y, int64_t B,
   p.Kc = (int)Cin;
   p.ntaps = 9;
   p.kchunks = (int)(Cin / 64);
-  // tile box: TW x TH x TB = 128 output pixels
-  int TW = 1;
-  while (TW * 2 <= Wo && TW < 128 && Wo % (TW * 2) == 0) TW *= 2;
-  int TH = 1;
-  while (TW * TH * 2 <= 128 && TH * 2 <= Ho && Ho % (TH * 2) == 0) TH *= 2;
-  int TB = 128 / (TW * TH);
-  B200_CHECK_ARG(TW * TH * TB == 128, "conv3x3: cannot tile %lldx%lld output into 128-pixel boxes", (long long)Ho,
-                 (long long)Wo);
-  p.TW = TW, p.TH = TH, p.TB = TB;
-  p.Wo = (int)Wo, p.Ho = (int)Ho, p.Bn = (int)B;
-  p.tiles_x = (int)((Wo + TW - 1) / TW);
-  p.tiles_y = (int)((Ho + TH - 1) / TH);
-  p.tiles_b = (int)((B + TB - 1) / TB);
+  if (int rc = conv_tile_box(p, B, Ho, Wo)) return rc;
   for (int kh = 0; kh < 3; ++kh) {
     for (int kw = 0; kw < 3; ++kw) {
       const int t = kh * 3 + kw;
@@ -1060,10 +1269,53 @@ extern "C" int b200mix_conv3x3(const void* x, const void* w, void* y, int64_t B,
       dims[0] = 2 * Cin, dims[1] = W / 2, dims[2] = 2, dims[3] = H / 2, dims[4] = B;
       strides[0] = 2 * Cin * 2, strides[1] = W * Cin * 2, strides[2] = 2 * W * Cin * 2, strides[3] = H * W * Cin * 2;
     }
-    uint32_t box[5] = {64, (uint32_t)TW, 1, (uint32_t)TH, (uint32_t)TB};
+    uint32_t box[5] = {64, (uint32_t)p.TW, 1, (uint32_t)p.TH, (uint32_t)p.TB};
     if (int rc = encode_tmap_bf16_sw128(&tmA, x, 5, dims, strides, box)) return rc;
   }
   return dispatch_igemm(tmA, w, 9 * Cin, 9 * Cin, p, reinterpret_cast<cudaStream_t>(stream), g_force_bn);
+}
+
+
+// nearest-2x upsample + conv3x3 in one pass over the LOW-resolution input (Upsample2D, resnet.py:137-216: F.interpolate
+// (scale 2, nearest) followed by the 3x3 conv). Output pixel (2i + py, 2j + px) only sees the 2 x 2 input neighbourhood
+// (i - 1 + py .. i + py, j - 1 + px .. j + px): taps of the 3x3 filter that hit the same input pixel are pre-summed per
+// output parity, so the conv is 4 taps instead of 9 (4/9 of the FLOPs), the 4x larger upsampled tensor is never written
+// or read, and the halo is TMA zero fill exactly as for the plain conv (U[-1] = 0 <-> X[-1], U[2H] = 0 <-> X[H]).
+// w4: bf16 [Cout, 4 parities (py, px), 4 taps (a, b), Cin] with tap (a, b) of parity (py, px) = sum of w[ky][kx] over
+// ky in {0 | 1,2} (py = 0: a = 0 | 1) resp. {0,1 | 2} (py = 1), same for kx (ops.fold_upsample_conv_weight).
+extern "C" int b200mix_conv3x3_up2x(const void* x, const void* w4, void* y, int64_t B, int64_t H, int64_t W, int64_t Cin,
+                                    int64_t Cout, const b200mix_epilogue* epi, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  B200_CHECK_ARG(x && w4 && y, "conv3x3_up2x: null pointer");
+  B200_CHECK_ARG(Cin % 64 == 0, "conv3x3_up2x: Cin=%lld must be a multiple of 64", (long long)Cin);
+  B200_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cout > 0, "conv3x3_up2x: bad shape");
+  IGemmParams p = {};
+  p.N = (int)Cout;
+  p.Kc = (int)Cin;
+  p.ntaps = 4;
+  p.kchunks = (int)(Cin / 64);
+  if (int rc = conv_tile_box(p, B, H, W)) return rc;
+  p.up = 1;
+  p.par_tiles = (p.tiles_x * p.tiles_y * p.tiles_b + 1) / 2 * 2;
+  for (int par = 0; par < 4; ++par)
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const int t = par * 4 + a * 2 + b;
+        p.tap_dc[t] = 0, p.tap_p[t] = 0, p.tap_dy[t] = a - 1 + (par >> 1), p.tap_dx[t] = b - 1 + (par & 1);
+      }
+  if (int rc = fill_epilogue(p, epi, y, Cout, 4 * H * W)) return rc;
+  if (p.glu) {
+    set_error("conv3x3_up2x: GLU epilogue not supported");
+    return B200MIX_ERR_INVALID;
+  }
+  CUtensorMap tmA;
+  {
+    uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, 1, (uint64_t)H, (uint64_t)B};
+    uint64_t strides[4] = {(uint64_t)Cin * 2, (uint64_t)(W * Cin * 2), (uint64_t)(W * Cin * 2), (uint64_t)(H * W * Cin * 2)};
+    uint32_t box[5] = {64, (uint32_t)p.TW, 1, (uint32_t)p.TH, (uint32_t)p.TB};
+    if (int rc = encode_tmap_bf16_sw128(&tmA, x, 5, dims, strides, box)) return rc;
+  }
+  return dispatch_igemm(tmA, w4, 16 * Cin, 16 * Cin, p, reinterpret_cast<cudaStream_t>(stream), g_force_bn);
 }
 
 

@@ -202,6 +202,42 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, bias=None, *, stride=1, row_add=No
     return out
 
 
+def fold_upsample_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """w: [Cout, 3, 3, Cin] (any float dtype; fold from the fp32 master weights when they exist) -> bf16 [Cout, 16, Cin],
+    the per-output-parity 2x2 filters of nearest-2x-upsample + conv3x3 (b200mix_conv3x3_up2x). Row index =
+    (py*2 + px)*4 + a*2 + b; taps that read the same low-resolution pixel are summed in fp32 and rounded once."""
+    O, _, _, I = w.shape
+    wf = w.float()
+    groups = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}  # parity -> (taps folded into a = 0, taps folded into a = 1)
+    out = torch.empty(O, 2, 2, 2, 2, I, dtype=torch.float32, device=w.device)
+    for py in range(2):
+        for px in range(2):
+            for a in range(2):
+                for b in range(2):
+                    out[:, py, px, a, b] = sum(wf[:, ky, kx] for ky in groups[py][a] for kx in groups[px][b])
+    return out.reshape(O, 16, I).to(bf16).contiguous()
+
+
+def conv3x3_up2x(x: torch.Tensor, w4: torch.Tensor, bias=None, *, row_add=None, residual=None, act=ACT_NONE,
+                 out_scale=1.0, out=None) -> torch.Tensor:
+    """conv3x3(nearest_upsample_2x(x)) from the low-resolution x: bf16 NHWC [B,H,W,Cin]; w4 = fold_upsample_conv_weight(w).
+    Returns bf16 NHWC [B,2H,2W,Cout] (Upsample2D, resnet.py:169-218)."""
+    _req(x, bf16, "x"), _req(w4, bf16, "w4")
+    B, H, W, Cin = x.shape
+    Cout = w4.shape[0]
+    assert x.is_contiguous() and w4.is_contiguous() and tuple(w4.shape[1:]) == (16, Cin)
+    if out is None:
+        out = torch.empty(B, 2 * H, 2 * W, Cout, device=x.device, dtype=bf16)
+    e = make_epilogue(bias=bias, row_add=row_add, ld_row=0 if row_add is None else row_add.stride(0),
+                      rows_per_group=4 * H * W, residual=residual, ldr=Cout, act=act, out_scale=out_scale)
+    with _Timed("igemm", 2.0 * B * 4 * H * W * Cout * 4 * Cin, "flop",
+                lambda: f"convup {B * 4 * H * W}x{Cout}x{4 * Cin}" + _epi_tag(e)):
+        check(lib.b200mix_conv3x3_up2x(_p(x), _p(w4), _p(out), B, H, W, Cin, Cout, ctypes.byref(e), _stream()),
+              "b200mix_conv3x3_up2x")
+    _count()
+    return out
+
+
 def conv3x3_small_cin(x: torch.Tensor, w: torch.Tensor, bias=None) -> torch.Tensor:
     B, H, W, Cin = x.shape
     Cout = w.shape[0]

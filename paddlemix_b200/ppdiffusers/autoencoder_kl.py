@@ -78,7 +78,7 @@ class AutoencoderKL:
         for i in range(len(boc)):
             prev, out = out, rev[i]
             res = [_VaeResnet(f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else out, out, g) for j in range(layers_per_block + 1)]
-            ups = _Conv3x3(f"decoder.up_blocks.{i}.upsamplers.0.conv", out, out) if i != len(boc) - 1 else None
+            ups = _Conv3x3(f"decoder.up_blocks.{i}.upsamplers.0.conv", out, out, upsample=True) if i != len(boc) - 1 else None
             self.up.append((res, ups))
         self.norm_out = _Norm("decoder.conv_norm_out", boc[0])
         self.conv_out = _Conv3x3("decoder.conv_out", boc[0], out_channels)
@@ -186,7 +186,7 @@ class AutoencoderKL:
             for r in res:
                 h = r(h)
             if ups is not None:
-                h = ops.conv3x3(ops.upsample_nearest2x(h), ups.w, ups.b)
+                h = ups.up2x(h)
         n = ops.groupnorm_nhwc(h, self.norm_out.w, self.norm_out.b, groups=self.config.norm_num_groups, eps=1e-6, silu=True)
         y = ops.conv3x3(n, self.conv_out.w, self.conv_out.b)
         return ops.nhwc_to_nchw(y, out_dtype=torch.float32)

@@ -207,8 +207,10 @@ class _Linear:
 
 
 class _Conv3x3:
-    def __init__(self, name, cin=None, cout=None):
-        self.name, self.cin, self.cout = name, cin, cout
+    def __init__(self, name, cin=None, cout=None, upsample=False):
+        # upsample: the conv of an Upsample2D (resnet.py:169-218); its filter is folded per output parity at load time so
+        # that nearest-2x + conv3x3 run as one 4-tap pass over the low-resolution input (ops.conv3x3_up2x)
+        self.name, self.cin, self.cout, self.upsample = name, cin, cout, upsample
 
     def shapes(self):
         return {self.name + ".weight": (self.cout, self.cin, 3, 3), self.name + ".bias": (self.cout,)}
@@ -217,6 +219,14 @@ class _Conv3x3:
         w = _to_t(P[self.name + ".weight"])  # [O, I, 3, 3] -> [O, 3, 3, I]
         self.w = w.permute(0, 2, 3, 1).contiguous().to(dev, bf16)
         self.b = _to_t(P[self.name + ".bias"]).to(dev)
+        if self.upsample:
+            from .. import ops
+            self.w4 = ops.fold_upsample_conv_weight(w.permute(0, 2, 3, 1).to(dev, torch.float32))
+
+    def up2x(self, h):
+        """conv(nearest_upsample_2x(h))"""
+        from .. import ops
+        return ops.conv3x3_up2x(h, self.w4, self.b)
 
 
 class _Resnet:
@@ -482,7 +492,7 @@ class UNet2DConditionModel:
                 elif t != "UpBlock2D":
                     raise NotImplementedError(f"up block type {t}")
             if i != n - 1:
-                blk.up = _Conv3x3(f"up_blocks.{i}.upsamplers.0.conv", out_ch, out_ch)
+                blk.up = _Conv3x3(f"up_blocks.{i}.upsamplers.0.conv", out_ch, out_ch, upsample=True)
             self.up.append(blk)
         self.norm_out, self.conv_out = _Norm("conv_norm_out", boc[0]), _Conv3x3("conv_out", boc[0], c.out_channels)
 
@@ -700,7 +710,7 @@ class UNet2DConditionModel:
                 if blk.attns:
                     h = blk.attns[j](h, ctx, kw, am, eam)
             if blk.up is not None:
-                h = ops.conv3x3(ops.upsample_nearest2x(h), blk.up.w, blk.up.b)
+                h = blk.up.up2x(h)
         n = ops.groupnorm_nhwc(h, self.norm_out.w, self.norm_out.b, groups=self.config.norm_num_groups,
                                eps=self.config.norm_eps, silu=True)
         return ops.conv3x3(n, self.conv_out.w, self.conv_out.b)

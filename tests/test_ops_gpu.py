@@ -61,6 +61,95 @@ def test_linear_persistent_many_tiles(ops):
     close(out, ref, GEMM_ATOL, GEMM_RTOL, "big linear")
 
 
+def _streamk(lib, on, max_clusters=0):
+    import ctypes
+    for f in (lib.b200mix_debug_streamk, lib.b200mix_debug_max_clusters):
+        f.argtypes, f.restype = [ctypes.c_int], None
+    lib.b200mix_debug_streamk(on)
+    lib.b200mix_debug_max_clusters(max_clusters)
+
+
+@pytest.mark.parametrize("M,N,K,clusters,bn", [
+    (8192, 1280, 1280, 0, 0),     # SDXL out-projection: 160 tile pairs on 74 clusters -> 86 stream-K tiles + 1 round
+    (8192, 1280, 5120, 0, 0),     # FF2
+    (2048, 512, 1024, 3, 256),    # 16 tile pairs on 3 clusters: 4 stream-K tiles, every cluster has a tail and / or a head
+    (1536, 768, 576, 5, 128),     # 36 tile pairs on 5 clusters, 9 k-blocks: 6 stream-K tiles; ragged last n-tile
+    (1000, 328, 640, 3, 64),      # ragged M (phantom rows in the last pair) and ragged N
+    (1280, 1024, 512, 7, 256),    # 20 on 7: 13 stream-K tiles (almost two rounds)
+])
+@pytest.mark.parametrize("epi", ["plain", "bias_res", "glu", "fp32"])
+def test_linear_streamk(ops, M, N, K, clusters, bn, epi):
+    """Stream-K head of the tile schedule (csrc/gemm.cu SegIter): tiles split between two clusters must give the same
+    result as the round-robin schedule up to the fp32 summation order, for every epilogue path (coalesced, direct / GLU,
+    fp32 output), and must be reproducible run to run."""
+    from paddlemix_b200._lib import lib
+    a, w = rnd(M, K, seed=31), rnd(N, K, seed=32, scale=K ** -0.5)
+    bias = rnd(N, seed=33, dtype=torch.float32) if epi != "plain" else None
+    res = rnd(M, N, seed=34) if epi == "bias_res" else None
+    kw = dict(residual=res, glu=1 if epi == "glu" else 0, out_fp32=(epi == "fp32"))
+    outs = {}
+    try:
+        for on in (1, 0):
+            _streamk(lib, on, clusters)
+            lib.b200mix_debug_force_bn(bn)
+            outs[on] = ops.linear(a, w, bias, **kw)
+            if on:
+                again = ops.linear(a, w, bias, **kw)
+    finally:
+        _streamk(lib, 1, 0)
+        lib.b200mix_debug_force_bn(0)
+    assert torch.equal(outs[1], again), "stream-K result is not reproducible"
+    z = a.float() @ w.float().t() + (bias if bias is not None else 0)
+    if epi == "glu":
+        ref = z[:, 0::2] * F.gelu(z[:, 1::2])
+    else:
+        ref = z + (res.float() if res is not None else 0)
+    close(outs[1], ref, GEMM_ATOL, 1.5e-2 if epi == "glu" else GEMM_RTOL, f"stream-K {M}x{N}x{K} {epi}")
+    close(outs[1], outs[0].float(), GEMM_ATOL, 1.5e-2 if epi == "glu" else GEMM_RTOL, f"stream-K vs round-robin {epi}")
+
+
+@pytest.mark.parametrize("clusters", [0, 5])
+def test_conv3x3_streamk(ops, clusters):
+    from paddlemix_b200._lib import lib
+    B, H, W, Cin, Cout = (8, 32, 32, 320, 1280) if clusters == 0 else (3, 32, 32, 128, 320)
+    x = rnd(B, H, W, Cin, seed=35)
+    w = rnd(Cout, 3, 3, Cin, seed=36, scale=(9 * Cin) ** -0.5)
+    bias, temb, res = rnd(Cout, seed=37, dtype=torch.float32), rnd(B, Cout, seed=38, dtype=torch.float32), rnd(B, H, W, Cout, seed=39)
+    try:
+        _streamk(lib, 1, clusters)
+        out = ops.conv3x3(x, w, bias, row_add=temb, residual=res)
+    finally:
+        _streamk(lib, 1, 0)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1)
+    ref = (ref + temb[:, :, None, None]).permute(0, 2, 3, 1) + res.float()
+    close(out, ref, GEMM_ATOL, GEMM_RTOL, f"conv3x3 stream-K clusters={clusters}")
+
+
+def test_linear_streamk_many_launches_and_streams(ops):
+    """Flags are lowered by the consumer: 50 back-to-back launches, then a second stream (its own workspace slot), then a
+    CUDA graph captured on a third stream, all give the bits of the first launch."""
+    M, N, K = 8192, 1280, 1280
+    a, w, res = rnd(M, K, seed=40), rnd(N, K, seed=41, scale=K ** -0.5), rnd(M, N, seed=42)
+    first = ops.linear(a, w, residual=res)
+    for _ in range(50):
+        out = ops.linear(a, w, residual=res)
+    assert torch.equal(out, first)
+    s2 = torch.cuda.Stream()
+    s2.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s2):
+        out2 = ops.linear(a, w, residual=res)
+    s2.synchronize()
+    assert torch.equal(out2, first)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out3 = ops.linear(a, w, residual=res)
+    for _ in range(3):
+        out3.zero_()
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out3, first)
+
+
 @pytest.mark.parametrize("act", [1, 2, 3, 4])
 def test_linear_act(ops, act):
     M, N, K = 512, 256, 192
@@ -114,6 +203,33 @@ def test_conv3x3(ops, B, H, W, Cin, Cout, stride):
     ref = (ref + temb[:, :, None, None]).permute(0, 2, 3, 1)
     assert out.shape == ref.shape
     close(out, ref, GEMM_ATOL, GEMM_RTOL, f"conv3x3 {B}x{H}x{W} {Cin}->{Cout} s{stride}")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (1, 8, 8, 128, 320), (3, 32, 32, 320, 640),
+                                            (1, 4, 4, 64, 32), (5, 8, 16, 64, 96), (2, 64, 64, 128, 128)])
+@pytest.mark.parametrize("epi", ["bias", "full"])
+def test_conv3x3_up2x(ops, B, H, W, Cin, Cout, epi):
+    """Upsample2D (resnet.py:169-218): F.interpolate(scale_factor=2, mode='nearest') + conv3x3, fused as per-parity 2x2
+    convs over the low-resolution input. Odd tile counts per parity (phantom tile), ragged N and every border are covered."""
+    x = rnd(B, H, W, Cin, seed=50)
+    w = rnd(Cout, 3, 3, Cin, seed=51, scale=(9 * Cin) ** -0.5)
+    bias = rnd(Cout, seed=52, dtype=torch.float32)
+    w4 = ops.fold_upsample_conv_weight(w)
+    assert w4.shape == (Cout, 16, Cin)
+    kw = {}
+    if epi == "full":
+        kw = dict(row_add=rnd(B, Cout, seed=53, dtype=torch.float32), residual=rnd(B, 2 * H, 2 * W, Cout, seed=54), out_scale=0.5)
+    out = ops.conv3x3_up2x(x, w4, bias, **kw)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w.float().permute(0, 3, 1, 2), bias, padding=1)
+    if epi == "full":
+        ref = (ref + kw["row_add"][:, :, None, None] + kw["residual"].float().permute(0, 3, 1, 2)) * 0.5
+    ref = ref.permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    close(out, ref, GEMM_ATOL, GEMM_RTOL, f"conv3x3_up2x {B}x{H}x{W} {Cin}->{Cout} {epi}")
+    # the unfused pair of launches it replaces
+    two = ops.conv3x3(ops.upsample_nearest2x(x), w, bias, **kw)
+    close(out, two.float(), GEMM_ATOL, GEMM_RTOL, "fused vs upsample + conv")
 
 
 def test_conv3x3_residual(ops):
