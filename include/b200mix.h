@@ -59,6 +59,21 @@ typedef struct b200mix_epilogue {
   int32_t out_fp32;       /* 0: bf16 output, 1: fp32 output */
   float out_scale;        /* 1.0f for none */
   int64_t residual_row_mod; /* 0: residual row = m */
+  /* LayerNorm folded into the two Linear layers either side of it (BasicTransformerBlock: h = to_out(..) + h;
+   * n = norm(h); q = to_q(n), attention.py:352-489). The PRODUCER of h passes stats_out = int64 [M][2], ZEROED by the
+   * caller: its epilogue adds, per output row, the sum and the sum of squares of the bf16 values it stores, as 2^24
+   * fixed point with integer atomics (integer adds commute: the totals are reproducible bit for bit).
+   * The CONSUMER of LayerNorm(h) is called on h itself with the norm's affine folded into its weights,
+   *   W'[n,k] = bf16(W[n,k] * gamma[k]),  ln_colsum[n] = sum_k W'[n,k],  bias'[n] = bias[n] + sum_k W[n,k] * beta[k],
+   * passes ln_stats = that table, and rebuilds mean / rstd of every row in its epilogue:
+   *   out[m,n] = rstd[m] * (acc[m,n] - mean[m] * ln_colsum[n]) + bias'[n]     (== Linear(LayerNorm(h)) algebraically;
+   * h is not rounded a second time, so the result is closer to the fp32 reference than the two-kernel form).
+   * ln_rms = 1: RMSNorm (no mean term). All NULL / 0 when unused. */
+  void* stats_out;
+  const void* ln_stats;
+  const float* ln_colsum;
+  int32_t ln_rms;
+  float ln_eps;
 } b200mix_epilogue;
 
 const char* b200mix_last_error(void);

@@ -32,6 +32,11 @@ class Epilogue(Structure):
         ("out_fp32", c_int32),
         ("out_scale", c_float),
         ("residual_row_mod", c_int64),
+        ("stats_out", c_void_p),
+        ("ln_stats", c_void_p),
+        ("ln_colsum", c_void_p),
+        ("ln_rms", c_int32),
+        ("ln_eps", c_float),
     ]
 
 

@@ -56,6 +56,13 @@ struct IGemmParams {
   // residual at residual + b*r_bstride + x*ldr; plain mode (c_bstride == 0) uses the flat row index for both.
   long long c_bstride, r_bstride;
   long long res_row_mod;  // > 0: residual row = flat row % res_row_mod (a [rows, N] table shared by all groups)
+  // LayerNorm folded into the GEMMs either side of it (b200mix_epilogue: stats_out / ln_stats), see fill_epilogue
+  long long* stats_out;       // producer: [M][2] fixed-point (sum, sum of squares) of the bf16 output rows, += by atomics
+  const long long* ln_stats;  // consumer: the same table for this GEMM's input rows
+  const float* ln_colsum;     // consumer: [N] sum_k W'[n, k]
+  int ln_rms;
+  float ln_eps;
+  float ln_inv_k;             // 2^-24 / K
   // stream-K head (see SegIter): the first sk_tiles super-tiles are cut into equal k-block ranges, one per cluster
   int sk_tiles;
   float4* sk_ws;          // [cluster][cta rank][chunk][8][128 rows] fp32 partial accumulators
@@ -72,6 +79,9 @@ struct IGemmParams {
 // the head piece's epilogue - which runs (1 + T mod C / C) tiles later - adds them to its own accumulators and finishes
 // the tile (fixed split and fixed order: results are reproducible run to run). The remaining T - sk_tiles tiles (a
 // multiple of C) follow round-robin as before. Every cluster thus gets T / C tiles' worth of k-blocks.
+#ifndef LN_PROBE  // measurement builds (tools/ln_fold_probe.py): 1 = no statistics load / math, 2 = no transform of r[]
+#define LN_PROBE 0
+#endif
 constexpr int SK_WS_FLOAT4_PER_CTA = 8 * 8 * 128;  // 8 chunks x 8 float4 x 128 rows = 128 KB
 enum { SEG_FULL = 0, SEG_TAIL = 1, SEG_HEAD = 2 };
 struct SegIter {
@@ -335,7 +345,7 @@ __device__ __forceinline__ void epilogue_prefetch_staged(const IGemmParams& p, u
 
 __device__ __forceinline__ void epilogue_chunk_staged(const IGemmParams& p, const ActCoef& ac, const uint32_t (&r)[32],
                                                       const uint4 (&resv)[4], const float* bias_c, const RowMap& rm,
-                                                      uint8_t* stage, int lane, long long g, int n_abs) {
+                                                      uint8_t* stage, int lane, long long g, int n_abs, uint64_t (&st)[2]) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -394,6 +404,15 @@ __device__ __forceinline__ void epilogue_chunk_staged(const IGemmParams& p, cons
     const uint4 w = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
     *reinterpret_cast<uint4*>(stage + stage_addr(lane, j)) = w;
+    if (p.stats_out) {  // row statistics of the ROUNDED values (what the consumer of this tensor reads), packed fp32 pairs
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint64_t ab = pack_f32x2(bf16_lo(ww[u]), bf16_hi(ww[u]));
+        st[0] = fadd2(st[0], ab);
+        st[1] = ffma2(ab, ab, st[1]);
+      }
+    }
   }
   __syncwarp();
   uint4* cbase = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + n_abs) + piece;
@@ -437,6 +456,7 @@ __global__ void __launch_bounds__(320, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   uint8_t* stage_all = smem + STAGES * Cfg::STAGE_BYTES + 256;  // 8 epilogue warps x 2 KB transpose buffers
   float* bias_all = reinterpret_cast<float*>(stage_all + 8 * 2048);  // 8 epilogue warps x 128 floats (their 4 chunks)
+  float* colsum_all = bias_all + 8 * 128;                            // same layout: folded-LayerNorm column sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -571,6 +591,7 @@ __global__ void __launch_bounds__(320, 1)
     const int wg = (warp - IG_EPI_BASE) >> 2;
     uint8_t* stage = stage_all + (warp - IG_EPI_BASE) * 2048;
     float* bias_s = bias_all + (warp - IG_EPI_BASE) * 128;
+    float* colsum_s = colsum_all + (warp - IG_EPI_BASE) * 128;
     const ActCoef ac = act_coef(p.act, p.glu);
     const bool staged_ok = p.vec_ok && !p.glu && !p.out_fp32 && ((p.c_bstride | p.r_bstride) & 7) == 0;
     const int row = q * 32 + lane;
@@ -623,15 +644,48 @@ __global__ void __launch_bounds__(320, 1)
         rm.valid |= (__shfl_sync(0xffffffffu, valid ? 1u : 0u, src) & 1u) << s4;
       }
       // this warp's bias values (its <= 4 chunks of the tile) go to shared memory while the mainloop still runs: read
-      // back as broadcast float4s they cost ~30 cycles per chunk instead of an L2 round trip (L1 does not keep them)
+      // back as broadcast float4s they cost ~30 cycles per chunk instead of an L2 round trip (L1 does not keep them).
+      // Folded LayerNorm (consumer side): y = rstd * (acc - mean * colsum[n]) + bias'[n] needs the column sums the same
+      // way plus this row's fixed-point totals. ALL of these loads are issued before any of them is consumed, so a tile's
+      // preparation costs one L2 round trip, not three.
+      constexpr int NI = (BN / 32 + 1) / 2;
+      float bias_r[NI], cs_r[NI];
+      longlong2 t_stats = make_longlong2(0ll, 0ll);
       if (p.bias) {
 #pragma unroll
-        for (int i = 0; i < (BN / 32 + 1) / 2; ++i) {
+        for (int i = 0; i < NI; ++i) {
           const int col = n0 + (wg + 2 * i) * 32 + lane;
-          bias_s[i * 32 + lane] = (wg + 2 * i < BN / 32 && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+          bias_r[i] = (wg + 2 * i < BN / 32 && col < p.N) ? __ldg(p.bias + col) : 0.0f;
         }
-        __syncwarp();
       }
+      if (p.ln_stats) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int col = n0 + (wg + 2 * i) * 32 + lane;
+          cs_r[i] = (wg + 2 * i < BN / 32 && col < p.N) ? __ldg(p.ln_colsum + col) : 0.0f;
+        }
+        if (LN_PROBE != 1) t_stats = __ldg(reinterpret_cast<const longlong2*>(p.ln_stats) + (valid ? gm : 0ll));
+      }
+      if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) bias_s[i * 32 + lane] = bias_r[i];
+      }
+      if (p.ln_stats) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) colsum_s[i * 32 + lane] = cs_r[i];
+      }
+      __syncwarp();
+      float ln_rstd = 1.0f, ln_shift = 0.0f;
+      if (p.ln_stats && LN_PROBE != 1) {  // mean / rstd of my row from the totals the producing GEMM's epilogues accumulated
+        // fp32 on purpose: ~10 FP64 instructions per thread and tile cost the 1280-deep GEMMs 12 % (tools/ln_fold_probe.py,
+        // profiles/r02_ln_fold_probe.txt). E[x^2] - mean^2 in fp32 is good to ~1e-7 * mean^2 / var relative: below the bf16
+        // resolution of the inputs themselves for any row bf16 can represent (|mean| / std < 2^8).
+        const float mean = p.ln_rms ? 0.0f : __ll2float_rn(t_stats.x) * p.ln_inv_k;
+        const float var = fmaxf(fmaf(-mean, mean, __ll2float_rn(t_stats.y) * p.ln_inv_k), 0.0f);
+        ln_rstd = rsqrtf(var + p.ln_eps);
+        ln_shift = -ln_rstd * mean;
+      }
+      uint64_t st_acc[2] = {0ull, 0ull};  // producer side: packed (even, odd column) sum / sum of squares of my row over my chunks
       // residual pieces are fetched one chunk ahead (the first chunk's even before the accumulators are ready), so
       // their L2 latency overlaps the previous chunk's work instead of sitting on the critical path of each chunk
 #ifndef EPI_PIPE
@@ -678,20 +732,36 @@ __global__ void __launch_bounds__(320, 1)
             r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + part[j].w);
           }
         }
+        if (p.ln_stats && LN_PROBE != 2) {
+          tmem_wait_ld();
+          const float4* c4 = reinterpret_cast<const float4*>(colsum_s + (c >> 1) * 32);
+          const uint64_t rstd2 = pack_f32x2(ln_rstd, ln_rstd), shift2 = pack_f32x2(ln_shift, ln_shift);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 cs = c4[j];
+            float a, b;
+            unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), rstd2,
+                               fmul2(shift2, pack_f32x2(cs.x, cs.y))), a, b);
+            r[4 * j + 0] = __float_as_uint(a), r[4 * j + 1] = __float_as_uint(b);
+            unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), rstd2,
+                               fmul2(shift2, pack_f32x2(cs.z, cs.w))), a, b);
+            r[4 * j + 2] = __float_as_uint(a), r[4 * j + 3] = __float_as_uint(b);
+          }
+        }
         if (st_cur) {  // warp-uniform: coalesced path through the transpose buffer
 #if EPI_PIPE
           uint4 res_next[4];
           const bool st_next = (c + 2 < BN / 32) && (n_abs + 96 <= p.N);
           if (st_next) epilogue_prefetch_staged(p, res_next, rm, lane, n_abs + 64);
           tmem_wait_ld();
-          epilogue_chunk_staged(p, ac, r, res_cur, bias_s + (c >> 1) * 32, rm, stage, lane, g, n_abs);
+          epilogue_chunk_staged(p, ac, r, res_cur, bias_s + (c >> 1) * 32, rm, stage, lane, g, n_abs, st_acc);
 #pragma unroll
           for (int s4 = 0; s4 < 4; ++s4) res_cur[s4] = res_next[s4];
           st_cur = st_next;
 #else
           epilogue_prefetch_staged(p, res_cur, rm, lane, n_abs);
           tmem_wait_ld();
-          epilogue_chunk_staged(p, ac, r, res_cur, bias_s + (c >> 1) * 32, rm, stage, lane, g, n_abs);
+          epilogue_chunk_staged(p, ac, r, res_cur, bias_s + (c >> 1) * 32, rm, stage, lane, g, n_abs, st_acc);
           st_cur = (c + 2 < BN / 32) && (n_abs + 96 <= p.N);
 #endif
         } else {
@@ -708,6 +778,15 @@ __global__ void __launch_bounds__(320, 1)
       else mbar_arrive(&tempty[as]);
       as ^= 1;
       if (as == 0) aphase ^= 1;
+      if (p.stats_out && seg_mode != SEG_TAIL && valid) {
+        // 2^24 fixed point: integer adds commute, so the row totals are the same bits whatever order the tiles finish in
+        float s0, s1, q0, q1;
+        unpack_f32x2(st_acc[0], s0, s1);
+        unpack_f32x2(st_acc[1], q0, q1);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.stats_out + 2 * gm);
+        atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn((s0 + s1) * 16777216.0f)));
+        atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn((q0 + q1) * 16777216.0f)));
+      }
       if (seg_mode != SEG_FULL) {
         // tail: all 256 epilogue threads' partials are visible device-wide before the flag goes up;
         // head: everybody has read the partial before the flag is lowered for the next launch
@@ -961,6 +1040,7 @@ static int g_streamk = [] {
 // 80 (FF2, K = 5120) +2 %, 20 (the 1280-wide projections, already bound by the L2 -> SM operand fill) -20 %.
 constexpr int SK_MIN_KBLOCKS = 64;
 constexpr int SK_MAX_CLUSTERS = 74;
+static int sk_min_kblocks() { return g_streamk >= 2 ? 8 : SK_MIN_KBLOCKS; }  // 2 = tests: split shallow reductions too
 
 // Stream-K workspaces: SK_POOL slots per device (19 MB of partial accumulators + 148 flags each), allocated together on
 // the first eager GEMM call (never inside a stream capture). A slot belongs to ONE stream: launches on a stream are
@@ -1025,7 +1105,7 @@ static bool sk_workspace(cudaStream_t stream, float4** ws, unsigned int** flags)
 template <int BN, int STAGES, bool PAIR>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IGemmParams p, cudaStream_t stream) {
   using Cfg = IGemmCfg<BN, PAIR>;
-  constexpr int smem_bytes = STAGES * Cfg::STAGE_BYTES + 1024 + 256 + 8 * 2048 + 8 * 512;  // + epilogue transpose / bias
+  constexpr int smem_bytes = STAGES * Cfg::STAGE_BYTES + 1024 + 256 + 8 * 2048 + 2 * 8 * 512;  // + epilogue transpose / bias / colsum
   static_assert(smem_bytes <= 227 * 1024, "stage count does not fit shared memory");
   static bool configured = false;
   if (!configured) {
@@ -1042,7 +1122,7 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IGemmPar
   p.sk_tiles = 0;
   const int rem = total_super % clusters;
   if (g_streamk && rem != 0 && total_super > clusters && clusters <= SK_MAX_CLUSTERS &&
-      p.ntaps * p.kchunks >= SK_MIN_KBLOCKS && sk_workspace(stream, &p.sk_ws, &p.sk_flags))
+      p.ntaps * p.kchunks >= sk_min_kblocks() && sk_workspace(stream, &p.sk_ws, &p.sk_flags))
     p.sk_tiles = clusters + rem;
   B200_CUDA(launch_pdl(igemm_kernel<BN, STAGES, PAIR>, dim3(2 * clusters), dim3(320), smem_bytes, stream, 2, tmA, tmB,
                        p));
@@ -1073,7 +1153,7 @@ static int pick_bn(long long tiles_m, long long N, int kblocks) {
     const long long tiles = ((tiles_m + 1) / 2) * tn;
     double waves = double((tiles + clusters - 1) / clusters);
     // stream-K head (launch_igemm): a ragged last round costs its fraction plus about a fifth of a tile for the split
-    if (g_streamk && kblocks >= SK_MIN_KBLOCKS && tiles > clusters && tiles % clusters != 0)
+    if (g_streamk && kblocks >= sk_min_kblocks() && tiles > clusters && tiles % clusters != 0)
       waves = double(tiles) / clusters + 0.2;
     const double cost = waves * (bn / eff[i]);
     if (cost < best * 0.999) best = cost, best_bn = bn;
@@ -1119,7 +1199,7 @@ static int dispatch_igemm(const CUtensorMap& tmA, const void* W, long long ldw, 
 }
 
 static int fill_epilogue(IGemmParams& p, const b200mix_epilogue* e, void* C, long long ldc, long long rows_default) {
-  static const b200mix_epilogue kNone = {nullptr, nullptr, nullptr, 0, 0, nullptr, 0, 0, 0, 0, 1.0f, 0};
+  static const b200mix_epilogue kNone = {nullptr, nullptr, nullptr, 0, 0, nullptr, 0, 0, 0, 0, 1.0f, 0, nullptr, nullptr, nullptr, 0, 0.0f};
   if (!e) e = &kNone;
   p.bias = e->bias;
   p.row_add = e->row_add;
@@ -1135,6 +1215,15 @@ static int fill_epilogue(IGemmParams& p, const b200mix_epilogue* e, void* C, lon
   p.glu = e->glu;
   p.out_fp32 = e->out_fp32;
   p.out_scale = e->out_scale == 0.0f ? 1.0f : e->out_scale;
+  p.stats_out = reinterpret_cast<long long*>(e->stats_out);
+  p.ln_stats = reinterpret_cast<const long long*>(e->ln_stats);
+  p.ln_colsum = e->ln_colsum;
+  p.ln_rms = e->ln_rms, p.ln_eps = e->ln_eps;
+  p.ln_inv_k = static_cast<float>(1.0 / 16777216.0 / static_cast<double>(p.Kc));
+  B200_CHECK_ARG(!(p.ln_stats || p.stats_out) || p.ntaps == 1, "row statistics (folded LayerNorm) are a Linear feature");
+  B200_CHECK_ARG(!p.ln_stats || p.ln_colsum, "ln_stats needs ln_colsum");
+  B200_CHECK_ARG(!p.ln_stats || reinterpret_cast<uintptr_t>(p.ln_stats) % 16 == 0, "ln_stats must be 16-byte aligned");
+  B200_CHECK_ARG(!p.stats_out || reinterpret_cast<uintptr_t>(p.stats_out) % 16 == 0, "stats_out must be 16-byte aligned");
   B200_CHECK_ARG(!(p.glu && (p.N & 1)), "GLU epilogue needs an even N (got %d)", p.N);
   B200_CHECK_ARG(!(p.glu && (p.row_gate || p.residual || p.act)),
                  "GLU epilogue cannot be combined with gate / residual / activation");
@@ -1146,6 +1235,9 @@ static int fill_epilogue(IGemmParams& p, const b200mix_epilogue* e, void* C, lon
   if (p.row_add) vec = vec && (reinterpret_cast<uintptr_t>(p.row_add) % 16 == 0) && (p.ld_row % 4 == 0);
   if (p.row_gate) vec = vec && (reinterpret_cast<uintptr_t>(p.row_gate) % 16 == 0) && (p.ld_row % 4 == 0);
   p.vec_ok = vec ? 1 : 0;
+  // the statistics are taken in the coalesced bf16 epilogue: whole 32-column chunks, 16-byte aligned rows
+  B200_CHECK_ARG(!p.stats_out || (vec && !p.glu && !p.out_fp32 && p.N % 32 == 0),
+                 "stats_out needs a bf16 output with N %% 32 == 0 and 16-byte aligned rows, no GLU");
   return 0;
 }
 
@@ -1174,7 +1266,7 @@ extern "C" int b200mix_linear(const void* A, int64_t lda, const void* W, int64_t
 
   // M <= 8: weight-streaming kernel (decode steps, embedding MLPs) unless the epilogue needs per-group vectors
   if (g_skinny && M <= 8 && K % 8 == 0 && K < (1ll << 31) &&
-      (!epi || (!epi->row_add && !epi->row_gate && epi->residual_row_mod == 0 &&
+      (!epi || (!epi->row_add && !epi->row_gate && epi->residual_row_mod == 0 && !epi->stats_out && !epi->ln_stats &&
                 (epi->out_scale == 0.0f || epi->out_scale == 1.0f) && !(epi->glu && (N & 1)) &&
                 !(epi->glu && (epi->residual || epi->act))))) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -33,12 +33,17 @@ __device__ __forceinline__ float silu_f(float x) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// GroupNorm statistics: per (batch, CTA, group) partial sum / sum of squares in double, reduced in a fixed order
-// (no atomics => bit-reproducible). Block = PPB pixels x CV 8-channel vectors; each thread owns a fixed channel
-// vector, so every row is read with fully coalesced 16-byte loads.
+// GroupNorm statistics: per (batch, CTA, group) partial sum / sum of squares, exchanged as FIXED-POINT int64 (sum: 2^24,
+// sum of squares: 2^16) so that the cross-CTA reduction is integer adds: exact, order-independent (bit-reproducible
+// without atomics-ordering concerns) and off the FP64 pipe. The first version kept the partials in double; on this
+// part ~100 dependent DADDs per CTA (one warp, one group per lane) cost more than streaming the CTA's pixels
+// (tools/ln_fold_probe.py measured ~40 cycles per warp-level FP64 instruction). Only the last three operations per
+// group (mean, variance from the int64 totals) are double. Block = PPB pixels x CV 8-channel vectors; each thread owns
+// a fixed channel vector, so every row is read with fully coalesced 16-byte loads.
 // ------------------------------------------------------------------------------------------------------------
+constexpr float GN_FIX_SUM = 16777216.0f, GN_FIX_SQ = 65536.0f;
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, const __nv_bfloat16* __restrict__ x2,
-                                int C2, double* __restrict__ partial, float* __restrict__ mr,
+                                int C2, long long* __restrict__ partial, float* __restrict__ mr,  // n_per_group: 1 / elements per group
                                 unsigned int* __restrict__ counters, long long HW, int groups, int PPB, int pix_per_cta,
                                 double n_per_group, float eps) {
   extern __shared__ float sm[];  // [PPB][2][C]
@@ -91,14 +96,28 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
   }
   __syncthreads();
   const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    double ss = 0.0, qq = 0.0;
-    for (int l = 0; l < PPB; ++l) {
+  // `per` threads cooperate on one group (host guarantees blockDim >= groups): strided fp32 partial sums, combined in a
+  // fixed order through shared memory
+  const int per = blockDim.x / groups;
+  const int gq = threadIdx.x / per, jq = threadIdx.x % per;
+  float ss = 0.0f, qq = 0.0f;
+  if (gq < groups) {
+    const int n = PPB * cpg;
+    for (int e = jq; e < n; e += per) {
+      const int l = e / cpg, c = gq * cpg + (e - l * cpg);
       const float* row = sm + static_cast<size_t>(l) * 2 * C;
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) ss += row[c], qq += row[C + c];
+      ss += row[c], qq += row[C + c];
     }
-    double* o = partial + ((static_cast<long long>(b) * gridDim.x + blockIdx.x) * groups + g) * 2;
-    o[0] = ss, o[1] = qq;
+  }
+  __syncthreads();  // everybody has read the per-thread sums: the buffer is reused for the per-group combine
+  float2* comb = reinterpret_cast<float2*>(sm);  // [threads]
+  comb[threadIdx.x] = make_float2(ss, qq);
+  __syncthreads();
+  if (gq < groups && jq == 0) {
+    float a = 0.0f, c = 0.0f;
+    for (int t = 0; t < per; ++t) a += comb[threadIdx.x + t].x, c += comb[threadIdx.x + t].y;
+    long long* o = partial + ((static_cast<long long>(b) * gridDim.x + blockIdx.x) * groups + gq) * 2;
+    o[0] = __float2ll_rn(a * GN_FIX_SUM), o[1] = __float2ll_rn(c * GN_FIX_SQ);
   }
   // ---- the last CTA of this batch element reduces the per-CTA partials in a FIXED order (bit-reproducible whichever
   // CTA happens to be last) and writes (mean, rstd) per group: no separate finalize launch. The counter is reset for
@@ -113,22 +132,22 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  double* red = reinterpret_cast<double*>(sm);  // [threads][2] (dynamic smem is at least 256 * 16 bytes: host guarantees)
+  long long* red = reinterpret_cast<long long*>(sm);  // [threads][2] (dynamic smem is at least threads * 16 bytes: host guarantees)
   const int gx = gridDim.x;
-  const int per = blockDim.x / groups;  // threads cooperating on one group (host guarantees >= 1)
-  const int g = threadIdx.x / per, j = threadIdx.x % per;
-  double su = 0.0, sq = 0.0;
+  const int g = gq, j = jq;
+  long long su = 0, sq = 0;
   if (g < groups) {
-    const volatile double* srcp = partial + (static_cast<long long>(b) * gx * groups + g) * 2;
+    const volatile long long* srcp = partial + (static_cast<long long>(b) * gx * groups + g) * 2;
     for (int i = j; i < gx; i += per) su += srcp[static_cast<size_t>(i) * groups * 2], sq += srcp[static_cast<size_t>(i) * groups * 2 + 1];
   }
   red[2 * threadIdx.x] = su, red[2 * threadIdx.x + 1] = sq;
   __syncthreads();
   if (g < groups && j == 0) {
-    double a = 0.0, c = 0.0;
-    for (int t = 0; t < per; ++t) a += red[2 * (threadIdx.x + t)], c += red[2 * (threadIdx.x + t) + 1];
-    const double mean = a / n_per_group;
-    double var = c / n_per_group - mean * mean;
+    long long ai = 0, ci = 0;
+    for (int t = 0; t < per; ++t) ai += red[2 * (threadIdx.x + t)], ci += red[2 * (threadIdx.x + t) + 1];
+    // n_per_group arrives as its reciprocal: a double division is ~30 FP64 instructions on the kernel's critical tail
+    const double mean = static_cast<double>(ai) * (1.0 / GN_FIX_SUM) * n_per_group;
+    double var = static_cast<double>(ci) * (1.0 / GN_FIX_SQ) * n_per_group - mean * mean;
     if (var < 0.0) var = 0.0;
     mr[(b * groups + g) * 2 + 0] = static_cast<float>(mean);
     mr[(b * groups + g) * 2 + 1] = rsqrtf(static_cast<float>(var) + eps);
@@ -431,7 +450,7 @@ extern "C" int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2
   // partial region - changes from call to call.
   B200_CHECK_ARG(B <= 1024, "groupnorm: at most 1024 batch elements");
   unsigned int* counters = reinterpret_cast<unsigned int*>(stats);
-  double* dstats = reinterpret_cast<double*>(reinterpret_cast<char*>(stats) + 4096);
+  long long* dstats = reinterpret_cast<long long*>(reinterpret_cast<char*>(stats) + 4096);
   const long long need = 4096 + (long long)gx * B * groups * 16 + (long long)B * groups * 8;
   B200_CHECK_ARG(need <= stats_bytes, "groupnorm: stats scratch too small (%lld bytes needed)", need);
   B200_CHECK_ARG(groups <= 256 && groups <= threads, "groupnorm: at most min(256, block size) groups");
@@ -440,7 +459,7 @@ extern "C" int b200mix_groupnorm_nhwc(const void* x1, int64_t C1, const void* x2
   const size_t smem = std::max((size_t)PPB * 2 * C * sizeof(float), (size_t)threads * 2 * sizeof(double));
   B200_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(threads), smem, st, 1, reinterpret_cast<const __nv_bfloat16*>(x1),
                        (int)C1, reinterpret_cast<const __nv_bfloat16*>(x2), (int)C2, dstats, mr, counters, (long long)HW,
-                       (int)groups, PPB, (int)pix_per_cta, static_cast<double>(HW) * (double)(C / groups), eps));
+                       (int)groups, PPB, (int)pix_per_cta, 1.0 / (static_cast<double>(HW) * (double)(C / groups)), eps));
   B200_CUDA(launch_pdl(gn_apply_kernel, grid, dim3(threads), 0, st, 1, reinterpret_cast<const __nv_bfloat16*>(x1),
                        (int)C1, reinterpret_cast<const __nv_bfloat16*>(x2), (int)C2, gamma, beta,
                        reinterpret_cast<__nv_bfloat16*>(y), (const float*)mr, (long long)HW, (int)groups, (int)silu, PPB,

@@ -91,7 +91,8 @@ def init(device: int = 0):
 
 
 def make_epilogue(bias=None, row_add=None, row_gate=None, ld_row=0, rows_per_group=0, residual=None, ldr=0,
-                  act=ACT_NONE, glu=GLU_NONE, out_fp32=False, out_scale=1.0, residual_row_mod=0) -> Epilogue:
+                  act=ACT_NONE, glu=GLU_NONE, out_fp32=False, out_scale=1.0, residual_row_mod=0, stats_out=None,
+                  ln=None) -> Epilogue:
     e = Epilogue()
     e.bias = None if bias is None else _req(bias, torch.float32, "bias").data_ptr()
     e.row_add = None if row_add is None else _req(row_add, torch.float32, "row_add").data_ptr()
@@ -105,18 +106,65 @@ def make_epilogue(bias=None, row_add=None, row_gate=None, ld_row=0, rows_per_gro
     e.out_fp32 = 1 if out_fp32 else 0
     e.out_scale = float(out_scale)
     e.residual_row_mod = int(residual_row_mod)
+    e.stats_out = None if stats_out is None else _req(stats_out, torch.int64, "stats_out").data_ptr()
+    if ln is not None:  # folded LayerNorm, consumer side: (RowStats of the input rows, colsum [N] fp32, eps[, rms])
+        stats, colsum, eps = ln[:3]
+        e.ln_stats = _req(stats.buf, torch.int64, "ln_stats").data_ptr()
+        e.ln_colsum = _req(colsum, torch.float32, "ln_colsum").data_ptr()
+        e.ln_eps, e.ln_rms = float(eps), int(bool(ln[3])) if len(ln) > 3 else 0
     return e
 
 
+class RowStats:
+    """Sum and sum of squares of every row of a bf16 [M, N] GEMM output, accumulated by that GEMM's epilogue
+    (linear(..., stats=...)) as 2^24 fixed point: buf int64 [M, 2], zeroed before the producing call. Consumed by
+    linear(..., ln=(stats, colsum, eps))."""
+    SCALE = float(1 << 24)
+
+    def __init__(self, buf: torch.Tensor, width: int):
+        self.buf, self.width = buf, width
+
+    @staticmethod
+    def arena(n: int, rows: int, device) -> torch.Tensor:
+        """n zeroed [rows, 2] tables in one allocation / one memset (a transformer stack takes 1 + 3 per block)."""
+        return torch.zeros(n, rows, 2, device=device, dtype=torch.int64)
+
+    def mean_rstd(self, eps: float):
+        """(mean, rstd) per row, the way the consuming epilogue rebuilds them (for tests)."""
+        t = self.buf.double() / self.SCALE
+        mean = t[:, 0] / self.width
+        var = (t[:, 1] / self.width - mean * mean).clamp_min(0)
+        return mean.float(), torch.rsqrt(var.float() + eps)
+
+
+def fold_layernorm_into_linear(w: torch.Tensor, gamma: torch.Tensor, beta=None, bias=None):
+    """w: fp32 [N, K] (the consumer's weight), gamma / beta: the LayerNorm affine over K, bias: the consumer's bias or None.
+    Returns (W' bf16 [N, K], colsum fp32 [N], bias' fp32 [N]) for linear(h, W', bias', ln=(stats, colsum, eps)) ==
+    linear(layernorm(h) * gamma + beta, w, bias)."""
+    wf = w.float()
+    w2 = (wf * gamma.float()[None, :]).to(bf16).contiguous()
+    colsum = w2.float().sum(1).contiguous()
+    b2 = torch.zeros(w.shape[0], device=w.device, dtype=torch.float32) if bias is None else bias.float().clone()
+    if beta is not None:
+        b2 = b2 + wf @ beta.float()
+    return w2, colsum, b2.contiguous()
+
+
+
 def _epi_tag(e) -> str:
-    parts = [n for n, on in (("bias", e.bias), ("radd", e.row_add), ("gate", e.row_gate), ("res", e.residual),
-                             (f"act{e.act}", e.act), (f"glu{e.glu}", e.glu), ("f32", e.out_fp32)) if on]
+    parts = [n for n, on in (("ln", e.ln_stats), ("bias", e.bias), ("radd", e.row_add), ("gate", e.row_gate),
+                             ("res", e.residual), (f"act{e.act}", e.act), (f"glu{e.glu}", e.glu), ("f32", e.out_fp32),
+                             ("stats", e.stats_out)) if on]
     return (" " + "+".join(parts)) if parts else ""
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, act=ACT_NONE, glu=GLU_NONE, residual=None, row_add=None,
-           row_gate=None, rows_per_group=0, out_fp32=False, out=None, out_scale=1.0, residual_row_mod=0) -> torch.Tensor:
-    """out[M, N(/2)] = epilogue(a[M, K] @ w[N, K]^T). a: bf16 [..., K] (last dim contiguous), w: bf16 [N, K]."""
+           row_gate=None, rows_per_group=0, out_fp32=False, out=None, out_scale=1.0, residual_row_mod=0, stats=False,
+           ln=None):
+    """out[M, N(/2)] = epilogue(a[M, K] @ w[N, K]^T). a: bf16 [..., K] (last dim contiguous), w: bf16 [N, K].
+    stats=True or a ZEROED int64 [M, 2] tensor (RowStats.arena): also returns the RowStats of the output rows
+    (-> (out, RowStats)); ln=(RowStats of a's rows, colsum, eps[, rms]): a is the UN-normalised tensor and w / bias carry
+    the folded affine (fold_layernorm_into_linear)."""
     _req(a, bf16, "a"), _req(w, bf16, "w")
     K = a.shape[-1]
     a2 = a.reshape(-1, K)
@@ -130,15 +178,25 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, act=ACT_NONE, glu=GLU
     if residual is not None:
         res2 = residual.reshape(-1, residual.shape[-1])
     mod = row_add if row_add is not None else row_gate
+    rs = None
+    want_stats = stats is not None and stats is not False
+    if want_stats:
+        buf = torch.zeros(M, 2, device=a.device, dtype=torch.int64) if stats is True else stats
+        if tuple(buf.shape) != (M, 2):
+            raise ValueError(f"stats table must be int64 [{M}, 2], got {tuple(buf.shape)}")
+        rs = RowStats(buf, N)
+    if ln is not None and (ln[0].buf.shape[0] != M or ln[0].width != K):
+        raise ValueError(f"row statistics are for a [{ln[0].buf.shape[0]}, {ln[0].width}] tensor, the input is [{M}, {K}]")
     e = make_epilogue(bias=bias, row_add=row_add, row_gate=row_gate, ld_row=0 if mod is None else mod.stride(0),
                       rows_per_group=rows_per_group, residual=res2, ldr=0 if res2 is None else res2.stride(0), act=act,
-                      glu=glu, out_fp32=out_fp32, out_scale=out_scale, residual_row_mod=residual_row_mod)
+                      glu=glu, out_fp32=out_fp32, out_scale=out_scale, residual_row_mod=residual_row_mod,
+                      stats_out=None if rs is None else rs.buf, ln=ln)
     out2 = out.reshape(-1, n_out)
     with _Timed("igemm", 2.0 * M * N * K, "flop", lambda: f"lin {M}x{N}x{K}" + _epi_tag(e)):
         check(lib.b200mix_linear(_p(a2), a2.stride(0), _p(w), w.stride(0), _p(out2), out2.stride(0), M, N, K,
                                  ctypes.byref(e), _stream()), "b200mix_linear")
     _count()
-    return out
+    return (out, rs) if want_stats else out
 
 
 def linear_batched(a: torch.Tensor, w: torch.Tensor, bias=None, *, out: torch.Tensor, act=ACT_NONE, glu=GLU_NONE,

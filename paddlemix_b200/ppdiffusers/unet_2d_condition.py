@@ -17,6 +17,7 @@ from dataclasses import dataclass
 from types import SimpleNamespace
 from typing import Any, Dict, Optional, Tuple, Union
 
+import os
 import numpy as np
 import torch
 
@@ -110,7 +111,11 @@ class Attention:
         out[:, :d] = w
         return out.reshape(H * dp, -1)
 
-    def load(self, P, dev):
+    def load(self, P, dev, norm=None):
+        """norm: the LayerNorm in front of this layer (BasicTransformerBlock.norm1 / norm2); its affine is folded into a
+        second copy of the query-side projection so that the block can run without the LayerNorm kernel (see
+        _BasicTransformerBlock.__call__); the plain weights stay for custom processors."""
+        from .. import ops
         n = self.name
         wq = self._pad_rows(_to_t(P[n + ".to_q.weight"]).t().contiguous())
         wk = self._pad_rows(_to_t(P[n + ".to_k.weight"]).t().contiguous())
@@ -124,8 +129,13 @@ class Attention:
         if self.is_cross:
             self.w_q = wq.to(dev, bf16).contiguous()
             self.w_kv_host = torch.cat([wk, wv], 0)  # batched across blocks by the model
+            w_in = wq
         else:
-            self.w_qkv = torch.cat([wq, wk, wv], 0).to(dev, bf16).contiguous()
+            w_in = torch.cat([wq, wk, wv], 0)
+            self.w_qkv = w_in.to(dev, bf16).contiguous()
+        self.ln_fold = None
+        if norm is not None:
+            self.ln_fold = ops.fold_layernorm_into_linear(w_in.to(dev, torch.float32), norm.w, norm.b)
         self.w_o = wo.to(dev, bf16).contiguous()
         self.b_o = _to_t(P[n + ".to_out.0.bias"]).to(dev)
 
@@ -154,21 +164,28 @@ class Attention:
             raise ValueError(f"attention mask batch {m.shape[0]} does not match the input batch {batch_size}")
         return m if m.dtype in (torch.float32, bf16) else m.float()
 
-    def fused_forward(self, x, ctx=None, residual=None, attention_mask=None):
+    def fused_forward(self, x, ctx=None, residual=None, attention_mask=None, x_stats=None, out_stats=None):
         """x: [B,S,C] bf16. Returns attention output after to_out, as the reference processors do; `residual` (optional)
-        is added in the out-projection's epilogue."""
+        is added in the out-projection's epilogue. x_stats (ops.RowStats of x's rows): x is the UN-normalised hidden
+        state and the query-side projection applies the folded LayerNorm; out_stats (a zeroed int64 [rows, 2] table):
+        also return the RowStats of the result (for the next folded LayerNorm)."""
         from .. import ops
         B, S, C = x.shape
         H, dp = self.heads, self.head_pad
+        if x_stats is not None:
+            w_in, colsum, b_in = self.ln_fold
+            ln = (x_stats, colsum, self.ln_eps)
+        else:
+            w_in, b_in, ln = (self.w_q if self.is_cross else self.w_qkv), None, None
         if not self.is_cross:
-            qkv = ops.linear(x, self.w_qkv)  # [B,S,3*H*dp]
+            qkv = ops.linear(x, w_in, b_in, ln=ln)  # [B,S,3*H*dp]
             q, k, v = (qkv[:, :, i * self.inner:(i + 1) * self.inner].unflatten(-1, (H, dp)) for i in range(3))
         else:
-            q = ops.linear(x, self.w_q).unflatten(-1, (H, dp))
+            q = ops.linear(x, w_in, b_in, ln=ln).unflatten(-1, (H, dp))
             k, v = self._kv
         mask = self.prepare_attention_mask(attention_mask, k.shape[1], B)
         o = ops.sdpa(q, k, v, scale=self.scale, attn_mask=mask)
-        return ops.linear(o.reshape(B, S, H * dp), self.w_o, self.b_o, residual=residual)
+        return ops.linear(o.reshape(B, S, H * dp), self.w_o, self.b_o, residual=residual, stats=out_stats)
 
     def fused_forward_residual(self, x, residual, attention_mask=None):
         """Same as fused_forward but with the residual add fused into the out-projection epilogue."""
@@ -295,21 +312,47 @@ class _BasicTransformerBlock:
         out[self.name + ".ff.net.0.proj.bias"] = (8 * self.dim,)
         return out
 
+    LN_EPS = 1e-5
+
     def load(self, P, dev):
-        for m in (self.norm1, self.norm2, self.norm3, self.attn1, self.attn2, self.ff2):
+        from .. import ops
+        for m in (self.norm1, self.norm2, self.norm3, self.ff2):
             m.load(P, dev)
+        self.attn1.load(P, dev, norm=self.norm1)
+        self.attn2.load(P, dev, norm=self.norm2)
+        self.attn1.ln_eps = self.attn2.ln_eps = self.LN_EPS
         # GEGLU: proj(x).chunk(2) = (value, gate) -> interleave rows so both land in the same accumulator tile
         w = _to_t(P[self.name + ".ff.net.0.proj.weight"]).t().contiguous()  # [8C, C]
         b = _to_t(P[self.name + ".ff.net.0.proj.bias"])
         half = w.shape[0] // 2
-        self.ff1_w = torch.stack([w[:half], w[half:]], 1).reshape(2 * half, -1).contiguous().to(dev, bf16)
-        self.ff1_b = torch.stack([b[:half], b[half:]], 1).reshape(2 * half).contiguous().to(dev)
+        w_il = torch.stack([w[:half], w[half:]], 1).reshape(2 * half, -1).contiguous()
+        b_il = torch.stack([b[:half], b[half:]], 1).reshape(2 * half).contiguous()
+        self.ff1_w = w_il.to(dev, bf16)
+        self.ff1_b = b_il.to(dev)
+        # norm3 folded into the GEGLU projection (W' = W * gamma, bias' = bias + W beta, column sums of W')
+        self.ff1_fold = ops.fold_layernorm_into_linear(w_il.to(dev, torch.float32), self.norm3.w, self.norm3.b, self.ff1_b)
 
-    def __call__(self, h, ctx, cross_attention_kwargs, attention_mask=None, encoder_attention_mask=None):
-        """attention.py:352-489: attn1 gets `attention_mask`, attn2 gets `encoder_attention_mask` (:411-441)."""
+    def __call__(self, h, ctx, cross_attention_kwargs, attention_mask=None, encoder_attention_mask=None, h_stats=None,
+                 stats_tables=None):
+        """attention.py:352-489: attn1 gets `attention_mask`, attn2 gets `encoder_attention_mask` (:411-441).
+        h_stats = ops.RowStats of h (left by the GEMM that produced h): the three LayerNorms then never run as kernels.
+        Each is folded into the projection that consumes it (norm1 -> to_q|k|v, norm2 -> attn2.to_q, norm3 -> GEGLU
+        proj), whose epilogue rebuilds the row's mean / rstd from the statistics the producing GEMM's epilogue took of
+        the residual stream (stats_tables: three zeroed int64 [rows, 2] tables for the three residual updates of this
+        block). Returns (h, RowStats of h) in that mode. Custom processors get the reference order
+        (norm -> processor -> residual add) on explicit LayerNorm kernels."""
         from .. import ops
         from .._lib import GLU_GEGLU
         kw = cross_attention_kwargs or {}
+        default = type(self.attn1.processor) is AttnProcessorB200 and type(self.attn2.processor) is AttnProcessorB200
+        if h_stats is not None and default and not kw:
+            h, st = self.attn1.fused_forward(h, None, residual=h, attention_mask=attention_mask, x_stats=h_stats,
+                                             out_stats=stats_tables[0])
+            h, st = self.attn2.fused_forward(h, None, residual=h, attention_mask=encoder_attention_mask, x_stats=st,
+                                             out_stats=stats_tables[1])
+            w3, colsum3, b3 = self.ff1_fold
+            ff = ops.linear(h, w3, b3, glu=GLU_GEGLU, ln=(st, colsum3, self.LN_EPS))
+            return ops.linear(ff, self.ff2.w, self.ff2.b, residual=h, stats=stats_tables[2])
         n = ops.layernorm(h, self.norm1.w, self.norm1.b, eps=1e-5)
         if type(self.attn1.processor) is AttnProcessorB200 and not kw:
             h = self.attn1.fused_forward_residual(n, h, attention_mask)
@@ -324,7 +367,7 @@ class _BasicTransformerBlock:
                                           attention_mask=encoder_attention_mask, **kw), h)
         n = ops.layernorm(h, self.norm3.w, self.norm3.b, eps=1e-5)
         ff = ops.linear(n, self.ff1_w, self.ff1_b, glu=GLU_GEGLU)
-        return ops.linear(ff, self.ff2.w, self.ff2.b, residual=h)
+        return ops.linear(ff, self.ff2.w, self.ff2.b, residual=h, stats=None if h_stats is None else stats_tables[2])
 
 
 def _add(a, b):
@@ -334,6 +377,7 @@ def _add(a, b):
 
 class _Transformer2D:
     """Transformer2DModel (transformer_2d.py:54-509), continuous-input branch."""
+    FOLD_LAYERNORM = os.environ.get("B200MIX_FOLD_LN", "1") != "0"  # measurement switch: 0 = explicit LayerNorm kernels
 
     def __init__(self, name, dim, heads, ctx_dim, layers, groups, use_linear):
         self.name, self.dim, self.groups = name, dim, groups
@@ -356,9 +400,18 @@ class _Transformer2D:
         from .. import ops
         B, H, W, C = x.shape
         n = ops.groupnorm_nhwc(x, self.norm.w, self.norm.b, groups=self.groups, eps=1e-6, silu=False)
-        h = ops.linear(n.reshape(B, H * W, C), self.proj_in.w, self.proj_in.b)
-        for blk in self.blocks:
-            h = blk(h, ctx, cross_attention_kwargs, attention_mask, encoder_attention_mask)
+        # the residual stream travels with its row statistics (taken by the epilogue of whichever GEMM wrote it), so
+        # the blocks' LayerNorms are folded into their consumers; FOLD_LAYERNORM = False restores the explicit kernels
+        if self.FOLD_LAYERNORM and C % 32 == 0:
+            tables = ops.RowStats.arena(1 + 3 * len(self.blocks), B * H * W, x.device)  # one memset for the whole stack
+            h, st = ops.linear(n.reshape(B, H * W, C), self.proj_in.w, self.proj_in.b, stats=tables[0])
+            for j, blk in enumerate(self.blocks):
+                h, st = blk(h, ctx, cross_attention_kwargs, attention_mask, encoder_attention_mask, h_stats=st,
+                            stats_tables=tables[1 + 3 * j:4 + 3 * j])
+        else:
+            h = ops.linear(n.reshape(B, H * W, C), self.proj_in.w, self.proj_in.b)
+            for blk in self.blocks:
+                h = blk(h, ctx, cross_attention_kwargs, attention_mask, encoder_attention_mask)
         out = ops.linear(h, self.proj_out.w, self.proj_out.b, residual=x.reshape(B, H * W, C))
         return out.reshape(B, H, W, C)
 

@@ -90,7 +90,7 @@ def test_linear_streamk(ops, M, N, K, clusters, bn, epi):
     outs = {}
     try:
         for on in (1, 0):
-            _streamk(lib, on, clusters)
+            _streamk(lib, 2 * on, clusters)  # 2 = split shallow reductions too (the default keeps them round-robin)
             lib.b200mix_debug_force_bn(bn)
             outs[on] = ops.linear(a, w, bias, **kw)
             if on:
@@ -116,7 +116,7 @@ def test_conv3x3_streamk(ops, clusters):
     w = rnd(Cout, 3, 3, Cin, seed=36, scale=(9 * Cin) ** -0.5)
     bias, temb, res = rnd(Cout, seed=37, dtype=torch.float32), rnd(B, Cout, seed=38, dtype=torch.float32), rnd(B, H, W, Cout, seed=39)
     try:
-        _streamk(lib, 1, clusters)
+        _streamk(lib, 2, clusters)
         out = ops.conv3x3(x, w, bias, row_add=temb, residual=res)
     finally:
         _streamk(lib, 1, 0)
@@ -128,7 +128,7 @@ def test_conv3x3_streamk(ops, clusters):
 def test_linear_streamk_many_launches_and_streams(ops):
     """Flags are lowered by the consumer: 50 back-to-back launches, then a second stream (its own workspace slot), then a
     CUDA graph captured on a third stream, all give the bits of the first launch."""
-    M, N, K = 8192, 1280, 1280
+    M, N, K = 8192, 1280, 5120  # 80 k-blocks: stream-K by default
     a, w, res = rnd(M, K, seed=40), rnd(N, K, seed=41, scale=K ** -0.5), rnd(M, N, seed=42)
     first = ops.linear(a, w, residual=res)
     for _ in range(50):
@@ -148,6 +148,51 @@ def test_linear_streamk_many_launches_and_streams(ops):
         g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out3, first)
+
+
+@pytest.mark.parametrize("M,C,N2,bn", [(8192, 1280, 3840, 0), (1000, 320, 640, 0), (300, 64, 96, 32), (4096, 640, 5120, 0),
+                                        (2048, 1280, 1280, 160), (520, 96, 64, 64)])
+@pytest.mark.parametrize("glu", [0, 1])
+def test_linear_folded_layernorm(ops, M, C, N2, bn, glu):
+    """BasicTransformerBlock (attention.py:352-489): h = to_out(o) + bias + residual; q = to_q(LayerNorm(h)).
+    Producer epilogue statistics + consumer epilogue normalisation against F.layer_norm -> F.linear in fp32 on the same
+    bf16 h. Tolerance: the usual bf16-output GEMM bound (the folded form rounds h once instead of twice)."""
+    from paddlemix_b200._lib import lib
+    K0 = 256
+    a, w0 = rnd(M, K0, seed=60), rnd(C, K0, seed=61, scale=K0 ** -0.5)
+    b0, res = rnd(C, seed=62, dtype=torch.float32), rnd(M, C, seed=63, scale=2.0)
+    res = (res.float() + 1.5).to(bf16)  # a row mean well away from zero
+    gamma = 1.0 + 0.3 * rnd(C, seed=64, dtype=torch.float32)
+    beta = 0.2 * rnd(C, seed=65, dtype=torch.float32)
+    w1 = rnd(N2, C, seed=66, dtype=torch.float32) * C ** -0.5
+    b1 = rnd(N2, seed=67, dtype=torch.float32)
+    lib.b200mix_debug_force_bn(bn)
+    try:
+        h, st = ops.linear(a, w0, b0, residual=res, stats=True)
+        plain = ops.linear(a, w0, b0, residual=res)
+        assert torch.equal(h, plain), "taking the statistics must not change the output"
+        hf = h.float()
+        tot = st.buf.double() / st.SCALE
+        close(tot[:, 0], hf.double().sum(1), 2e-2, 1e-4, "row sums")
+        close(tot[:, 1], (hf.double() * hf.double()).sum(1), 2e-2, 1e-4, "row sums of squares")
+        h2, st2 = ops.linear(a, w0, b0, residual=res, stats=True)
+        assert torch.equal(st2.buf, st.buf), "fixed-point row statistics must be reproducible bit for bit"
+        mean, rstd = st.mean_rstd(1e-5)
+        close(mean, hf.mean(1), 1e-4, 1e-4, "mean")
+        close(rstd, torch.rsqrt(hf.var(1, unbiased=False) + 1e-5), 1e-4, 2e-3, "rstd")
+        w1f, colsum, b1f = ops.fold_layernorm_into_linear(w1, gamma, beta, b1)
+        out = ops.linear(h, w1f, b1f, ln=(st, colsum, 1e-5), glu=glu)
+        again = ops.linear(h, w1f, b1f, ln=(st, colsum, 1e-5), glu=glu)
+    finally:
+        lib.b200mix_debug_force_bn(0)
+    assert torch.equal(out, again)
+    z = F.linear(F.layer_norm(hf, (C,), gamma, beta, 1e-5), w1, b1)
+    ref = z[:, 0::2] * F.gelu(z[:, 1::2]) if glu else z
+    close(out, ref, 3e-2, 1.5e-2, f"folded layernorm {M}x{C}->{N2} glu={glu}")
+    # and against the two-kernel form it replaces
+    n = ops.layernorm(h, gamma, beta, eps=1e-5)
+    two = ops.linear(n, w1.to(bf16), b1, glu=glu)
+    close(out, two.float(), 6e-2, 3e-2, "folded vs layernorm kernel + linear")
 
 
 @pytest.mark.parametrize("act", [1, 2, 3, 4])
