@@ -82,6 +82,8 @@ const char* b200mix_version(void);
  * place of paddle::Tensor in the reference ops. */
 int b200mix_init(int device);
 int b200mix_num_sms(void);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream`: zeroes the row-statistics tables of b200mix_epilogue.stats_out. */
+int b200mix_zero_bytes(void* ptr, int64_t bytes, void* stream);
 
 /* ---- the path's only collective -------------------------------------------------------------
  * Images are sharded over ranks (one process per GPU, weights replicated, no per-step communication); the finished

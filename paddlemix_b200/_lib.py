@@ -47,6 +47,7 @@ GLU_NONE, GLU_GEGLU, GLU_SWIGLU = 0, 1, 2
 SIGNATURES = {
     "b200mix_init": [c_int],
     "b200mix_num_sms": [],
+    "b200mix_zero_bytes": [c_void_p, c_int64, c_void_p],
     "b200mix_nccl_load": [c_char_p],
     "b200mix_nccl_version": [],
     "b200mix_nccl_unique_id": [c_void_p],

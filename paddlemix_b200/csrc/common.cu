@@ -123,6 +123,15 @@ int b200mix_init(int device) {
   return b200::ensure_device();
 }
 
+/* Zero `bytes` bytes on the caller's stream (a memset node under stream capture): the folded-LayerNorm statistics tables
+ * (b200mix_epilogue.stats_out) must be zero before the producing GEMM runs. */
+int b200mix_zero_bytes(void* ptr, int64_t bytes, void* stream) {
+  if (int rc = b200::ensure_device()) return rc;
+  B200_CHECK_ARG(ptr && bytes >= 0, "zero_bytes: bad arguments");
+  B200_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int b200mix_num_sms(void) {
   if (b200::ensure_device() != 0) return B200MIX_ERR_NO_DEVICE;
   return b200::num_sms();

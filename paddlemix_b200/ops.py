@@ -127,7 +127,9 @@ class RowStats:
     @staticmethod
     def arena(n: int, rows: int, device) -> torch.Tensor:
         """n zeroed [rows, 2] tables in one allocation / one memset (a transformer stack takes 1 + 3 per block)."""
-        return torch.zeros(n, rows, 2, device=device, dtype=torch.int64)
+        buf = torch.empty(n, rows, 2, device=device, dtype=torch.int64)
+        check(lib.b200mix_zero_bytes(_p(buf), buf.numel() * 8, _stream()), "b200mix_zero_bytes")
+        return buf
 
     def mean_rstd(self, eps: float):
         """(mean, rstd) per row, the way the consuming epilogue rebuilds them (for tests)."""
@@ -181,7 +183,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias=None, *, act=ACT_NONE, glu=GLU
     rs = None
     want_stats = stats is not None and stats is not False
     if want_stats:
-        buf = torch.zeros(M, 2, device=a.device, dtype=torch.int64) if stats is True else stats
+        buf = RowStats.arena(1, M, a.device)[0] if stats is True else stats
         if tuple(buf.shape) != (M, 2):
             raise ValueError(f"stats table must be int64 [{M}, 2], got {tuple(buf.shape)}")
         rs = RowStats(buf, N)

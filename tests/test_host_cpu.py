@@ -174,3 +174,104 @@ def test_data_parallel_plumbing_gloo(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0, out.decode()
+
+
+def test_fold_layernorm_into_linear_algebra():
+    """The load-time fold behind b200mix_epilogue.ln_stats: Linear(LayerNorm(h)) == rstd * (h W'^T - mean * colsum) + bias'
+    (BasicTransformerBlock norm1/2/3 -> to_q|k|v / to_q / GEGLU proj, attention.py:352-489). fp64 on the CPU; the only
+    difference left is the bf16 rounding of W' = W * gamma."""
+    import torch
+    import torch.nn.functional as F
+
+    from paddlemix_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    M, K, N = 37, 96, 40
+    h = (torch.randn(M, K, generator=g) * 2 + 0.7).to(torch.bfloat16).double()
+    w, b = torch.randn(N, K, generator=g) * K ** -0.5, torch.randn(N, generator=g)
+    gamma, beta = 1 + 0.3 * torch.randn(K, generator=g), 0.2 * torch.randn(K, generator=g)
+    w2, colsum, b2 = ops.fold_layernorm_into_linear(w, gamma, beta, b)
+    assert w2.dtype == torch.bfloat16 and torch.equal(colsum, w2.float().sum(1))
+    mean, var = h.mean(1, keepdim=True), h.var(1, unbiased=False, keepdim=True)
+    rstd = torch.rsqrt(var + 1e-5)
+    out = rstd * (h @ w2.double().t() - mean * colsum.double()[None]) + b2.double()[None]
+    ref = F.linear(F.layer_norm(h, (K,), gamma.double(), beta.double(), 1e-5), w.double(), b.double())
+    assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    # with unrounded folded weights the identity is exact
+    w2x = w.double() * gamma.double()[None]
+    outx = rstd * (h @ w2x.t() - mean * w2x.sum(1)[None]) + (b.double() + w.double() @ beta.double())[None]
+    assert (outx - ref).abs().max().item() < 1e-9
+    # fixed-point row totals (2^24) reproduce mean / rstd the way the consuming epilogue rebuilds them
+    tab = torch.stack([(h.sum(1) * ops.RowStats.SCALE).round(), ((h * h).sum(1) * ops.RowStats.SCALE).round()], 1).to(torch.int64)
+    m2, r2 = ops.RowStats(tab, K).mean_rstd(1e-5)
+    assert (m2.double() - mean[:, 0]).abs().max().item() < 1e-5 and (r2.double() / rstd[:, 0] - 1).abs().max().item() < 1e-4
+
+
+def test_fold_upsample_conv_weight_algebra():
+    """b200mix_conv3x3_up2x's per-parity 2x2 filters == F.interpolate(scale 2, nearest) + conv3x3 (Upsample2D,
+    resnet.py:169-218), including the zero padding at every border."""
+    import torch
+    import torch.nn.functional as F
+
+    from paddlemix_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    O, I, H, W = 6, 5, 4, 7
+    w = torch.randn(O, 3, 3, I, generator=g).to(torch.bfloat16).float()
+    w4 = ops.fold_upsample_conv_weight(w).float().reshape(O, 2, 2, 2, 2, I)
+    x = torch.randn(2, I, H, W, generator=g)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w.permute(0, 3, 1, 2), padding=1)
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for py in range(2):
+        for px in range(2):
+            acc = 0
+            for a in range(2):
+                for b in range(2):
+                    dy, dx = a - 1 + py, b - 1 + px  # the tap table of b200mix_conv3x3_up2x (csrc/gemm.cu)
+                    acc = acc + torch.einsum("bchw,oc->bohw", xp[:, :, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W], w4[:, py, px, a, b])
+            out[:, :, py::2, px::2] = acc
+    assert (out - ref).abs().max().item() < 2e-2 * ref.abs().max().item()  # bf16 rounding of the summed taps only
+
+
+def test_streamk_schedule_covers_every_k_block_once():
+    """Python mirror of SegIter (csrc/gemm.cu): the stream-K head + round-robin rest visits every (tile, k-block) exactly
+    once, every cluster gets the same number of k-blocks (+-1), a split tile has exactly one head piece (last piece of
+    cluster c) and one tail piece (first piece of cluster c + 1)."""
+    import random
+
+    def segs(sk_tiles, total, kblocks, c, nc):
+        units = sk_tiles * kblocks
+        u, u1, out = c * units // nc, (c + 1) * units // nc, []
+        while u < u1:
+            st = u // kblocks
+            kb0 = u - st * kblocks
+            kb1 = min(kblocks, kb0 + (u1 - u))
+            u += kb1 - kb0
+            out.append((st, kb0, kb1))
+        out += [(st, 0, kblocks) for st in range(sk_tiles + c, total, nc)]
+        return out
+
+    rnd = random.Random(0)
+    checked = 0
+    while checked < 300:
+        nc, total, kb = rnd.randint(1, 74), rnd.randint(2, 1500), rnd.randint(8, 400)
+        if total <= nc or total % nc == 0:
+            continue
+        checked += 1
+        sk = nc + total % nc
+        allsegs = [segs(sk, total, kb, c, nc) for c in range(nc)]
+        seen = set()
+        for c, ss in enumerate(allsegs):
+            for i, (st, a, b) in enumerate(ss):
+                assert a < b
+                if a > 0:  # tail piece
+                    assert i == 0 and b == kb
+                    assert [s for s in allsegs[c - 1] if s[0] == st] == [(st, 0, a)]
+                elif b < kb:  # head piece
+                    assert allsegs[c + 1][0] == (st, b, kb)
+                    assert all(s[1] == 0 and s[2] == kb for s in ss[i + 1:])
+                for k in range(a, b):
+                    assert (st, k) not in seen
+                    seen.add((st, k))
+        assert len(seen) == total * kb
+        lens = [sum(b - a for _, a, b in ss) for ss in allsegs]
+        assert max(lens) - min(lens) <= 1
