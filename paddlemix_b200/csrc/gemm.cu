@@ -343,6 +343,7 @@ __device__ __forceinline__ void epilogue_prefetch_staged(const IGemmParams& p, u
   }
 }
 
+template <bool STATS>
 __device__ __forceinline__ void epilogue_chunk_staged(const IGemmParams& p, const ActCoef& ac, const uint32_t (&r)[32],
                                                       const uint4 (&resv)[4], const float* bias_c, const RowMap& rm,
                                                       uint8_t* stage, int lane, long long g, int n_abs, uint64_t (&st)[2]) {
@@ -404,7 +405,7 @@ __device__ __forceinline__ void epilogue_chunk_staged(const IGemmParams& p, cons
     const uint4 w = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
     *reinterpret_cast<uint4*>(stage + stage_addr(lane, j)) = w;
-    if (p.stats_out) {  // row statistics of the ROUNDED values (what the consumer of this tensor reads), packed fp32 pairs
+    if (STATS) {  // row statistics of the ROUNDED values (what the consumer of this tensor reads), packed fp32 pairs
       const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -442,7 +443,10 @@ struct IGemmCfg {
 #endif
 constexpr int IG_WARP_MMA = IGEMM_ROLES_LOW ? 1 : 8, IG_WARP_TMA = IGEMM_ROLES_LOW ? 0 : 9, IG_EPI_BASE = IGEMM_ROLES_LOW ? 2 : 0;
 
-template <int BN, int STAGES, bool PAIR>
+// LNM: the folded-LayerNorm epilogues are separate instantiations - the plain kernel carries none of their code (with
+// runtime flags only, their live ranges and branches cost every GEMM of the step ~2 %: 58.2 vs 57.0 ms on one clock).
+enum { LNM_NONE = 0, LNM_CONSUMER = 1, LNM_PRODUCER = 2 };
+template <int BN, int STAGES, bool PAIR, int LNM>
 __global__ void __launch_bounds__(320, 1)
     igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ IGemmParams p) {
@@ -658,7 +662,7 @@ __global__ void __launch_bounds__(320, 1)
           bias_r[i] = (wg + 2 * i < BN / 32 && col < p.N) ? __ldg(p.bias + col) : 0.0f;
         }
       }
-      if (p.ln_stats) {
+      if (LNM == LNM_CONSUMER) {
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
           const int col = n0 + (wg + 2 * i) * 32 + lane;
@@ -670,13 +674,13 @@ __global__ void __launch_bounds__(320, 1)
 #pragma unroll
         for (int i = 0; i < NI; ++i) bias_s[i * 32 + lane] = bias_r[i];
       }
-      if (p.ln_stats) {
+      if (LNM == LNM_CONSUMER) {
 #pragma unroll
         for (int i = 0; i < NI; ++i) colsum_s[i * 32 + lane] = cs_r[i];
       }
       __syncwarp();
       float ln_rstd = 1.0f, ln_shift = 0.0f;
-      if (p.ln_stats && LN_PROBE != 1) {  // mean / rstd of my row from the totals the producing GEMM's epilogues accumulated
+      if (LNM == LNM_CONSUMER && LN_PROBE != 1) {  // mean / rstd of my row from the totals the producing GEMM's epilogues accumulated
         // fp32 on purpose: ~10 FP64 instructions per thread and tile cost the 1280-deep GEMMs 12 % (tools/ln_fold_probe.py,
         // profiles/r02_ln_fold_probe.txt). E[x^2] - mean^2 in fp32 is good to ~1e-7 * mean^2 / var relative: below the bf16
         // resolution of the inputs themselves for any row bf16 can represent (|mean| / std < 2^8).
@@ -732,7 +736,7 @@ __global__ void __launch_bounds__(320, 1)
             r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + part[j].w);
           }
         }
-        if (p.ln_stats && LN_PROBE != 2) {
+        if (LNM == LNM_CONSUMER && LN_PROBE != 2) {
           tmem_wait_ld();
           const float4* c4 = reinterpret_cast<const float4*>(colsum_s + (c >> 1) * 32);
           const uint64_t rstd2 = pack_f32x2(ln_rstd, ln_rstd), shift2 = pack_f32x2(ln_shift, ln_shift);
@@ -754,14 +758,14 @@ __global__ void __launch_bounds__(320, 1)
           const bool st_next = (c + 2 < BN / 32) && (n_abs + 96 <= p.N);
           if (st_next) epilogue_prefetch_staged(p, res_next, rm, lane, n_abs + 64);
           tmem_wait_ld();
-          epilogue_chunk_staged(p, ac, r, res_cur, bias_s + (c >> 1) * 32, rm, stage, lane, g, n_abs, st_acc);
+          epilogue_chunk_staged<LNM == LNM_PRODUCER>(p, ac, r, res_cur, bias_s + (c >> 1) * 32, rm, stage, lane, g, n_abs, st_acc);
 #pragma unroll
           for (int s4 = 0; s4 < 4; ++s4) res_cur[s4] = res_next[s4];
           st_cur = st_next;
 #else
           epilogue_prefetch_staged(p, res_cur, rm, lane, n_abs);
           tmem_wait_ld();
-          epilogue_chunk_staged(p, ac, r, res_cur, bias_s + (c >> 1) * 32, rm, stage, lane, g, n_abs, st_acc);
+          epilogue_chunk_staged<LNM == LNM_PRODUCER>(p, ac, r, res_cur, bias_s + (c >> 1) * 32, rm, stage, lane, g, n_abs, st_acc);
           st_cur = (c + 2 < BN / 32) && (n_abs + 96 <= p.N);
 #endif
         } else {
@@ -778,7 +782,7 @@ __global__ void __launch_bounds__(320, 1)
       else mbar_arrive(&tempty[as]);
       as ^= 1;
       if (as == 0) aphase ^= 1;
-      if (p.stats_out && seg_mode != SEG_TAIL && valid) {
+      if (LNM == LNM_PRODUCER && seg_mode != SEG_TAIL && valid) {
         // 2^24 fixed point: integer adds commute, so the row totals are the same bits whatever order the tiles finish in
         float s0, s1, q0, q1;
         unpack_f32x2(st_acc[0], s0, s1);
@@ -1102,14 +1106,14 @@ static bool sk_workspace(cudaStream_t stream, float4** ws, unsigned int** flags)
   return true;
 }
 
-template <int BN, int STAGES, bool PAIR>
-static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IGemmParams p, cudaStream_t stream) {
+template <int BN, int STAGES, bool PAIR, int LNM>
+static int launch_igemm_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, IGemmParams p, cudaStream_t stream) {
   using Cfg = IGemmCfg<BN, PAIR>;
   constexpr int smem_bytes = STAGES * Cfg::STAGE_BYTES + 1024 + 256 + 8 * 2048 + 2 * 8 * 512;  // + epilogue transpose / bias / colsum
   static_assert(smem_bytes <= 227 * 1024, "stage count does not fit shared memory");
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, PAIR, LNM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    smem_bytes));
     configured = true;
   }
@@ -1124,9 +1128,27 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, IGemmPar
   if (g_streamk && rem != 0 && total_super > clusters && clusters <= SK_MAX_CLUSTERS &&
       p.ntaps * p.kchunks >= sk_min_kblocks() && sk_workspace(stream, &p.sk_ws, &p.sk_flags))
     p.sk_tiles = clusters + rem;
-  B200_CUDA(launch_pdl(igemm_kernel<BN, STAGES, PAIR>, dim3(2 * clusters), dim3(320), smem_bytes, stream, 2, tmA, tmB,
+  B200_CUDA(launch_pdl(igemm_kernel<BN, STAGES, PAIR, LNM>, dim3(2 * clusters), dim3(320), smem_bytes, stream, 2, tmA, tmB,
                        p));
   return 0;
+}
+
+template <int BN, int STAGES, bool PAIR>
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IGemmParams& p, cudaStream_t stream) {
+  if (p.ln_stats && p.stats_out) {
+    set_error("one GEMM cannot both consume and produce row statistics");
+    return B200MIX_ERR_INVALID;
+  }
+  if (p.ln_stats || p.stats_out) {
+    if constexpr (PAIR) {
+      return p.ln_stats ? launch_igemm_mode<BN, STAGES, true, LNM_CONSUMER>(tmA, tmB, p, stream)
+                        : launch_igemm_mode<BN, STAGES, true, LNM_PRODUCER>(tmA, tmB, p, stream);
+    } else {
+      set_error("the folded-LayerNorm epilogues are built for the CTA-pair kernel only");
+      return B200MIX_ERR_INVALID;
+    }
+  }
+  return launch_igemm_mode<BN, STAGES, PAIR, LNM_NONE>(tmA, tmB, p, stream);
 }
 
 // Test / measurement hook (see b200mix_debug_gemm_pair): 1 = CTA-pair MMA (default), 0 = per-CTA MMA + multicast B.

@@ -137,8 +137,15 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1, co
   const int g = gq, j = jq;
   long long su = 0, sq = 0;
   if (g < groups) {
-    const volatile long long* srcp = partial + (static_cast<long long>(b) * gx * groups + g) * 2;
-    for (int i = j; i < gx; i += per) su += srcp[static_cast<size_t>(i) * groups * 2], sq += srcp[static_cast<size_t>(i) * groups * 2 + 1];
+    // L2 loads (the partials were published with __threadfence + the arrival counter), several in flight: a volatile
+    // loop here serialised ~28 L2 round trips and was half of the kernel's 15 us on the small slices (ncu: SMs active
+    // 49 % of the elapsed cycles, profiles/r02_ncu_full_norm.txt)
+    const longlong2* srcp = reinterpret_cast<const longlong2*>(partial + (static_cast<long long>(b) * gx * groups + g) * 2);
+#pragma unroll 4
+    for (int i = j; i < gx; i += per) {
+      const longlong2 t = __ldcg(srcp + static_cast<size_t>(i) * groups);
+      su += t.x, sq += t.y;
+    }
   }
   red[2 * threadIdx.x] = su, red[2 * threadIdx.x + 1] = sq;
   __syncthreads();
