@@ -275,3 +275,25 @@ def test_streamk_schedule_covers_every_k_block_once():
         assert len(seen) == total * kb
         lens = [sum(b - a for _, a, b in ss) for ss in allsegs]
         assert max(lens) - min(lens) <= 1
+
+
+def test_epilogue_struct_layout_matches_header(tmp_path):
+    """The ctypes mirror of b200mix_epilogue (paddlemix_b200/_lib.py) against what a C compiler makes of include/b200mix.h:
+    same size, same offset for every field (a silent mismatch would shift every epilogue pointer)."""
+    import ctypes
+    import os
+    import subprocess
+
+    from paddlemix_b200._lib import Epilogue
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fields = [f[0] for f in Epilogue._fields_]
+    src = tmp_path / "layout.c"
+    lines = "".join(f'  printf("{f} %zu\\n", offsetof(b200mix_epilogue, {f}));\n' for f in fields)
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "b200mix.h"\nint main(void) {\n'
+                   '  printf("sizeof %zu\\n", sizeof(b200mix_epilogue));\n' + lines + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    assert int(out["sizeof"]) == ctypes.sizeof(Epilogue)
+    for f in fields:
+        assert int(out[f]) == getattr(Epilogue, f).offset, f

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_ops_gpu.py -q -m gpu -p no:cacheprovider -x -k "folded" 2>&1 | tail -3
-for v in main lnp1; do
-  if [ "$v" = main ]; then unset B200MIX_LIB; else export B200MIX_LIB=$PWD/paddlemix_b200/csrc/build/variants/libb200mix_$v.so; fi
+for v in main lnp1 lnp2; do  # variants: tools/build_variant.sh lnp1 -DLN_PROBE=1, lnp2 -DLN_PROBE=2 (skipped when absent)
+  if [ "$v" = main ]; then unset B200MIX_LIB; else export B200MIX_LIB=$PWD/paddlemix_b200/csrc/build/variants/libb200mix_$v.so; [ -f "$B200MIX_LIB" ] || continue; fi
   echo "== $v"; timeout 300 python tools/ln_fold_probe.py 2>&1 | tail -6
 done
 unset B200MIX_LIB
