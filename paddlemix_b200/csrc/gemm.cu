@@ -702,12 +702,13 @@ __global__ void __launch_bounds__(320, 1)
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
       if (seg_mode == SEG_HEAD) {
-        // the partner's partial was published ~a tile ago; a bounded spin turns a scheduling accident (the partner
-        // cluster not resident) into an error instead of a hang
+        // the partner's partial was published ~a tile ago; a bounded spin (2^35 cycles, ~18 s: far beyond any time slice
+        // the context can lose) turns a scheduling accident (the partner cluster never resident) into an error instead
+        // of a hang
         const unsigned int* flag = p.sk_flags + sk_slot;
         const long long t_start = clock64();
         while (ld_acquire_gpu(flag) == 0u) {
-          if (clock64() - t_start > (1ll << 32)) __trap();
+          if (clock64() - t_start > (1ll << 35)) __trap();
         }
       }
 #pragma unroll 1
