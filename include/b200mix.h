@@ -68,7 +68,10 @@ typedef struct b200mix_epilogue {
    * passes ln_stats = that table, and rebuilds mean / rstd of every row in its epilogue:
    *   out[m,n] = rstd[m] * (acc[m,n] - mean[m] * ln_colsum[n]) + bias'[n]     (== Linear(LayerNorm(h)) algebraically;
    * h is not rounded a second time, so the result is closer to the fp32 reference than the two-kernel form).
-   * ln_rms = 1: RMSNorm (no mean term). All NULL / 0 when unused. */
+   * ln_rms = 1: RMSNorm (no mean term). All NULL / 0 when unused.
+   * Range: the int64 totals hold |sum x| and sum x^2 up to 2^63 / 2^24 = 5.5e11 per row (a 1280-wide row of RMS 2e4);
+   * mean / variance are rebuilt in fp32 (E[x^2] - mean^2), accurate to ~1e-7 * mean^2 / var, i.e. below the bf16
+   * resolution of h for every row bf16 can represent. Callers with rows outside that range keep b200mix_layernorm. */
   void* stats_out;
   const void* ln_stats;
   const float* ln_colsum;
